@@ -1,0 +1,222 @@
+/* pprb200.h -- C ABI of libpprb200.so, the B200 (sm_100a) Personalized-PageRank engine.
+ *
+ * This is the drop-in boundary for the hot path of joezie/Personalized-PageRank-Algorithms-on-Neo4j.
+ * The reference has no FFI layer: its operator API is three Java interfaces
+ * (Whole_Graph_Util_Interface, Topk_Util_Interface, Preprocessing_Interface) implemented by one class
+ * per algorithm.  Each entry point below names the reference method it replaces
+ * (J/ = src/main/java/joezie/fora_neo4j/).  The Java classes keep their names and call these through
+ * JNI or Panama; the Python mirror used by the tests binds them with ctypes.
+ *
+ * Conventions
+ *   - every function returns an int32 status: 0 = OK, negative = error (PPR_E_*); the message is
+ *     available from ppr_last_error().  Nothing throws or aborts.
+ *   - handles are opaque, owned by the library until the matching destroy call.
+ *   - host arrays passed in are borrowed for the duration of the call only; output buffers are
+ *     caller-owned and caller-sized.  Pinned buffers from ppr_host_alloc() make the copies faster.
+ *   - vertex ids are "mapped" ids in [0, n): the Neo4j original <-> mapped translation stays on the
+ *     host side, exactly where Graph.toMappedNodeId / toOriginalNodeId sit in the reference.
+ *   - a context is used by one thread at a time (the reference harness is single threaded).
+ *   - there is NO CPU fallback: every query runs CUDA kernels on the context's device and fails with
+ *     PPR_E_CUDA when no device is usable.
+ *   - results are deterministic functions of (graph, arguments, seed) and do not depend on the number
+ *     of walk shards: residues/reserves are accumulated in 2^-62 fixed point with integer atomics
+ *     (DESIGN.md), walks use Philox4x32-10 keyed by (seed, start vertex, walk index).
+ */
+#ifndef PPRB200_H
+#define PPRB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPR_OK 0
+#define PPR_E_INVALID (-1) /* bad argument */
+#define PPR_E_CUDA (-2)    /* CUDA runtime error / no device */
+#define PPR_E_NOMEM (-3)   /* host or device allocation failed */
+#define PPR_E_RANGE (-4)   /* graph exceeds supported ranges (n < 2^31, degree < 2^24, m < 2^40) */
+#define PPR_E_CAPACITY (-5)/* caller buffer too small; required size reported through the count output */
+#define PPR_E_STATE (-6)   /* call sequence error (e.g. export before any query) */
+
+/* flags */
+#define PPR_RESTART_AT_WALK_START 0 /* default: reference behaviour, J/Monte_Carlo.java:87-90 */
+#define PPR_RESTART_AT_SOURCE 1     /* dangling vertices send a walk back to the query source */
+
+#define PPR_FX_ONE (1ull << 62) /* fixed-point scale of the raw uint64 vectors */
+
+typedef struct ppr_ctx ppr_ctx;
+typedef struct ppr_graph ppr_graph;
+typedef struct ppr_pairs ppr_pairs; /* result of the all-pair backward search */
+
+/* Accuracy parameters the reference passes to the algorithm constructors (delta, pfail; min_delta for
+ * FORA top-k).  Algo_Conf derives them from the graph (J/Algo_Conf.java:29-81); a NULL ppr_conf*, or a
+ * field <= 0, selects exactly that derivation: delta = pfail = 1/n; top-k: delta0 = 1/k,
+ * min_delta = 1/n, pfail = 1/n/n/ln(n / k) with integer n / k. */
+typedef struct ppr_conf {
+    double delta;
+    double pfail;
+    double min_delta;
+} ppr_conf;
+
+/* Work and timing counters of the last query (all phases run on the context's stream). */
+typedef struct ppr_stats {
+    int64_t pushes;        /* vertices pushed (V_p) */
+    int64_t edges;         /* edges relaxed (E_p) */
+    int64_t iters;         /* synchronous push iterations */
+    int64_t rounds;        /* rmax-halving rounds (FORA) / delta rounds (FORA top-k) */
+    int64_t walks;         /* random walks executed on this shard */
+    int64_t walks_total;   /* random walks of the whole query (all shards) */
+    int64_t steps;         /* random-walk moves executed on this shard */
+    int64_t walk_sources;  /* vertices that started walks */
+    uint64_t rmax_fx;      /* final push threshold, fixed point */
+    uint64_t rsum_fx;      /* residue mass handed to the walk phase, fixed point */
+    double omega;          /* omega of the query (J/Fora_Whole_Graph.java:87, J/Monte_Carlo.java:145) */
+    float ms_push;         /* CUDA-event time of the push kernel(s) */
+    float ms_walk;         /* CUDA-event time of the walk kernel(s) */
+    float ms_select;       /* CUDA-event time of top-k selection */
+    float ms_total;        /* CUDA-event time of the whole device part of the call */
+    int32_t launches;      /* kernels launched by the call */
+    int32_t reserved;
+} ppr_stats;
+
+/* ---------------------------------------------------------------- lifecycle
+ * Replaces the embedded-database lifecycle of the driver: PPR.createDb / registerShutdownHook /
+ * shutDown (J/PPR.java:35-68).  `device` is the CUDA ordinal (one context per GPU, one process per
+ * GPU in multi-GPU runs). */
+int32_t ppr_init(int32_t device, ppr_ctx** out);
+int32_t ppr_shutdown(ppr_ctx* ctx);
+const char* ppr_last_error(ppr_ctx* ctx); /* ctx may be NULL: last error of a failed ppr_init */
+int32_t ppr_device_info(ppr_ctx* ctx, int32_t* sm_count, int64_t* total_mem, char* name, int32_t name_cap);
+
+/* Tunables that replace the wall-clock push/walk balancer of J/Fora_Whole_Graph.java:35,93-103:
+ * the push keeps halving rmax while (vertices pushed + edges relaxed) < walk_cost * r_sum * omega and
+ * rounds < max_rounds.  Defaults: walk_cost = 32, max_rounds = 64. */
+int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_rounds);
+
+/* Pinned host memory for result buffers (optional). */
+int32_t ppr_host_alloc(ppr_ctx* ctx, int64_t bytes, void** out);
+int32_t ppr_host_free(ppr_ctx* ctx, void* p);
+
+/* ---------------------------------------------------------------- graph export
+ * Replaces PPR.setupAdjMatrix (J/PPR.java:136-152: GraphLoader ... load(HeavyGraphFactory)) and the
+ * Graph accessors used on the hot path (nodeCount J/PPR.java:129, degree, getTarget,
+ * forEachRelationship; call sites in SURVEY.md section 8b).  Input is the canonical CSR of the
+ * topology: row_ptr[n+1] (int64), col_idx[m] (int32 mapped target ids, any order, parallel edges
+ * kept).  The library copies it to the device and builds out-degrees, the packed vertex table, the
+ * CSC and reciprocal degrees there. */
+int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const int64_t* row_ptr, const int32_t* col_idx,
+                         ppr_graph** out);
+int32_t ppr_graph_destroy(ppr_graph* g);
+int64_t ppr_graph_node_count(const ppr_graph* g); /* Graph.nodeCount() */
+int64_t ppr_graph_rel_count(const ppr_graph* g);  /* rel_amount, J/PPR.java:131 */
+/* Copy the device-built CSC back (tests / export): col_ptr[n+1], row_idx[m], sources ascending per column. */
+int32_t ppr_graph_export_csc(ppr_graph* g, int64_t* col_ptr, int32_t* row_idx);
+
+/* ---------------------------------------------------------------- single-source queries
+ * All outputs are dense length-n vectors of doubles unless stated; stats may be NULL. */
+
+/* Forward_Push.computeWholeGraphPPR(src, rmax), J/Forward_Push.java:63-142.  residue_out and rsum_out
+ * may be NULL.  rsum_out receives the residue mass left (getUpdatedRsum, J/Forward_Push.java:252). */
+int32_t ppr_forward_push(ppr_graph* g, int32_t src, double alpha, double rmax, double* reserve_out,
+                         double* residue_out, double* rsum_out, ppr_stats* stats);
+
+/* Monte_Carlo.computeWholeGraphPPR(src, eps), J/Monte_Carlo.java:136-158 (delta = pfail = 1/n,
+ * J/Algo_Conf.java:29-35). */
+int32_t ppr_monte_carlo(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed, const ppr_conf* conf,
+                        double* ppr_out, ppr_stats* stats);
+
+/* Fora_Whole_Graph.computeWholeGraphPPR(src, eps), J/Fora_Whole_Graph.java:82-146 (delta = pfail = 1/n,
+ * J/Algo_Conf.java:45-53). */
+int32_t ppr_fora(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed, int32_t flags,
+                 const ppr_conf* conf, double* ppr_out, ppr_stats* stats);
+
+/* Fora_Topk.computeTopKPPR(src, _, eps) followed by getTopKNodeIds(k), J/Fora_Topk.java:102-184,82-99,
+ * parameters per J/Algo_Conf.java:71-81.  Returns every vertex whose estimate is >= the k-th largest
+ * (ties included, so *count_out may exceed k), sorted by descending estimate, ties by ascending id.
+ * cap is the capacity of ids_out / vals_out; on PPR_E_CAPACITY *count_out holds the needed size. */
+int32_t ppr_fora_topk(ppr_graph* g, int32_t src, double alpha, double eps, int32_t k, uint64_t seed, int32_t flags,
+                      const ppr_conf* conf, int32_t* ids_out, double* vals_out, int32_t cap, int32_t* count_out, ppr_stats* stats);
+
+/* Algo_Util.kth_ppr + retrieveTopK + getTopKNodeIds over an arbitrary dense vector
+ * (J/Algo_Util.java:32-73, J/Forward_Push.java:394-429).  Only positive entries count as present. */
+int32_t ppr_topk(ppr_ctx* ctx, const double* vec, int64_t n, int32_t k, int32_t* ids_out, double* vals_out,
+                 int32_t cap, int32_t* count_out, double* kth_out);
+
+/* Power_Method.computeWholeGraphPPR(src), J/Power_Method.java:44-101 (`iters` synchronous rounds; the
+ * reference uses 100).  Double arithmetic, deterministic pull over the CSC. */
+int32_t ppr_power_iteration(ppr_graph* g, int32_t src, double alpha, int32_t iters, double* out);
+
+/* Throughput path: nq FORA queries back to back, results written to ppr_out[q*n .. (q+1)*n) while
+ * the next query computes.  Query q uses seed + q.  stats_out (nullable) is an array of nq entries. */
+int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq, double alpha, double eps, uint64_t seed,
+                       int32_t flags, const ppr_conf* conf, double* ppr_out, ppr_stats* stats_out);
+
+/* ---------------------------------------------------------------- backward search / all pairs */
+
+/* Backward_Search.backward_search_whole_graph(target), J/Backward_Search.java:38-100: reserve_out[v] =
+ * estimate of pi(v, target). */
+int32_t ppr_backward_search(ppr_graph* g, int32_t target, double alpha, double rmax, double* reserve_out,
+                            ppr_stats* stats);
+
+/* Base_Whole_Graph.preprocessing(threshold, k), J/Base_Whole_Graph.java:58-164, compute part: backward
+ * search from every target in [t_lo, t_hi) (a rank's block in multi-GPU runs), keeping pi(v,t) >=
+ * threshold, grouped by source v.  k < 0 keeps everything with targets ascending; k >= 0 keeps the
+ * entries >= the k-th largest per source, sorted by descending value (ties: ascending target). */
+int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double threshold, int32_t k, int32_t t_lo, int32_t t_hi,
+                               ppr_pairs** out, ppr_stats* stats);
+int64_t ppr_pairs_count(const ppr_pairs* p);
+/* src_ptr[n+1], tgt[count], val[count] (val_fx may be NULL; raw fixed-point values otherwise). */
+int32_t ppr_pairs_export(const ppr_pairs* p, int64_t* src_ptr, int32_t* tgt, double* val, uint64_t* val_fx);
+int32_t ppr_pairs_destroy(ppr_pairs* p);
+
+/* ---------------------------------------------------------------- sharded execution (multi-GPU)
+ * Walks shard over GPUs (one process and one context per GPU, graph replicated).  Each rank runs the
+ * (deterministic) push, then only the walks whose global index falls in
+ * [W*shard/nshards, W*(shard+1)/nshards), and leaves its raw fixed-point partial vector on the
+ * device: rank 0's partial carries the push reserve, the others only walk contributions, so an
+ * integer all-reduce(sum) over ranks (NCCL, ncclUint64 / int64 bit pattern) gives exactly the
+ * single-GPU vector.  ppr_result_devptr exposes the device buffer for that collective;
+ * ppr_result_export converts it to doubles afterwards. */
+int32_t ppr_fora_shard(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed, int32_t flags,
+                       const ppr_conf* conf, int32_t shard, int32_t nshards, ppr_stats* stats);
+int32_t ppr_monte_carlo_shard(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed,
+                              const ppr_conf* conf, int32_t shard, int32_t nshards, ppr_stats* stats);
+/* Device pointer and length (elements) of the raw uint64 result vector of the last query on g. */
+int32_t ppr_result_devptr(ppr_graph* g, uint64_t* devptr_out, int64_t* n_out);
+/* Convert the raw result vector to doubles (after an external all-reduce if sharded).
+ * divisor = 0: value * 2^-62 (push / FORA); divisor > 0: count / divisor (Monte-Carlo omega). */
+int32_t ppr_result_export(ppr_graph* g, double divisor, double* out);
+
+/* ---------------------------------------------------------------- raw state of the last query (parity tests)
+ * Fixed-point vectors exactly as the kernels left them: reserve (or FORA estimate / Monte-Carlo
+ * counts) and residue.  Either pointer may be NULL. */
+int32_t ppr_last_raw(ppr_graph* g, uint64_t* reserve_fx, uint64_t* residue_fx);
+
+/* Stepped forward push for schedule tests: same device code as ppr_forward_push, one synchronous
+ * iteration per call.  begin() seeds the frontier for (src, rmax); each step() returns the frontier
+ * it pushed (ids in frontier_out, unordered; count in *count_out; 0 = converged). */
+int32_t ppr_push_trace_begin(ppr_graph* g, int32_t src, double alpha, double rmax);
+int32_t ppr_push_trace_step(ppr_graph* g, int32_t* frontier_out, int64_t cap, int64_t* count_out);
+
+/* Terminal vertex of walk `j` started at `start` (Monte_Carlo.random_walk / random_walk_no_zero_hop,
+ * J/Monte_Carlo.java:60-133), for `count` consecutive walk indices starting at j0; runs the walk
+ * kernel's device function one walk per thread. */
+int32_t ppr_walk_terminals(ppr_graph* g, int32_t start, int32_t restart, uint64_t j0, int64_t count, uint64_t seed,
+                           uint64_t tag, double alpha, int32_t no_zero_hop, int32_t* terminals_out);
+
+/* ---------------------------------------------------------------- synthetic inputs (bench / tests)
+ * Seeded R-MAT generator (a, b, c; d = 1-a-b-c), `m` directed edges over `n` vertices (n need not be
+ * a power of two: out-of-range endpoints are redrawn), self loops and duplicates kept, optional
+ * random relabelling and symmetrisation (each generated edge also inserted reversed; m counts both).
+ * Host-only (no CUDA), deterministic for a given argument list and independent of thread count.
+ * row_ptr[n+1] and col_idx[m] are caller-allocated; rows come out in ascending target order. */
+int32_t ppr_rmat_generate(int64_t n, int64_t m, double a, double b, double c, uint64_t seed, int32_t permute,
+                          int32_t symmetric, int64_t* row_ptr, int32_t* col_idx);
+
+const char* ppr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPRB200_H */

@@ -1,0 +1,193 @@
+// common.cuh -- shared device helpers and host-side engine structs of libpprb200.so (sm_100a only).
+//
+// Arithmetic contract (DESIGN.md "Fixed point"): residues and reserves are uint64 holding
+// value * 2^62; all accumulation is integer so atomics commute and every schedule gives the same
+// bits.  Reference formulas are cited per kernel (J/ = src/main/java/joezie/fora_neo4j/ of the
+// reference repository).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pprb200.h"
+
+typedef uint64_t u64;
+typedef int64_t i64;
+typedef uint32_t u32;
+typedef int32_t i32;
+typedef unsigned long long ull;
+
+#define FX_ONE (1ull << 62)
+#define FX_INV (1.0 / 4611686018427387904.0)  // 2^-62
+#define FX_SCALE 4611686018427387904.0
+
+// Packed vertex record: (first edge offset << 24) | degree.  One 8-byte load gives both, so a walk
+// step touches one sector of the vertex table and one of the edge array.
+#define VTX_DEG_BITS 24
+#define VTX_DEG_MASK ((1ull << VTX_DEG_BITS) - 1)
+#define VTX_MAX_DEG ((1ll << VTX_DEG_BITS) - 1)
+#define VTX_MAX_EDGES (1ll << 40)
+
+// Forward-push work classes
+#define PUSH_SMALL_MAX 64   // degree <= this: warp-cooperative gather over 32 vertices
+#define PUSH_CHUNK 1024     // larger rows are cut into chunks of this many edges, one warp per chunk
+
+#define PUSH_THREADS 256
+#define WALK_THREADS 256
+
+#define CUDA_TRY(expr)                                                       \
+    do {                                                                     \
+        cudaError_t e__ = (expr);                                            \
+        if (e__ != cudaSuccess) return ctx_fail_cuda(ctx, e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ u64 mulhi64(u64 a, u64 b) { return __umul64hi(a, b); }
+__device__ __forceinline__ u64 vtx_begin(u64 p) { return p >> VTX_DEG_BITS; }
+__device__ __forceinline__ u32 vtx_deg(u64 p) { return (u32)(p & VTX_DEG_MASK); }
+
+// thr(u) of the forward push: J/Forward_Push.java:132 tests r/d >= rmax; d == 0 gives +inf >= rmax for
+// any positive residue, i.e. threshold "one unit".
+__device__ __forceinline__ u64 thr_fwd(u64 rmax_fx, u32 d) {
+    if (d == 0) return 1ull;
+    u64 hi = __umul64hi(rmax_fx, (u64)d);
+    return hi ? ~0ull : rmax_fx * (u64)d;
+}
+
+struct Philox4 { u32 x0, x1, x2, x3; };
+__device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1) {
+    const u32 M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        u32 hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        u32 hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        u32 n0 = hi1 ^ c1 ^ k0;
+        u32 n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o; o.x0 = c0; o.x1 = c1; o.x2 = c2; o.x3 = c3;
+    return o;
+}
+
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+#endif
+
+// ------------------------------------------------------------------------------------------ device-resident control block
+// One per workspace; written by the kernels, read back by the host once per call.
+struct PushCtl {
+    // frontier bookkeeping (index = iteration parity)
+    u32 cnt[2];        // frontier sizes
+    u32 ns[2];         // staged small items
+    u32 nl[2];         // staged large items
+    u32 nchunks[2];    // chunk descriptors
+    u64 dang[2];       // dangling mass headed for the source
+    // work counters
+    u64 reserve_total; // sum of everything moved into reserve by pushes
+    u64 pushes, edges, iters, rounds;
+    u64 rmax_fx;
+    double rmax;
+    // walk preparation
+    u64 rsum_fx;       // sum of (1-alpha) parts handed to walks
+    i64 N;             // (long)(omega * r_sum)
+    u64 total_walks;
+    u32 n_sources;
+    u32 cont;          // balance loop: 1 = run another rmax-halving round
+    u64 steps;         // walk moves executed (this shard)
+    u64 walks_done;    // walks executed (this shard)
+    // radix select
+    u32 sel_count;     // survivors written
+    u32 sel_pos;       // positives seen
+    u64 sel_kth;
+    u32 err;           // device-side error flags
+    u32 src_dangling;  // 1 = the query source has no out-edges (result is {src: 1})
+    u32 err_a;         // error raised during a phase A (kept apart from err so each flag is only read behind a barrier)
+    u32 pad2;
+    u64 pairs;         // all-pair backward search: (v, t) pairs written by the batch
+    u64 pairs_needed;  // ... and the number that qualified (> capacity means the batch must be rerun)
+};
+
+// ------------------------------------------------------------------------------------------ host structs
+struct ppr_ctx {
+    int device;
+    int sm_count;
+    size_t total_mem;
+    std::string name;
+    std::string err;
+    cudaStream_t stream;   // compute
+    cudaStream_t copy;     // result download (batch pipeline)
+    cudaEvent_t ev[8];
+    double walk_cost;
+    int max_rounds;
+};
+
+struct DevGraph {
+    i64 n, m;
+    u64* out_vtx;   // [n] packed (begin<<24 | out-degree)
+    i32* col_idx;   // [m]
+    u32* out_deg;   // [n]
+    u64* in_vtx;    // [n] packed over the CSC
+    i32* row_idx;   // [m]
+    u64* invdeg;    // [n] (2^64-1)/out_deg, 0 for dangling
+};
+
+struct Workspace {
+    i64 n;
+    u64* r;         // residue
+    u64* reserve;   // reserve / result
+    u64* est;       // FORA top-k estimate (push reserve + walk contributions)
+    u32* front[2];  // frontier lists
+    u64* s_pack; u64* s_q;   // staged small items (packed vertex record, per-edge amount)
+    u64* l_pack; u64* l_q;   // staged large items
+    uint2* chunks;  i64 chunk_cap;
+    // walk sources
+    u32* ws_v; u64* ws_begin; u64* ws_inc; u64* ws_rem;
+    u64* blk_a; u64* blk_b; u64* blk_c;  // per-CTA partials of the in-kernel scans
+    double* out_f64;   // conversion buffer for downloads
+    u32* hist;         // radix-select histograms
+    i32* sel_ids; u64* sel_vals; i64 sel_cap;
+    PushCtl* ctl;      // device
+    PushCtl* ctl_host; // pinned mirror
+    int coop_blocks;   // grid size of the cooperative kernels
+};
+
+struct ppr_graph {
+    ppr_ctx* ctx;
+    DevGraph d;
+    Workspace ws[2];    // two workspaces: batch pipeline overlaps download of query i with query i+1
+    int last_ws;        // workspace holding the last result
+    int last_kind;      // 0 none, 1 reserve vector, 2 est vector
+    std::vector<i64> h_rowptr_dummy;
+    // stepped push (trace) state
+    bool trace_active; int trace_parity; i32 trace_src; u64 trace_alpha_q64;
+};
+
+struct ppr_pairs {
+    i64 n;
+    std::vector<i64> src_ptr;
+    std::vector<i32> tgt;
+    std::vector<u64> val;
+};
+
+int32_t ctx_fail(ppr_ctx* ctx, int32_t code, const std::string& msg);
+int32_t ctx_fail_cuda(ppr_ctx* ctx, cudaError_t e, const char* expr, const char* file, int line);
+
+// host-side parameter helpers (restated from J/Algo_Conf.java and the algorithm classes; see api.cu)
+static inline u64 h_alpha_q64(double alpha) { return (u64)__builtin_ldexp(alpha, 64); }
+static inline u64 h_stop_threshold(double alpha) { return (u64)__builtin_ceil(__builtin_ldexp(alpha, 53)); }
+static inline u64 h_walk_key(u64 seed, u64 tag) { return seed + tag * 0x9E3779B97F4A7C15ull; }
+static inline u64 h_rmax_to_fx(double rmax) {
+    double x = rmax * FX_SCALE;
+    if (!(x >= 1.0)) return 1;
+    if (x >= 18446744073709551615.0) return ~0ull;
+    return (u64)x;
+}

@@ -1,0 +1,1071 @@
+// pprb200.cu -- host side of libpprb200.so: contexts, graph export, kernel launches, the C ABI.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (see Makefile).  There is no CPU path:
+// every entry point that computes launches the kernels in push.cuh / walk.cuh / select.cuh /
+// backward.cuh on the context's device and reports PPR_E_CUDA when that is impossible.
+//
+// Parameter derivations restate J/Algo_Conf.java:29-81, J/Fora_Whole_Graph.java:86-87,
+// J/Fora_Topk.java:109-125 and J/Monte_Carlo.java:145 (J/ = src/main/java/joezie/fora_neo4j/).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "backward.cuh"
+#include "common.cuh"
+#include "push.cuh"
+#include "select.cuh"
+#include "walk.cuh"
+
+static thread_local std::string g_init_err;
+
+int32_t ctx_fail(ppr_ctx* ctx, int32_t code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_init_err = msg;
+    return code;
+}
+int32_t ctx_fail_cuda(ppr_ctx* ctx, cudaError_t e, const char* expr, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, expr);
+    cudaGetLastError();
+    return ctx_fail(ctx, e == cudaErrorMemoryAllocation ? PPR_E_NOMEM : PPR_E_CUDA, buf);
+}
+
+// ============================================================================================= graph build kernels
+__global__ void k_build_vtx(const i64* __restrict__ ptr, u64* __restrict__ vtx, u32* __restrict__ deg, u64* __restrict__ invdeg,
+                            i64 n) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    for (i64 v = gtid; v < n; v += gsize) {
+        i64 b = ptr[v], e = ptr[v + 1];
+        u64 d = (u64)(e - b);
+        vtx[v] = ((u64)b << VTX_DEG_BITS) | d;
+        if (deg) deg[v] = (u32)d;
+        if (invdeg) invdeg[v] = d ? ~0ull / d : 0ull;
+    }
+}
+
+// ============================================================================================= context
+extern "C" const char* ppr_version(void) { return "pprb200 0.1 (sm_100a)"; }
+
+extern "C" int32_t ppr_init(int32_t device, ppr_ctx** out) {
+    if (!out) return ctx_fail(nullptr, PPR_E_INVALID, "ppr_init: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return ctx_fail(nullptr, PPR_E_CUDA, std::string("ppr_init: no CUDA device (") + cudaGetErrorString(e) +
+                                                  "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return ctx_fail(nullptr, PPR_E_INVALID, "ppr_init: device ordinal out of range");
+    ppr_ctx* ctx = new (std::nothrow) ppr_ctx();
+    if (!ctx) return ctx_fail(nullptr, PPR_E_NOMEM, "ppr_init: host allocation failed");
+    ctx->device = device;
+    ctx->walk_cost = 32.0;
+    ctx->max_rounds = 64;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        delete ctx;
+        return ctx_fail_cuda(nullptr, e, "cudaSetDevice/cudaGetDeviceProperties", __FILE__, __LINE__);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->total_mem = prop.totalGlobalMem;
+    ctx->name = prop.name;
+    if (!prop.cooperativeLaunch) { delete ctx; return ctx_fail(nullptr, PPR_E_CUDA, "device lacks cooperative launch"); }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return ctx_fail_cuda(nullptr, e, "cudaStreamCreate", __FILE__, __LINE__);
+    }
+    for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
+    *out = ctx;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_shutdown(ppr_ctx* ctx) {
+    if (!ctx) return PPR_E_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy);
+    delete ctx;
+    return PPR_OK;
+}
+
+extern "C" const char* ppr_last_error(ppr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
+
+extern "C" int32_t ppr_device_info(ppr_ctx* ctx, int32_t* sm_count, int64_t* total_mem, char* name, int32_t name_cap) {
+    if (!ctx) return PPR_E_INVALID;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (total_mem) *total_mem = (int64_t)ctx->total_mem;
+    if (name && name_cap > 0) { strncpy(name, ctx->name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_rounds) {
+    if (!ctx) return PPR_E_INVALID;
+    if (!(walk_cost >= 0) || max_rounds < 1) return ctx_fail(ctx, PPR_E_INVALID, "ppr_set_balance: walk_cost >= 0, max_rounds >= 1");
+    ctx->walk_cost = walk_cost;
+    ctx->max_rounds = max_rounds;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_host_alloc(ppr_ctx* ctx, int64_t bytes, void** out) {
+    if (!ctx || !out || bytes < 0) return PPR_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+    return PPR_OK;
+}
+extern "C" int32_t ppr_host_free(ppr_ctx* ctx, void* p) {
+    if (!ctx) return PPR_E_INVALID;
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return PPR_OK;
+}
+
+// ============================================================================================= workspace
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
+
+static void ws_free(Workspace& w) {
+    cudaFree(w.r); cudaFree(w.reserve); cudaFree(w.est); cudaFree(w.front[0]); cudaFree(w.front[1]);
+    cudaFree(w.s_pack); cudaFree(w.s_q); cudaFree(w.l_pack); cudaFree(w.l_q); cudaFree(w.chunks);
+    cudaFree(w.ws_v); cudaFree(w.ws_begin); cudaFree(w.ws_inc); cudaFree(w.ws_rem);
+    cudaFree(w.blk_a); cudaFree(w.blk_b); cudaFree(w.blk_c); cudaFree(w.out_f64); cudaFree(w.hist);
+    cudaFree(w.sel_ids); cudaFree(w.sel_vals); cudaFree(w.ctl);
+    if (w.ctl_host) cudaFreeHost(w.ctl_host);
+    memset(&w, 0, sizeof w);
+}
+
+static int32_t ws_alloc(ppr_ctx* ctx, Workspace& w, i64 n, i64 chunk_cap) {
+    memset(&w, 0, sizeof w);
+    w.n = n;
+    w.chunk_cap = chunk_cap;
+    size_t N = (size_t)n;
+    CUDA_TRY(dalloc(&w.r, N)); CUDA_TRY(dalloc(&w.reserve, N)); CUDA_TRY(dalloc(&w.est, N));
+    CUDA_TRY(dalloc(&w.front[0], N)); CUDA_TRY(dalloc(&w.front[1], N));
+    CUDA_TRY(dalloc(&w.s_pack, N)); CUDA_TRY(dalloc(&w.s_q, N)); CUDA_TRY(dalloc(&w.l_pack, N)); CUDA_TRY(dalloc(&w.l_q, N));
+    CUDA_TRY(dalloc(&w.chunks, (size_t)chunk_cap));
+    CUDA_TRY(dalloc(&w.ws_v, N)); CUDA_TRY(dalloc(&w.ws_begin, N + 64)); CUDA_TRY(dalloc(&w.ws_inc, N)); CUDA_TRY(dalloc(&w.ws_rem, N));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_push_query, PUSH_THREADS, 0));
+    int occ2 = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_topk_select, SEL_THREADS, 0));
+    int occ3 = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_bwd_batch, PUSH_THREADS, 0));
+    occ = std::min(occ, std::min(occ2, occ3));
+    if (occ < 1) return ctx_fail(ctx, PPR_E_CUDA, "cooperative kernels do not fit on an SM");
+    w.coop_blocks = ctx->sm_count * std::min(occ, 4);
+    CUDA_TRY(dalloc(&w.blk_a, (size_t)w.coop_blocks)); CUDA_TRY(dalloc(&w.blk_b, (size_t)w.coop_blocks));
+    CUDA_TRY(dalloc(&w.blk_c, (size_t)w.coop_blocks));
+    CUDA_TRY(dalloc(&w.out_f64, N));
+    CUDA_TRY(dalloc(&w.hist, (size_t)9 * 256));
+    w.sel_cap = std::min<i64>(n, (i64)1 << 22);
+    CUDA_TRY(dalloc(&w.sel_ids, (size_t)w.sel_cap)); CUDA_TRY(dalloc(&w.sel_vals, (size_t)w.sel_cap));
+    CUDA_TRY(dalloc(&w.ctl, 1));
+    CUDA_TRY(cudaMemset(w.ctl, 0, sizeof(PushCtl)));
+    CUDA_TRY(cudaHostAlloc((void**)&w.ctl_host, sizeof(PushCtl), cudaHostAllocDefault));
+    memset(w.ctl_host, 0, sizeof(PushCtl));
+    return PPR_OK;
+}
+
+// ============================================================================================= backward workspace
+struct BwdWorkspace {
+    i32 T; i64 n;
+    u64* r; u64* reserve; u64* front[2]; i64 front_cap;
+    u64* s_pack; u64* s_y; u32* s_t; u64* l_pack; u64* l_y; u32* l_t;
+    uint2* chunks; i64 chunk_cap;
+    u32* out_v; u32* out_t; u64* out_val; i64 out_cap;
+};
+static void bws_free(BwdWorkspace& b) {
+    cudaFree(b.r); cudaFree(b.reserve); cudaFree(b.front[0]); cudaFree(b.front[1]);
+    cudaFree(b.s_pack); cudaFree(b.s_y); cudaFree(b.s_t); cudaFree(b.l_pack); cudaFree(b.l_y); cudaFree(b.l_t);
+    cudaFree(b.chunks); cudaFree(b.out_v); cudaFree(b.out_t); cudaFree(b.out_val);
+    memset(&b, 0, sizeof b);
+}
+static int32_t bws_alloc(ppr_ctx* ctx, BwdWorkspace& b, i32 T, i64 n) {
+    memset(&b, 0, sizeof b);
+    b.T = T; b.n = n;
+    size_t tn = (size_t)T * (size_t)n;
+    b.front_cap = (i64)std::min<size_t>(tn, (size_t)1 << 24);
+    b.chunk_cap = (i64)std::min<size_t>(tn, (size_t)1 << 24);
+    b.out_cap = (i64)std::min<size_t>(tn, (size_t)1 << 25);
+    CUDA_TRY(dalloc(&b.r, tn)); CUDA_TRY(dalloc(&b.reserve, tn));
+    CUDA_TRY(dalloc(&b.front[0], (size_t)b.front_cap)); CUDA_TRY(dalloc(&b.front[1], (size_t)b.front_cap));
+    CUDA_TRY(dalloc(&b.s_pack, (size_t)b.front_cap)); CUDA_TRY(dalloc(&b.s_y, (size_t)b.front_cap)); CUDA_TRY(dalloc(&b.s_t, (size_t)b.front_cap));
+    CUDA_TRY(dalloc(&b.l_pack, (size_t)b.front_cap)); CUDA_TRY(dalloc(&b.l_y, (size_t)b.front_cap)); CUDA_TRY(dalloc(&b.l_t, (size_t)b.front_cap));
+    CUDA_TRY(dalloc(&b.chunks, (size_t)b.chunk_cap));
+    CUDA_TRY(dalloc(&b.out_v, (size_t)b.out_cap)); CUDA_TRY(dalloc(&b.out_t, (size_t)b.out_cap)); CUDA_TRY(dalloc(&b.out_val, (size_t)b.out_cap));
+    return PPR_OK;
+}
+
+// ============================================================================================= graph
+struct GraphExtra {  // host-side bookkeeping kept beside ppr_graph
+    bool ws1_ready;
+    BwdWorkspace bws; bool bws_ready;
+    int walk_blocks;
+    double last_divisor;
+};
+static std::vector<std::pair<ppr_graph*, GraphExtra*>> g_extras;
+static GraphExtra* extra_of(ppr_graph* g) {
+    for (auto& p : g_extras) if (p.first == g) return p.second;
+    return nullptr;
+}
+
+extern "C" int32_t ppr_graph_destroy(ppr_graph* g) {
+    if (!g) return PPR_E_INVALID;
+    ppr_ctx* ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy);
+    GraphExtra* x = extra_of(g);
+    ws_free(g->ws[0]);
+    if (x && x->ws1_ready) ws_free(g->ws[1]);
+    if (x && x->bws_ready) bws_free(x->bws);
+    cudaFree(g->d.out_vtx); cudaFree(g->d.col_idx); cudaFree(g->d.out_deg);
+    cudaFree(g->d.in_vtx); cudaFree(g->d.row_idx); cudaFree(g->d.invdeg);
+    for (size_t i = 0; i < g_extras.size(); i++) if (g_extras[i].first == g) { delete g_extras[i].second; g_extras.erase(g_extras.begin() + i); break; }
+    delete g;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const int64_t* row_ptr, const int32_t* col_idx,
+                                    ppr_graph** out) {
+    if (!ctx) return PPR_E_INVALID;
+    if (!out || !row_ptr || (m > 0 && !col_idx)) return ctx_fail(ctx, PPR_E_INVALID, "ppr_graph_create: NULL argument");
+    *out = nullptr;
+    if (n < 1 || n > 0x7fffffffll) return ctx_fail(ctx, PPR_E_RANGE, "ppr_graph_create: need 1 <= n < 2^31");
+    if (m < 0 || m >= VTX_MAX_EDGES) return ctx_fail(ctx, PPR_E_RANGE, "ppr_graph_create: need 0 <= m < 2^40");
+    if (row_ptr[0] != 0 || row_ptr[n] != m) return ctx_fail(ctx, PPR_E_INVALID, "ppr_graph_create: row_ptr[0] != 0 or row_ptr[n] != m");
+    i64 chunk_cap = 1;
+    for (i64 v = 0; v < n; v++) {
+        i64 d = row_ptr[v + 1] - row_ptr[v];
+        if (d < 0) return ctx_fail(ctx, PPR_E_INVALID, "ppr_graph_create: row_ptr not monotone");
+        if (d > VTX_MAX_DEG) return ctx_fail(ctx, PPR_E_RANGE, "ppr_graph_create: out-degree >= 2^24");
+        if (d > PUSH_SMALL_MAX) chunk_cap += (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
+    }
+    // CSC on the host: stable counting sort, sources ascend inside a column
+    std::vector<i64> cp;
+    std::vector<i32> ri;
+    try { cp.assign((size_t)n + 1, 0); ri.resize((size_t)m); } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed"); }
+    for (i64 e = 0; e < m; e++) {
+        i32 c = col_idx[e];
+        if (c < 0 || c >= n) return ctx_fail(ctx, PPR_E_INVALID, "ppr_graph_create: col_idx out of range");
+        cp[(size_t)c + 1]++;
+    }
+    for (i64 v = 0; v < n; v++) {
+        if (cp[v + 1] > VTX_MAX_DEG) return ctx_fail(ctx, PPR_E_RANGE, "ppr_graph_create: in-degree >= 2^24");
+        cp[v + 1] += cp[v];
+    }
+    {
+        std::vector<i64> pos(cp.begin(), cp.end() - 1);
+        for (i64 v = 0; v < n; v++)
+            for (i64 e = row_ptr[v]; e < row_ptr[v + 1]; e++) ri[(size_t)pos[col_idx[e]]++] = (i32)v;
+    }
+
+    cudaSetDevice(ctx->device);
+    ppr_graph* g = new (std::nothrow) ppr_graph();
+    GraphExtra* x = new (std::nothrow) GraphExtra();
+    if (!g || !x) { delete g; delete x; return ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed"); }
+    memset(&g->d, 0, sizeof g->d); memset(g->ws, 0, sizeof g->ws);
+    g->ctx = ctx; g->last_ws = 0; g->last_kind = 0; g->trace_active = false;
+    memset(x, 0, sizeof *x);
+    g_extras.push_back(std::make_pair(g, x));
+    g->d.n = n; g->d.m = m;
+    i64* d_ptr = nullptr;
+    int32_t rc = PPR_OK;
+    auto fail = [&](int32_t code) { cudaFree(d_ptr); ppr_graph_destroy(g); return code; };
+#define G_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail(ctx_fail_cuda(ctx, e__, #expr, __FILE__, __LINE__)); } while (0)
+    G_TRY(dalloc(&g->d.out_vtx, (size_t)n)); G_TRY(dalloc(&g->d.out_deg, (size_t)n)); G_TRY(dalloc(&g->d.invdeg, (size_t)n));
+    G_TRY(dalloc(&g->d.in_vtx, (size_t)n)); G_TRY(dalloc(&g->d.col_idx, (size_t)m)); G_TRY(dalloc(&g->d.row_idx, (size_t)m));
+    G_TRY(dalloc(&d_ptr, (size_t)n + 1));
+    int blocks = ctx->sm_count * 8;
+    G_TRY(cudaMemcpyAsync(d_ptr, row_ptr, ((size_t)n + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
+    k_build_vtx<<<blocks, 256, 0, ctx->stream>>>(d_ptr, g->d.out_vtx, g->d.out_deg, g->d.invdeg, n);
+    G_TRY(cudaGetLastError());
+    G_TRY(cudaStreamSynchronize(ctx->stream));
+    G_TRY(cudaMemcpyAsync(d_ptr, cp.data(), ((size_t)n + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
+    k_build_vtx<<<blocks, 256, 0, ctx->stream>>>(d_ptr, g->d.in_vtx, nullptr, nullptr, n);
+    G_TRY(cudaGetLastError());
+    if (m > 0) {
+        G_TRY(cudaMemcpyAsync(g->d.col_idx, col_idx, (size_t)m * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
+        G_TRY(cudaMemcpyAsync(g->d.row_idx, ri.data(), (size_t)m * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    G_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_ptr); d_ptr = nullptr;
+#undef G_TRY
+    rc = ws_alloc(ctx, g->ws[0], n, chunk_cap);
+    if (rc != PPR_OK) { ppr_graph_destroy(g); return rc; }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk, WALK_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+    x->walk_blocks = ctx->sm_count * occ;
+    *out = g;
+    return PPR_OK;
+}
+
+extern "C" int64_t ppr_graph_node_count(const ppr_graph* g) { return g ? g->d.n : -1; }
+extern "C" int64_t ppr_graph_rel_count(const ppr_graph* g) { return g ? g->d.m : -1; }
+
+__global__ void k_unpack_ptr(const u64* __restrict__ vtx, i64* __restrict__ ptr, i64 n, i64 m) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    for (i64 v = gtid; v < n; v += gsize) ptr[v] = (i64)vtx_begin(vtx[v]);
+    if (gtid == 0) ptr[n] = m;
+}
+extern "C" int32_t ppr_graph_export_csc(ppr_graph* g, int64_t* col_ptr, int32_t* row_idx) {
+    if (!g || !col_ptr || !row_idx) return PPR_E_INVALID;
+    ppr_ctx* ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    i64* d_ptr = nullptr;
+    CUDA_TRY(dalloc(&d_ptr, (size_t)g->d.n + 1));
+    k_unpack_ptr<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(g->d.in_vtx, d_ptr, g->d.n, g->d.m);
+    cudaError_t e = cudaMemcpyAsync(col_ptr, d_ptr, ((size_t)g->d.n + 1) * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && g->d.m) e = cudaMemcpyAsync(row_idx, g->d.row_idx, (size_t)g->d.m * sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_ptr);
+    CUDA_TRY(e);
+    return PPR_OK;
+}
+
+// ============================================================================================= launch helpers
+static void fill_push_args(PushArgs& A, ppr_graph* g, Workspace& w) {
+    memset(&A, 0, sizeof A);
+    A.n = g->d.n; A.out_vtx = g->d.out_vtx; A.col_idx = g->d.col_idx; A.out_deg = g->d.out_deg;
+    A.r = w.r; A.reserve = w.reserve; A.est = w.est; A.front[0] = w.front[0]; A.front[1] = w.front[1];
+    A.s_pack = w.s_pack; A.s_q = w.s_q; A.l_pack = w.l_pack; A.l_q = w.l_q; A.chunks = w.chunks;
+    A.ws_v = w.ws_v; A.ws_begin = w.ws_begin; A.ws_inc = w.ws_inc; A.ws_rem = w.ws_rem;
+    A.blk_a = w.blk_a; A.blk_b = w.blk_b; A.ctl = w.ctl;
+    A.prep_adds_push_part = 1;
+}
+
+static cudaError_t launch_push(ppr_ctx* ctx, Workspace& w, PushArgs& A) {
+    void* args[] = {&A};
+    return cudaLaunchCooperativeKernel((const void*)k_push_query, dim3(w.coop_blocks), dim3(PUSH_THREADS), args, 0, ctx->stream);
+}
+
+static cudaError_t launch_walk(ppr_ctx* ctx, ppr_graph* g, Workspace& w, u64* target, u64 seed, u64 tag, double alpha, i32 src,
+                               int restart_at_source, int no_zero_hop, u64 shard, u64 nshards) {
+    WalkArgs W;
+    memset(&W, 0, sizeof W);
+    W.out_vtx = g->d.out_vtx; W.col_idx = g->d.col_idx; W.ws_v = w.ws_v; W.ws_begin = w.ws_begin; W.ws_inc = w.ws_inc;
+    W.ws_rem = w.ws_rem; W.target = target; W.ctl = w.ctl; W.shard = shard; W.nshards = nshards;
+    u64 key = h_walk_key(seed, tag);
+    W.k0 = (u32)key; W.k1 = (u32)(key >> 32);
+    W.tstop = h_stop_threshold(alpha);
+    W.src = src; W.restart_at_source = restart_at_source; W.no_zero_hop = no_zero_hop;
+    k_walk<<<extra_of(g)->walk_blocks, WALK_THREADS, 0, ctx->stream>>>(W);
+    return cudaGetLastError();
+}
+
+static void stats_from_ctl(ppr_stats* st, const PushCtl* c, double omega) {
+    if (!st) return;
+    memset(st, 0, sizeof *st);
+    st->pushes = (i64)c->pushes; st->edges = (i64)c->edges; st->iters = (i64)c->iters; st->rounds = (i64)c->rounds;
+    st->walks = (i64)c->walks_done; st->walks_total = (i64)c->total_walks; st->steps = (i64)c->steps;
+    st->walk_sources = (i64)c->n_sources; st->rmax_fx = c->rmax_fx; st->rsum_fx = c->rsum_fx; st->omega = omega;
+}
+
+static int32_t check_query(ppr_graph* g, i32 v, double alpha, const char* who) {
+    if (!g) return PPR_E_INVALID;
+    if (v < 0 || v >= g->d.n) return ctx_fail(g->ctx, PPR_E_INVALID, std::string(who) + ": vertex id out of range");
+    if (!(alpha > 0.0 && alpha < 1.0)) return ctx_fail(g->ctx, PPR_E_INVALID, std::string(who) + ": alpha must be in (0, 1)");
+    return PPR_OK;
+}
+
+static int32_t export_vec(ppr_graph* g, Workspace& w, const u64* src, double divisor, double* out, cudaStream_t s) {
+    ppr_ctx* ctx = g->ctx;
+    k_export_f64<<<ctx->sm_count * 8, 256, 0, s>>>(src, w.out_f64, g->d.n, divisor);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, w.out_f64, (size_t)g->d.n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return PPR_OK;
+}
+
+static int32_t read_ctl(ppr_graph* g, Workspace& w) {
+    ppr_ctx* ctx = g->ctx;
+    CUDA_TRY(cudaMemcpyAsync(w.ctl_host, w.ctl, sizeof(PushCtl), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PPR_OK;
+}
+
+struct ForaParams { double delta, pfail, L, rmax, omega; };
+// J/Algo_Conf.java:45-53 and J/Fora_Whole_Graph.java:86-87
+static ForaParams fora_params(i64 n, i64 m, double alpha, double eps, const ppr_conf* conf) {
+    ForaParams p;
+    p.delta = 1.0 / (double)n; p.pfail = 1.0 / (double)n;
+    if (conf && conf->delta > 0) p.delta = conf->delta;
+    if (conf && conf->pfail > 0) p.pfail = conf->pfail;
+    p.L = std::log(2.0 / p.pfail);
+    p.rmax = eps * std::sqrt(p.delta / 3.0 / (double)m / p.L) / (1.0 - alpha);
+    p.omega = (eps + 2.0) * p.L / eps / eps / p.delta;
+    return p;
+}
+
+// ============================================================================================= forward push
+extern "C" int32_t ppr_forward_push(ppr_graph* g, int32_t src, double alpha, double rmax, double* reserve_out,
+                                    double* residue_out, double* rsum_out, ppr_stats* stats) {
+    int32_t rc = check_query(g, src, alpha, "ppr_forward_push");
+    if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    if (!(rmax > 0)) return ctx_fail(ctx, PPR_E_INVALID, "ppr_forward_push: rmax must be > 0");
+    cudaSetDevice(ctx->device);
+    Workspace& w = g->ws[0];
+    g->trace_active = false;
+    PushArgs A;
+    fill_push_args(A, g, w);
+    A.src = src; A.alpha_q64 = h_alpha_q64(alpha); A.alpha = alpha; A.rmax0 = rmax; A.mode = PMODE_PUSH; A.init = 1;
+    A.max_rounds = 1;
+    CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CUDA_TRY(launch_push(ctx, w, A));
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    int launches = 1;
+    if (reserve_out) { rc = export_vec(g, w, w.reserve, 0.0, reserve_out, ctx->stream); if (rc) return rc; launches++; }
+    if (residue_out) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // out_f64 is reused
+        rc = export_vec(g, w, w.r, 0.0, residue_out, ctx->stream); if (rc) return rc; launches++;
+    }
+    rc = read_ctl(g, w); if (rc) return rc;
+    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0;
+    if (rsum_out) *rsum_out = (double)(FX_ONE - w.ctl_host->reserve_total) * FX_INV;
+    if (stats) {
+        stats_from_ctl(stats, w.ctl_host, 0.0);
+        cudaEventElapsedTime(&stats->ms_push, ctx->ev[0], ctx->ev[1]);
+        stats->ms_total = stats->ms_push; stats->launches = launches;
+        stats->rsum_fx = FX_ONE - w.ctl_host->reserve_total;
+    }
+    return PPR_OK;
+}
+
+// ============================================================================================= FORA
+static int32_t fora_launch(ppr_graph* g, Workspace& w, i32 src, double alpha, double eps, u64 seed, int flags,
+                           const ppr_conf* conf, i32 shard, i32 nshards, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2, double* omega_out) {
+    ppr_ctx* ctx = g->ctx;
+    ForaParams p = fora_params(g->d.n, g->d.m, alpha, eps, conf);
+    PushArgs A;
+    fill_push_args(A, g, w);
+    A.src = src; A.alpha_q64 = h_alpha_q64(alpha); A.alpha = alpha; A.omega = p.omega; A.walk_cost = ctx->walk_cost;
+    A.rmax0 = p.rmax; A.max_rounds = ctx->max_rounds; A.mode = PMODE_FORA; A.init = 1;
+    A.zero_reserve_after_push = shard != 0; A.prep_adds_push_part = shard == 0;
+    if (omega_out) *omega_out = p.omega;
+    if (e0) CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    CUDA_TRY(launch_push(ctx, w, A));
+    if (e1) CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(launch_walk(ctx, g, w, w.reserve, seed, 0, alpha, src, (flags & PPR_RESTART_AT_SOURCE) ? 1 : 0, 1, (u64)shard, (u64)nshards));
+    if (e2) CUDA_TRY(cudaEventRecord(e2, ctx->stream));
+    return PPR_OK;
+}
+
+static int32_t check_fora(ppr_graph* g, i32 src, double alpha, double eps, i32 shard, i32 nshards, const char* who) {
+    int32_t rc = check_query(g, src, alpha, who);
+    if (rc) return rc;
+    if (!(eps > 0)) return ctx_fail(g->ctx, PPR_E_INVALID, std::string(who) + ": eps must be > 0");
+    if (nshards < 1 || shard < 0 || shard >= nshards) return ctx_fail(g->ctx, PPR_E_INVALID, std::string(who) + ": bad shard");
+    if (g->d.m < 1) return ctx_fail(g->ctx, PPR_E_INVALID, std::string(who) + ": graph has no edges");
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_fora_shard(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed, int32_t flags,
+                                  const ppr_conf* conf, int32_t shard, int32_t nshards, ppr_stats* stats) {
+    int32_t rc = check_fora(g, src, alpha, eps, shard, nshards, "ppr_fora");
+    if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    Workspace& w = g->ws[0];
+    g->trace_active = false;
+    double omega = 0;
+    rc = fora_launch(g, w, src, alpha, eps, seed, flags, conf, shard, nshards, ctx->ev[0], ctx->ev[1], ctx->ev[2], &omega);
+    if (rc) return rc;
+    rc = read_ctl(g, w); if (rc) return rc;
+    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0;
+    if (stats) {
+        stats_from_ctl(stats, w.ctl_host, omega);
+        cudaEventElapsedTime(&stats->ms_push, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&stats->ms_walk, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&stats->ms_total, ctx->ev[0], ctx->ev[2]);
+        stats->launches = 2;
+    }
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_fora(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed, int32_t flags,
+                            const ppr_conf* conf, double* ppr_out, ppr_stats* stats) {
+    if (g && !ppr_out) return ctx_fail(g->ctx, PPR_E_INVALID, "ppr_fora: ppr_out is NULL");
+    int32_t rc = ppr_fora_shard(g, src, alpha, eps, seed, flags, conf, 0, 1, stats);
+    if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    rc = export_vec(g, g->ws[0], g->ws[0].reserve, 0.0, ppr_out, ctx->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) stats->launches += 1;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq, double alpha, double eps, uint64_t seed,
+                                  int32_t flags, const ppr_conf* conf, double* ppr_out, ppr_stats* stats_out) {
+    if (!g) return PPR_E_INVALID;
+    ppr_ctx* ctx = g->ctx;
+    if (!srcs || !ppr_out || nq < 0) return ctx_fail(ctx, PPR_E_INVALID, "ppr_fora_batch: NULL argument");
+    for (int q = 0; q < nq; q++) { int32_t rc = check_fora(g, srcs[q], alpha, eps, 0, 1, "ppr_fora_batch"); if (rc) return rc; }
+    cudaSetDevice(ctx->device);
+    GraphExtra* x = extra_of(g);
+    if (!x->ws1_ready) {
+        int32_t rc = ws_alloc(ctx, g->ws[1], g->d.n, g->ws[0].chunk_cap);
+        if (rc) { ws_free(g->ws[1]); return rc; }
+        x->ws1_ready = true;
+    }
+    g->trace_active = false;
+    const i64 n = g->d.n;
+    // per-query events and control-block snapshots
+    std::vector<cudaEvent_t> ev((size_t)nq * 4);
+    for (auto& e : ev) cudaEventCreate(&e);
+    PushCtl* snaps = nullptr;
+    cudaError_t me = cudaHostAlloc((void**)&snaps, std::max<size_t>(1, (size_t)nq) * sizeof(PushCtl), cudaHostAllocDefault);
+    std::vector<double> omegas((size_t)nq, 0.0);
+    int32_t rc = PPR_OK;
+    auto cleanup = [&]() { for (auto& e : ev) cudaEventDestroy(e); if (snaps) cudaFreeHost(snaps); };
+    if (me != cudaSuccess) { cleanup(); return ctx_fail_cuda(ctx, me, "cudaHostAlloc", __FILE__, __LINE__); }
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    cudaEventCreateWithFlags(&copied[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&copied[1], cudaEventDisableTiming);
+    bool used[2] = {false, false};
+    auto issue_copy = [&](int q) -> cudaError_t {
+        // download of query q on the copy stream, overlapping the kernels of query q+1
+        Workspace& w = g->ws[q & 1];
+        cudaError_t e = cudaStreamWaitEvent(ctx->copy, ev[(size_t)q * 4 + 3], 0);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(ppr_out + (size_t)q * n, w.out_f64, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(copied[q & 1], ctx->copy);
+    };
+    for (int q = 0; q < nq && rc == PPR_OK; q++) {
+        Workspace& w = g->ws[q & 1];
+        cudaEvent_t* e = &ev[(size_t)q * 4];
+        if (used[q & 1]) cudaStreamWaitEvent(ctx->stream, copied[q & 1], 0);  // out_f64 of this workspace is free again
+        rc = fora_launch(g, w, srcs[q], alpha, eps, seed + (u64)q, flags, conf, 0, 1, e[0], e[1], e[2], &omegas[q]);
+        if (rc) break;
+        k_export_f64<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(w.reserve, w.out_f64, n, 0.0);
+        cudaMemcpyAsync(&snaps[q], w.ctl, sizeof(PushCtl), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(e[3], ctx->stream);
+        used[q & 1] = true;
+        if (q > 0) { cudaError_t ce = issue_copy(q - 1); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, "batch download", __FILE__, __LINE__); }
+    }
+    if (rc == PPR_OK && nq > 0) { cudaError_t ce = issue_copy(nq - 1); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, "batch download", __FILE__, __LINE__); }
+    cudaError_t s1 = cudaStreamSynchronize(ctx->stream), s2 = cudaStreamSynchronize(ctx->copy);
+    if (rc == PPR_OK && (s1 != cudaSuccess || s2 != cudaSuccess)) rc = ctx_fail_cuda(ctx, s1 != cudaSuccess ? s1 : s2, "batch sync", __FILE__, __LINE__);
+    if (rc == PPR_OK) {
+        if (stats_out) for (int q = 0; q < nq; q++) {
+            ppr_stats* st = &stats_out[q];
+            stats_from_ctl(st, &snaps[q], omegas[q]);
+            cudaEvent_t* e = &ev[(size_t)q * 4];
+            cudaEventElapsedTime(&st->ms_push, e[0], e[1]);
+            cudaEventElapsedTime(&st->ms_walk, e[1], e[2]);
+            cudaEventElapsedTime(&st->ms_total, e[0], e[3]);
+            st->launches = 3;
+        }
+        if (nq > 0) { g->last_ws = (nq - 1) & 1; g->last_kind = 1; x->last_divisor = 0.0; }
+    }
+    cudaEventDestroy(copied[0]); cudaEventDestroy(copied[1]);
+    cleanup();
+    return rc;
+}
+
+// ============================================================================================= Monte-Carlo
+extern "C" int32_t ppr_monte_carlo_shard(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed,
+                                         const ppr_conf* conf, int32_t shard, int32_t nshards, ppr_stats* stats) {
+    int32_t rc = check_query(g, src, alpha, "ppr_monte_carlo");
+    if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    if (!(eps > 0)) return ctx_fail(ctx, PPR_E_INVALID, "ppr_monte_carlo: eps must be > 0");
+    if (nshards < 1 || shard < 0 || shard >= nshards) return ctx_fail(ctx, PPR_E_INVALID, "ppr_monte_carlo: bad shard");
+    cudaSetDevice(ctx->device);
+    Workspace& w = g->ws[0];
+    g->trace_active = false;
+    // J/Algo_Conf.java:29-35, J/Monte_Carlo.java:145,149
+    double delta = 1.0 / (double)g->d.n, pfail = 1.0 / (double)g->d.n;
+    if (conf && conf->delta > 0) delta = conf->delta;
+    if (conf && conf->pfail > 0) pfail = conf->pfail;
+    double omega = 3 * std::log(2 / pfail) / eps / eps / delta;
+    if (!(omega < 1e18)) return ctx_fail(ctx, PPR_E_RANGE, "ppr_monte_carlo: omega too large");
+    u64 W = omega >= 1.0 ? (u64)std::floor(omega) : 0;
+    CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    k_mc_setup<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(w.reserve, g->d.n, w.ws_v, w.ws_begin, w.ws_inc, w.ws_rem, w.ctl,
+                                                          g->d.out_deg, src, W, (u64)shard, (u64)nshards);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CUDA_TRY(launch_walk(ctx, g, w, w.reserve, seed, 0, alpha, src, 1, 0, (u64)shard, (u64)nshards));
+    k_mc_dangling<<<1, 32, 0, ctx->stream>>>(w.reserve, w.ctl, src, W, (u64)shard, (u64)nshards);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    rc = read_ctl(g, w); if (rc) return rc;
+    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = omega;
+    if (stats) {
+        stats_from_ctl(stats, w.ctl_host, omega);
+        stats->walks_total = (i64)W;
+        cudaEventElapsedTime(&stats->ms_walk, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&stats->ms_total, ctx->ev[0], ctx->ev[2]);
+        stats->launches = 3;
+    }
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_monte_carlo(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed, const ppr_conf* conf,
+                                   double* ppr_out, ppr_stats* stats) {
+    if (g && !ppr_out) return ctx_fail(g->ctx, PPR_E_INVALID, "ppr_monte_carlo: ppr_out is NULL");
+    int32_t rc = ppr_monte_carlo_shard(g, src, alpha, eps, seed, conf, 0, 1, stats);
+    if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    rc = export_vec(g, g->ws[0], g->ws[0].reserve, extra_of(g)->last_divisor, ppr_out, ctx->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) stats->launches += 1;
+    return PPR_OK;
+}
+
+// ============================================================================================= result access
+extern "C" int32_t ppr_result_devptr(ppr_graph* g, uint64_t* devptr_out, int64_t* n_out) {
+    if (!g || !devptr_out) return PPR_E_INVALID;
+    if (g->last_kind == 0) return ctx_fail(g->ctx, PPR_E_STATE, "ppr_result_devptr: no query has run");
+    Workspace& w = g->ws[g->last_ws];
+    *devptr_out = (uint64_t)(uintptr_t)(g->last_kind == 2 ? w.est : w.reserve);
+    if (n_out) *n_out = g->d.n;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_result_export(ppr_graph* g, double divisor, double* out) {
+    if (!g || !out) return PPR_E_INVALID;
+    ppr_ctx* ctx = g->ctx;
+    if (g->last_kind == 0) return ctx_fail(ctx, PPR_E_STATE, "ppr_result_export: no query has run");
+    cudaSetDevice(ctx->device);
+    Workspace& w = g->ws[g->last_ws];
+    int32_t rc = export_vec(g, w, g->last_kind == 2 ? w.est : w.reserve, divisor, out, ctx->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_last_raw(ppr_graph* g, uint64_t* reserve_fx, uint64_t* residue_fx) {
+    if (!g) return PPR_E_INVALID;
+    ppr_ctx* ctx = g->ctx;
+    if (g->last_kind == 0) return ctx_fail(ctx, PPR_E_STATE, "ppr_last_raw: no query has run");
+    cudaSetDevice(ctx->device);
+    Workspace& w = g->ws[g->last_ws];
+    size_t bytes = (size_t)g->d.n * sizeof(u64);
+    if (reserve_fx) CUDA_TRY(cudaMemcpyAsync(reserve_fx, g->last_kind == 2 ? w.est : w.reserve, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (residue_fx) CUDA_TRY(cudaMemcpyAsync(residue_fx, w.r, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PPR_OK;
+}
+
+// ============================================================================================= top-k
+static int32_t run_select(ppr_graph* g, Workspace& w, const u64* vals, i64 n, i64 k) {
+    ppr_ctx* ctx = g->ctx;
+    SelArgs S;
+    S.vals = vals; S.n = n; S.k = k; S.hist = w.hist; S.sel_ids = w.sel_ids; S.sel_vals = w.sel_vals; S.sel_cap = w.sel_cap; S.ctl = w.ctl;
+    void* args[] = {&S};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_topk_select, dim3(w.coop_blocks), dim3(SEL_THREADS), args, 0, ctx->stream));
+    return PPR_OK;
+}
+
+// survivors -> (value desc, id asc), the order of getTopKNodeIds (J/Fora_Topk.java:82-99; ties are unordered there)
+static int32_t fetch_survivors(ppr_graph* g, Workspace& w, std::vector<i32>& ids, std::vector<u64>& vals) {
+    ppr_ctx* ctx = g->ctx;
+    i64 cnt = w.ctl_host->sel_count;
+    if (cnt > w.sel_cap) return ctx_fail(ctx, PPR_E_CAPACITY, "top-k: too many tied survivors for the selection buffer");
+    std::vector<i32> ti((size_t)cnt);
+    std::vector<u64> tv((size_t)cnt);
+    if (cnt) {
+        CUDA_TRY(cudaMemcpyAsync(ti.data(), w.sel_ids, (size_t)cnt * sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(tv.data(), w.sel_vals, (size_t)cnt * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<i64> ord((size_t)cnt);
+    for (i64 i = 0; i < cnt; i++) ord[(size_t)i] = i;
+    std::sort(ord.begin(), ord.end(), [&](i64 a, i64 b) { return tv[a] != tv[b] ? tv[a] > tv[b] : ti[a] < ti[b]; });
+    ids.resize((size_t)cnt); vals.resize((size_t)cnt);
+    for (i64 i = 0; i < cnt; i++) { ids[(size_t)i] = ti[(size_t)ord[(size_t)i]]; vals[(size_t)i] = tv[(size_t)ord[(size_t)i]]; }
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_fora_topk(ppr_graph* g, int32_t src, double alpha, double eps, int32_t k, uint64_t seed, int32_t flags,
+                                 const ppr_conf* conf, int32_t* ids_out, double* vals_out, int32_t cap, int32_t* count_out, ppr_stats* stats) {
+    int32_t rc = check_fora(g, src, alpha, eps, 0, 1, "ppr_fora_topk");
+    if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    if (k < 1 || !count_out || cap < 0 || (cap > 0 && (!ids_out || !vals_out))) return ctx_fail(ctx, PPR_E_INVALID, "ppr_fora_topk: bad k / buffers");
+    cudaSetDevice(ctx->device);
+    Workspace& w = g->ws[0];
+    g->trace_active = false;
+    const i64 n = g->d.n, m = g->d.m;
+    // J/Algo_Conf.java:71-81 (note the integer division n / k) and J/Fora_Topk.java:109-114
+    double min_delta = 1.0 / (double)n;
+    double delta_local = 1.0 / (double)k;
+    double pfail = 1.0 / (double)n / (double)n / std::log((double)(n / (i64)k));
+    if (conf && conf->delta > 0) delta_local = conf->delta;
+    if (conf && conf->pfail > 0) pfail = conf->pfail;
+    if (conf && conf->min_delta > 0) min_delta = conf->min_delta;
+    double epsilon = eps * 0.5;
+    double L = std::log(2.0 / pfail);
+    float ms_push = 0, ms_walk = 0, ms_sel = 0;
+    int launches = 0;
+    int round = 0;
+    double omega_local = 0;
+    bool dangling = false;
+    CUDA_TRY(cudaEventRecord(ctx->ev[4], ctx->stream));
+    while (delta_local >= min_delta) {
+        double rmax_local = epsilon * std::sqrt(delta_local / 3.0 / (double)m / L);
+        omega_local = (epsilon + 2.0) * L / epsilon / epsilon / delta_local;
+        rmax_local *= std::sqrt((double)m * rmax_local) * 3.0;  // J/Fora_Topk.java:133
+        PushArgs A;
+        fill_push_args(A, g, w);
+        A.src = src; A.alpha_q64 = h_alpha_q64(alpha); A.alpha = alpha; A.omega = omega_local; A.rmax0 = rmax_local;
+        A.max_rounds = 1; A.mode = PMODE_TOPK; A.init = round == 0;
+        CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+        CUDA_TRY(launch_push(ctx, w, A));
+        CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CUDA_TRY(launch_walk(ctx, g, w, w.est, seed, (u64)round, alpha, src, (flags & PPR_RESTART_AT_SOURCE) ? 1 : 0, 0, 0, 1));
+        CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+        rc = run_select(g, w, w.est, n, k); if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+        rc = read_ctl(g, w); if (rc) return rc;
+        launches += 3;
+        float t;
+        cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]); ms_push += t;
+        cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2]); ms_walk += t;
+        cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]); ms_sel += t;
+        if (w.ctl_host->src_dangling) { dangling = true; break; }  // J/Fora_Topk.java:128-132
+        round++;
+        double kth_d = (double)w.ctl_host->sel_kth * FX_INV;
+        if (kth_d >= (1 + epsilon) * delta_local || delta_local <= min_delta) break;
+        delta_local = std::max(min_delta, delta_local / 4.0);
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev[5], ctx->stream));
+    g->last_ws = 0; g->last_kind = 2; extra_of(g)->last_divisor = 0.0;
+    std::vector<i32> ids; std::vector<u64> vals;
+    rc = fetch_survivors(g, w, ids, vals); if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        stats_from_ctl(stats, w.ctl_host, omega_local);
+        stats->rounds = dangling ? 0 : round;
+        stats->ms_push = ms_push; stats->ms_walk = ms_walk; stats->ms_select = ms_sel;
+        cudaEventElapsedTime(&stats->ms_total, ctx->ev[4], ctx->ev[5]);
+        stats->launches = launches;
+    }
+    *count_out = (int32_t)ids.size();
+    if ((i64)ids.size() > cap) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_fora_topk: output buffers too small");
+    for (size_t i = 0; i < ids.size(); i++) { ids_out[i] = ids[i]; vals_out[i] = (double)vals[i] * FX_INV; }
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_topk(ppr_ctx* ctx, const double* vec, int64_t n, int32_t k, int32_t* ids_out, double* vals_out,
+                            int32_t cap, int32_t* count_out, double* kth_out) {
+    if (!ctx) return PPR_E_INVALID;
+    if (!vec || n < 1 || !count_out || cap < 0 || (cap > 0 && (!ids_out || !vals_out))) return ctx_fail(ctx, PPR_E_INVALID, "ppr_topk: bad arguments");
+    cudaSetDevice(ctx->device);
+    // a throw-away pseudo graph/workspace: only the selection buffers are needed
+    double* d_vec = nullptr; u64* d_bits = nullptr; u32* hist = nullptr; i32* sel_ids = nullptr; u64* sel_vals = nullptr; PushCtl* ctl = nullptr;
+    PushCtl hctl;
+    int32_t rc = PPR_OK;
+    cudaError_t e = cudaSuccess;
+    auto done = [&]() { cudaFree(d_vec); cudaFree(d_bits); cudaFree(hist); cudaFree(sel_ids); cudaFree(sel_vals); cudaFree(ctl); };
+#define T_TRY(expr) do { e = (expr); if (e != cudaSuccess) { done(); return ctx_fail_cuda(ctx, e, #expr, __FILE__, __LINE__); } } while (0)
+    T_TRY(dalloc(&d_vec, (size_t)n)); T_TRY(dalloc(&d_bits, (size_t)n)); T_TRY(dalloc(&hist, (size_t)9 * 256));
+    T_TRY(dalloc(&sel_ids, (size_t)n)); T_TRY(dalloc(&sel_vals, (size_t)n)); T_TRY(dalloc(&ctl, 1));
+    T_TRY(cudaMemcpyAsync(d_vec, vec, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_import_f64<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_vec, d_bits, n);
+    T_TRY(cudaGetLastError());
+    int occ = 0;
+    T_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_topk_select, SEL_THREADS, 0));
+    SelArgs S;
+    S.vals = d_bits; S.n = n; S.k = k; S.hist = hist; S.sel_ids = sel_ids; S.sel_vals = sel_vals; S.sel_cap = n; S.ctl = ctl;
+    void* args[] = {&S};
+    T_TRY(cudaLaunchCooperativeKernel((const void*)k_topk_select, dim3(ctx->sm_count * std::max(1, std::min(occ, 4))), dim3(SEL_THREADS), args, 0, ctx->stream));
+    T_TRY(cudaMemcpyAsync(&hctl, ctl, sizeof hctl, cudaMemcpyDeviceToHost, ctx->stream));
+    T_TRY(cudaStreamSynchronize(ctx->stream));
+    i64 cnt = hctl.sel_count;
+    std::vector<i32> ti((size_t)cnt);
+    if (cnt) { T_TRY(cudaMemcpy(ti.data(), sel_ids, (size_t)cnt * sizeof(i32), cudaMemcpyDeviceToHost)); }
+#undef T_TRY
+    done();
+    std::sort(ti.begin(), ti.end(), [&](i32 a, i32 b) { return vec[a] != vec[b] ? vec[a] > vec[b] : a < b; });
+    *count_out = (int32_t)cnt;
+    if (kth_out) { double kd; u64 kb = hctl.sel_kth; memcpy(&kd, &kb, 8); *kth_out = kb ? kd : 0.0; }
+    if (cnt > cap) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_topk: output buffers too small");
+    for (i64 i = 0; i < cnt; i++) { ids_out[i] = ti[(size_t)i]; vals_out[i] = vec[ti[(size_t)i]]; }
+    return rc;
+}
+
+// ============================================================================================= power iteration
+extern "C" int32_t ppr_power_iteration(ppr_graph* g, int32_t src, double alpha, int32_t iters, double* out) {
+    int32_t rc = check_query(g, src, alpha, "ppr_power_iteration");
+    if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    if (!out || iters < 0) return ctx_fail(ctx, PPR_E_INVALID, "ppr_power_iteration: bad arguments");
+    cudaSetDevice(ctx->device);
+    const i64 n = g->d.n;
+    const int nblk = ctx->sm_count * 4;
+    double *r = nullptr, *r2 = nullptr, *q = nullptr, *res = nullptr, *blk = nullptr;
+    auto done = [&]() { cudaFree(r); cudaFree(r2); cudaFree(q); cudaFree(res); cudaFree(blk); };
+    cudaError_t e;
+#define P_TRY(expr) do { e = (expr); if (e != cudaSuccess) { done(); return ctx_fail_cuda(ctx, e, #expr, __FILE__, __LINE__); } } while (0)
+    P_TRY(dalloc(&r, (size_t)n)); P_TRY(dalloc(&r2, (size_t)n)); P_TRY(dalloc(&q, (size_t)n)); P_TRY(dalloc(&res, (size_t)n)); P_TRY(dalloc(&blk, (size_t)nblk));
+    P_TRY(cudaMemsetAsync(r, 0, (size_t)n * 8, ctx->stream)); P_TRY(cudaMemsetAsync(res, 0, (size_t)n * 8, ctx->stream));
+    double one = 1.0;
+    P_TRY(cudaMemcpyAsync(r + src, &one, 8, cudaMemcpyHostToDevice, ctx->stream));
+    for (int it = 0; it < iters; it++) {
+        k_pm_scale<<<nblk, 256, 0, ctx->stream>>>(r, q, res, g->d.out_deg, n, alpha, blk);
+        k_pm_pull<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(q, r2, g->d.in_vtx, g->d.row_idx, n, src, blk, nblk);
+        std::swap(r, r2);
+    }
+    P_TRY(cudaGetLastError());
+    P_TRY(cudaMemcpyAsync(out, res, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    P_TRY(cudaStreamSynchronize(ctx->stream));
+#undef P_TRY
+    done();
+    return PPR_OK;
+}
+
+// ============================================================================================= backward search
+static int32_t bwd_run_batch(ppr_graph* g, BwdWorkspace& b, i32 t0, i32 T, double alpha, double threshold, PushCtl* hctl) {
+    ppr_ctx* ctx = g->ctx;
+    Workspace& w = g->ws[0];
+    const i64 n = g->d.n;
+    BwdArgs A;
+    memset(&A, 0, sizeof A);
+    A.n = n; A.in_vtx = g->d.in_vtx; A.row_idx = g->d.row_idx; A.invdeg = g->d.invdeg;
+    A.r = b.r; A.reserve = b.reserve; A.front[0] = b.front[0]; A.front[1] = b.front[1]; A.front_cap = b.front_cap;
+    A.s_pack = b.s_pack; A.s_y = b.s_y; A.s_t = b.s_t; A.l_pack = b.l_pack; A.l_y = b.l_y; A.l_t = b.l_t;
+    A.chunks = b.chunks; A.chunk_cap = b.chunk_cap; A.blk_a = w.blk_a; A.ctl = w.ctl; A.t0 = t0; A.T = T;
+    A.alpha_q64 = h_alpha_q64(alpha);
+    // J/Backward_Search.java:89 (r > rmax) and J/Base_Whole_Graph.java:83 (pi >= threshold), in fixed point
+    double fl = threshold > 0 ? std::floor(threshold * FX_SCALE) : 0.0;
+    double cl = threshold > 0 ? std::ceil(threshold * FX_SCALE) : 0.0;
+    A.rmax_fx = fl >= 18446744073709551615.0 ? ~0ull : (u64)fl;
+    A.thr_fx = cl >= 18446744073709551615.0 ? ~0ull : (u64)cl;
+    A.out_v = b.out_v; A.out_t = b.out_t; A.out_val = b.out_val; A.out_cap = b.out_cap;
+    CUDA_TRY(cudaMemsetAsync(b.r, 0, (size_t)T * n * 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(b.reserve, 0, (size_t)T * n * 8, ctx->stream));
+    void* args[] = {&A};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_bwd_batch, dim3(w.coop_blocks), dim3(PUSH_THREADS), args, 0, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(w.ctl_host, w.ctl, sizeof(PushCtl), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *hctl = *w.ctl_host;
+    return PPR_OK;
+}
+
+static int32_t bwd_ensure(ppr_graph* g, i32 T) {
+    GraphExtra* x = extra_of(g);
+    if (x->bws_ready && x->bws.T >= T) return PPR_OK;
+    if (x->bws_ready) { bws_free(x->bws); x->bws_ready = false; }
+    int32_t rc = bws_alloc(g->ctx, x->bws, T, g->d.n);
+    if (rc) { bws_free(x->bws); return rc; }
+    x->bws_ready = true;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_backward_search(ppr_graph* g, int32_t target, double alpha, double rmax, double* reserve_out,
+                                       ppr_stats* stats) {
+    int32_t rc = check_query(g, target, alpha, "ppr_backward_search");
+    if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    if (!reserve_out) return ctx_fail(ctx, PPR_E_INVALID, "ppr_backward_search: reserve_out is NULL");
+    cudaSetDevice(ctx->device);
+    g->trace_active = false;
+    rc = bwd_ensure(g, 1); if (rc) return rc;
+    BwdWorkspace& b = extra_of(g)->bws;
+    PushCtl h;
+    CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = bwd_run_batch(g, b, target, 1, alpha, rmax, &h); if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (h.err || h.err_a) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_backward_search: frontier buffers overflowed");
+    // keep the raw vectors reachable through ppr_last_raw: copy the single-target state into workspace 0
+    Workspace& w = g->ws[0];
+    CUDA_TRY(cudaMemcpyAsync(w.reserve, b.reserve, (size_t)g->d.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(w.r, b.r, (size_t)g->d.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0;
+    rc = export_vec(g, w, w.reserve, 0.0, reserve_out, ctx->stream); if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->pushes = (i64)h.pushes; stats->edges = (i64)h.edges; stats->iters = (i64)h.iters;
+        cudaEventElapsedTime(&stats->ms_push, ctx->ev[0], ctx->ev[1]);
+        stats->ms_total = stats->ms_push; stats->launches = 2;
+    }
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double threshold, int32_t k, int32_t t_lo, int32_t t_hi,
+                                          ppr_pairs** out, ppr_stats* stats) {
+    if (!g) return PPR_E_INVALID;
+    ppr_ctx* ctx = g->ctx;
+    if (!out) return ctx_fail(ctx, PPR_E_INVALID, "ppr_backward_all_pairs: out is NULL");
+    *out = nullptr;
+    if (!(alpha > 0 && alpha < 1)) return ctx_fail(ctx, PPR_E_INVALID, "ppr_backward_all_pairs: alpha must be in (0, 1)");
+    const i64 n = g->d.n;
+    if (t_lo < 0 || t_hi > n || t_lo > t_hi) return ctx_fail(ctx, PPR_E_INVALID, "ppr_backward_all_pairs: bad target range");
+    cudaSetDevice(ctx->device);
+    g->trace_active = false;
+    // batch size: dense per-target state is 16 n bytes; stay within a quarter of the free memory and 8 GB
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>(free_b / 4, (size_t)8 << 30);
+    i64 T = (i64)std::max<size_t>(1, budget / ((size_t)16 * (size_t)n));
+    T = std::min<i64>(T, 4096);
+    T = std::min<i64>(T, std::max<i64>(1, t_hi - t_lo));
+    int32_t rc = bwd_ensure(g, (i32)T); if (rc) return rc;
+    BwdWorkspace& b = extra_of(g)->bws;
+    T = std::min<i64>(T, b.T);
+    std::vector<u32> hv, ht; std::vector<u64> hval;
+    std::vector<u32> bv, bt; std::vector<u64> bval;
+    i64 pushes = 0, edges = 0, iters = 0;
+    int launches = 0;
+    CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    i64 curT = T;
+    for (i64 t0 = t_lo; t0 < t_hi;) {
+        i64 Tb = std::min<i64>(curT, t_hi - t0);
+        PushCtl h;
+        rc = bwd_run_batch(g, b, (i32)t0, (i32)Tb, alpha, threshold, &h); if (rc) return rc;
+        launches++;
+        if (h.err || h.err_a || h.pairs_needed > (u64)b.out_cap) {  // frontier or output overflow: rerun with fewer targets
+            if (Tb == 1) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_backward_all_pairs: a single target overflows the batch buffers");
+            curT = std::max<i64>(1, Tb / 2);
+            continue;
+        }
+        pushes += (i64)h.pushes; edges += (i64)h.edges; iters += (i64)h.iters;
+        size_t cnt = (size_t)h.pairs;
+        if (cnt) {
+            try { bv.resize(cnt); bt.resize(cnt); bval.resize(cnt); } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
+            CUDA_TRY(cudaMemcpyAsync(bv.data(), b.out_v, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(bt.data(), b.out_t, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(bval.data(), b.out_val, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            try { hv.insert(hv.end(), bv.begin(), bv.end()); ht.insert(ht.end(), bt.begin(), bt.end()); hval.insert(hval.end(), bval.begin(), bval.end()); }
+            catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
+        }
+        t0 += Tb;
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    // inverted index grouped by source v (J/Base_Whole_Graph.java:83-87): stable counting sort keeps targets ascending
+    ppr_pairs* P = new (std::nothrow) ppr_pairs();
+    if (!P) return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed");
+    P->n = n;
+    try {
+        P->src_ptr.assign((size_t)n + 1, 0);
+        for (size_t i = 0; i < hv.size(); i++) P->src_ptr[(size_t)hv[i] + 1]++;
+        for (i64 v = 0; v < n; v++) P->src_ptr[(size_t)v + 1] += P->src_ptr[(size_t)v];
+        P->tgt.resize(hv.size()); P->val.resize(hv.size());
+        std::vector<i64> pos(P->src_ptr.begin(), P->src_ptr.end() - 1);
+        for (size_t i = 0; i < hv.size(); i++) { i64 p = pos[hv[i]]++; P->tgt[(size_t)p] = (i32)ht[i]; P->val[(size_t)p] = hval[i]; }
+        if (k >= 0) {  // J/Base_Whole_Graph.java:133-148: keep >= k-th largest, sort descending (stable)
+            std::vector<i64> nptr((size_t)n + 1, 0);
+            std::vector<i32> ntgt; std::vector<u64> nval;
+            std::vector<i64> ord; std::vector<u64> tmp;
+            for (i64 v = 0; v < n; v++) {
+                i64 lo = P->src_ptr[(size_t)v], hi = P->src_ptr[(size_t)v + 1], len = hi - lo;
+                u64 kth = 0; bool have = false;
+                if (k >= 1 && k <= len) {
+                    tmp.assign(P->val.begin() + lo, P->val.begin() + hi);
+                    std::nth_element(tmp.begin(), tmp.begin() + (k - 1), tmp.end(), [](u64 a, u64 c) { return a > c; });
+                    kth = tmp[(size_t)k - 1]; have = true;
+                }
+                ord.clear();
+                for (i64 i = lo; i < hi; i++) if (!have || P->val[(size_t)i] >= kth) ord.push_back(i);
+                std::stable_sort(ord.begin(), ord.end(), [&](i64 a, i64 c) { return P->val[(size_t)a] > P->val[(size_t)c]; });
+                for (i64 i : ord) { ntgt.push_back(P->tgt[(size_t)i]); nval.push_back(P->val[(size_t)i]); }
+                nptr[(size_t)v + 1] = (i64)ntgt.size();
+            }
+            P->src_ptr.swap(nptr); P->tgt.swap(ntgt); P->val.swap(nval);
+        }
+    } catch (...) { delete P; return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->pushes = pushes; stats->edges = edges; stats->iters = iters;
+        cudaEventElapsedTime(&stats->ms_push, ctx->ev[0], ctx->ev[1]);
+        stats->ms_total = stats->ms_push; stats->launches = launches; stats->rounds = launches;
+    }
+    *out = P;
+    return PPR_OK;
+}
+
+extern "C" int64_t ppr_pairs_count(const ppr_pairs* p) { return p ? (int64_t)p->tgt.size() : -1; }
+extern "C" int32_t ppr_pairs_export(const ppr_pairs* p, int64_t* src_ptr, int32_t* tgt, double* val, uint64_t* val_fx) {
+    if (!p || !src_ptr) return PPR_E_INVALID;
+    memcpy(src_ptr, p->src_ptr.data(), p->src_ptr.size() * sizeof(i64));
+    if (tgt && !p->tgt.empty()) memcpy(tgt, p->tgt.data(), p->tgt.size() * sizeof(i32));
+    if (val) for (size_t i = 0; i < p->val.size(); i++) val[i] = (double)p->val[i] * FX_INV;
+    if (val_fx && !p->val.empty()) memcpy(val_fx, p->val.data(), p->val.size() * sizeof(u64));
+    return PPR_OK;
+}
+extern "C" int32_t ppr_pairs_destroy(ppr_pairs* p) { delete p; return PPR_OK; }
+
+// ============================================================================================= stepped push (trace)
+extern "C" int32_t ppr_push_trace_begin(ppr_graph* g, int32_t src, double alpha, double rmax) {
+    int32_t rc = check_query(g, src, alpha, "ppr_push_trace_begin");
+    if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    if (!(rmax > 0)) return ctx_fail(ctx, PPR_E_INVALID, "ppr_push_trace_begin: rmax must be > 0");
+    cudaSetDevice(ctx->device);
+    Workspace& w = g->ws[0];
+    PushArgs A;
+    fill_push_args(A, g, w);
+    A.src = src; A.alpha_q64 = h_alpha_q64(alpha); A.alpha = alpha; A.rmax0 = rmax; A.mode = PMODE_PUSH; A.init = 1;
+    int blocks = ctx->sm_count * 4;
+    k_step_init<<<blocks, PUSH_THREADS, 0, ctx->stream>>>(A);
+    k_step_seed<<<1, 32, 0, ctx->stream>>>(A);
+    k_step_scan<<<blocks, PUSH_THREADS, 0, ctx->stream>>>(A, 0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    g->trace_active = true; g->trace_parity = 0; g->trace_src = src; g->trace_alpha_q64 = A.alpha_q64;
+    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_push_trace_step(ppr_graph* g, int32_t* frontier_out, int64_t cap, int64_t* count_out) {
+    if (!g || !count_out) return PPR_E_INVALID;
+    ppr_ctx* ctx = g->ctx;
+    if (!g->trace_active) return ctx_fail(ctx, PPR_E_STATE, "ppr_push_trace_step: call ppr_push_trace_begin first");
+    cudaSetDevice(ctx->device);
+    Workspace& w = g->ws[0];
+    int par = g->trace_parity;
+    int32_t rc = read_ctl(g, w); if (rc) return rc;
+    i64 cnt = w.ctl_host->cnt[par];
+    *count_out = cnt;
+    if (cnt == 0) return PPR_OK;
+    if (frontier_out) {
+        if (cnt > cap) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_push_trace_step: frontier_out too small");
+        CUDA_TRY(cudaMemcpyAsync(frontier_out, w.front[par], (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PushArgs A;
+    fill_push_args(A, g, w);
+    A.src = g->trace_src; A.alpha_q64 = g->trace_alpha_q64; A.mode = PMODE_PUSH;
+    int blocks = ctx->sm_count * 4;
+    k_step_a<<<blocks, PUSH_THREADS, 0, ctx->stream>>>(A, par);
+    k_step_b<<<blocks, PUSH_THREADS, 0, ctx->stream>>>(A, par);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    g->trace_parity = par ^ 1;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_walk_terminals(ppr_graph* g, int32_t start, int32_t restart, uint64_t j0, int64_t count, uint64_t seed,
+                                      uint64_t tag, double alpha, int32_t no_zero_hop, int32_t* terminals_out) {
+    int32_t rc = check_query(g, start, alpha, "ppr_walk_terminals");
+    if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    if (restart < 0 || restart >= g->d.n || count < 0 || !terminals_out) return ctx_fail(ctx, PPR_E_INVALID, "ppr_walk_terminals: bad arguments");
+    if (count == 0) return PPR_OK;
+    cudaSetDevice(ctx->device);
+    i32* d_out = nullptr;
+    CUDA_TRY(dalloc(&d_out, (size_t)count));
+    u64 key = h_walk_key(seed, tag);
+    k_walk_terminals<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(g->d.out_vtx, g->d.col_idx, (u32)start, (u32)restart, j0,
+                                                                              count, (u32)key, (u32)(key >> 32),
+                                                                              h_stop_threshold(alpha), no_zero_hop, d_out);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(terminals_out, d_out, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    CUDA_TRY(e);
+    return PPR_OK;
+}

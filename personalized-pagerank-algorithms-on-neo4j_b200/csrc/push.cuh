@@ -1,0 +1,503 @@
+// push.cuh -- frontier-synchronous forward push (Forward Push and FORA's push phase) for sm_100a.
+//
+// Replaces the FIFO loops of J/Forward_Push.java:85-141 (whole graph) and :165-248 (incremental,
+// FORA top-k) and FORA's balance loop J/Fora_Whole_Graph.java:93-103.
+//
+// One synchronous iteration = two phases separated by a grid-wide barrier:
+//   phase A (per frontier vertex): capture x = r[v]; reserve[v] += mulhi(x, alpha); r[v] = leftover;
+//            stage (packed vertex record, per-edge amount q) by degree class;
+//   phase B (per edge): old = atomicAdd(&r[u], q); the add that crosses thr(u) appends u to the next
+//            frontier (exactly one add crosses, because after phase A every residue is below its
+//            threshold and phase B only adds) -- no dense scan, no duplicates, no flags to clear.
+// Work classes in phase B: rows of <= PUSH_SMALL_MAX edges are gathered 32 vertices per warp with a
+// warp prefix sum (lanes walk the concatenated edge list, so neighbour loads stay dense even for
+// degree-1 vertices); longer rows are cut into PUSH_CHUNK-edge chunks, one warp per chunk with
+// coalesced 128-byte neighbour loads.  Dangling vertices reduce their mass per CTA and one thread adds
+// it to r[source] (J/Forward_Push.java:101-115).
+//
+// The whole query (all iterations, FORA's rmax-halving rounds and the walk-source scan) runs as ONE
+// cooperative persistent kernel: frontier sizes never travel to the host.  The same device functions
+// are also wrapped as plain kernels for the stepped/trace API used by the schedule tests.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+namespace cg = cooperative_groups;
+
+struct PushArgs {
+    // graph
+    i64 n;
+    const u64* out_vtx;
+    const i32* col_idx;
+    const u32* out_deg;
+    // state
+    u64* r;
+    u64* reserve;
+    u64* est;
+    u32* front[2];
+    u64* s_pack; u64* s_q; u64* l_pack; u64* l_q;
+    uint2* chunks;
+    u32* ws_v; u64* ws_begin; u64* ws_inc; u64* ws_rem;
+    u64* blk_a; u64* blk_b;
+    PushCtl* ctl;
+    // query
+    i32 src;
+    u64 alpha_q64;
+    double alpha;
+    double omega;       // FORA omega (whole graph) or the round's omega (top-k)
+    double walk_cost;
+    double rmax0;       // initial rmax (double)
+    int max_rounds;
+    int mode;           // 0: plain push, one round | 1: FORA whole graph | 2: FORA top-k round
+    int init;           // 1: reset state and seed r[src] = 1
+    int zero_reserve_after_push;  // shard != 0 of a multi-GPU FORA: drop the push reserve before the walk prep
+    int prep_adds_push_part;      // shard == 0
+};
+
+#define PMODE_PUSH 0
+#define PMODE_FORA 1
+#define PMODE_TOPK 2
+
+// --------------------------------------------------------------------------------- small device utilities
+__device__ __forceinline__ void warp_append_u32(u32* list, u32* counter, bool pred, u32 value) {
+    u32 mask = __ballot_sync(0xffffffffu, pred);
+    if (mask) {
+        u32 leader = __ffs(mask) - 1;
+        u32 base = 0;
+        if (lane_id() == leader) base = atomicAdd(counter, (u32)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pred) list[base + __popc(mask & lanemask_lt())] = value;
+    }
+}
+
+__device__ __forceinline__ u64 rmax_to_fx_dev(double rmax) {
+    double x = __dmul_rn(rmax, FX_SCALE);
+    if (!(x >= 1.0)) return 1ull;
+    if (x >= 18446744073709551615.0) return ~0ull;
+    return (u64)x;  // truncation
+}
+
+// --------------------------------------------------------------------------------- frontier seeding by dense scan
+// {v : r[v] >= thr(v)}: start of a round (rmax just changed) -- the counterpart of Q / Q_next hand-over
+// in J/Fora_Topk.java:145 and of the fresh queue in J/Forward_Push.java:81.
+__device__ void push_scan(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize) {
+    PushCtl* ctl = A.ctl;
+    for (i64 base = 0; base < A.n; base += gsize) {
+        i64 v = base + gtid;
+        bool pred = false;
+        if (v < A.n) {
+            u64 x = A.r[v];
+            if (x) pred = x >= thr_fwd(rmax_fx, A.out_deg[v]);
+        }
+        warp_append_u32(A.front[par], &ctl->cnt[par], pred, (u32)v);
+    }
+}
+
+// --------------------------------------------------------------------------------- phase A
+__device__ void push_phase_a(const PushArgs& A, int par, i64 gtid, i64 gsize) {
+    PushCtl* ctl = A.ctl;
+    const u32 cnt = *(volatile u32*)&ctl->cnt[par];
+    if (gtid == 0) {  // recycle the other parity's counters (last read before the preceding barrier)
+        ctl->cnt[par ^ 1] = 0; ctl->ns[par ^ 1] = 0; ctl->nl[par ^ 1] = 0; ctl->nchunks[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
+        ctl->pushes += cnt;
+    }
+    u64 edges_local = 0, resv_local = 0, dang_local = 0;
+    const u32* F = A.front[par];
+    for (i64 base = 0; base < cnt; base += gsize) {
+        i64 i = base + gtid;
+        bool is_small = false, is_large = false;
+        u64 pk = 0, q = 0;
+        if (i < cnt) {
+            u32 v = F[i];
+            pk = A.out_vtx[v];
+            u32 d = vtx_deg(pk);
+            u64 x = A.r[v];
+            u64 a = mulhi64(x, A.alpha_q64);
+            u64 y = x - a;
+            u64 left;
+            if (d == 0) { q = y; left = 0; dang_local += y; }
+            else { q = y / (u64)d; left = y - q * (u64)d; }
+            A.r[v] = left;
+            A.reserve[v] += a;
+            resv_local += a;
+            edges_local += d;
+            is_small = d > 0 && d <= PUSH_SMALL_MAX;
+            is_large = d > PUSH_SMALL_MAX;
+        }
+        // staged small items: warp-aggregated append of (pack, q)
+        u32 mask = __ballot_sync(0xffffffffu, is_small);
+        if (mask) {
+            u32 leader = __ffs(mask) - 1, b = 0;
+            if (lane_id() == leader) b = atomicAdd(&ctl->ns[par], (u32)__popc(mask));
+            b = __shfl_sync(0xffffffffu, b, leader);
+            if (is_small) { u32 slot = b + __popc(mask & lanemask_lt()); A.s_pack[slot] = pk; A.s_q[slot] = q; }
+        }
+        if (is_large) {
+            u32 slot = atomicAdd(&ctl->nl[par], 1u);
+            A.l_pack[slot] = pk; A.l_q[slot] = q;
+            u32 d = vtx_deg(pk);
+            u32 nch = (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
+            u32 cb = atomicAdd(&ctl->nchunks[par], nch);
+            for (u32 c = 0; c < nch; c++) A.chunks[cb + c] = make_uint2(slot, c);
+        }
+    }
+    edges_local = warp_sum_u64(edges_local);
+    resv_local = warp_sum_u64(resv_local);
+    dang_local = warp_sum_u64(dang_local);
+    if (lane_id() == 0) {
+        if (edges_local) atomicAdd((ull*)&ctl->edges, (ull)edges_local);
+        if (resv_local) atomicAdd((ull*)&ctl->reserve_total, (ull)resv_local);
+        if (dang_local) atomicAdd((ull*)&ctl->dang[par], (ull)dang_local);
+    }
+}
+
+// --------------------------------------------------------------------------------- phase B
+// One relaxed edge: add q to r[u] and detect the threshold crossing.
+__device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32 u, u64 q) {
+    u64 old = atomicAdd((ull*)&A.r[u], (ull)q);
+    u64 th = thr_fwd(rmax_fx, __ldg(&A.out_deg[u]));
+    return old < th && old + q >= th;
+}
+
+__device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u64* sm_excl /*[warps][32]*/,
+                             u64* sm_beg, u64* sm_q) {
+    PushCtl* ctl = A.ctl;
+    const u32 ns = *(volatile u32*)&ctl->ns[par];
+    const u32 nch = *(volatile u32*)&ctl->nchunks[par];
+    const i64 gwarp = gtid >> 5, nwarps = gsize >> 5;
+    const u32 lane = lane_id();
+    const int wib = threadIdx.x >> 5;
+    u32* next = A.front[par ^ 1];
+    u32* next_cnt = &ctl->cnt[par ^ 1];
+    u64* w_excl = sm_excl + wib * 32;
+    u64* w_beg = sm_beg + wib * 32;
+    u64* w_q = sm_q + wib * 32;
+
+    // (1) short rows: 32 vertices per warp, lanes sweep the concatenated edge list
+    for (i64 wbase = gwarp * 32; wbase < ns; wbase += nwarps * 32) {
+        i64 item = wbase + lane;
+        u64 pk = 0, q = 0;
+        if (item < ns) { pk = A.s_pack[item]; q = A.s_q[item]; }
+        u32 d = vtx_deg(pk);
+        u32 incl = d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        u32 excl = incl - d;
+        u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        w_excl[lane] = excl;
+        w_beg[lane] = vtx_begin(pk) - excl;  // edge address of concatenated position e is w_beg[owner] + e
+        w_q[lane] = q;
+        __syncwarp();
+        for (u32 eb = 0; eb < total; eb += 32) {
+            u32 e = eb + lane;
+            bool cross = false;
+            u32 u = 0;
+            if (e < total) {
+                int o = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) { int p = o + s; if ((u32)w_excl[p] <= e) o = p; }
+                u = (u32)__ldg(&A.col_idx[w_beg[o] + e]);
+                cross = relax_edge(A, rmax_fx, u, w_q[o]);
+            }
+            warp_append_u32(next, next_cnt, cross, u);
+        }
+        __syncwarp();
+    }
+
+    // (2) long rows: one warp per PUSH_CHUNK-edge chunk
+    for (i64 c = gwarp; c < nch; c += nwarps) {
+        uint2 desc = A.chunks[c];
+        u64 pk = A.l_pack[desc.x];
+        u64 q = A.l_q[desc.x];
+        u32 d = vtx_deg(pk);
+        u32 off = desc.y * PUSH_CHUNK;
+        u32 len = min((u32)PUSH_CHUNK, d - off);
+        const i32* row = A.col_idx + vtx_begin(pk) + off;
+        for (u32 eb = 0; eb < len; eb += 64) {  // two independent edges per lane in flight
+            u32 e0 = eb + lane, e1 = eb + 32 + lane;
+            u32 u0 = 0, u1 = 0;
+            bool c0 = false, c1 = false;
+            if (e0 < len) u0 = (u32)__ldg(&row[e0]);
+            if (e1 < len) u1 = (u32)__ldg(&row[e1]);
+            if (e0 < len) c0 = relax_edge(A, rmax_fx, u0, q);
+            if (e1 < len) c1 = relax_edge(A, rmax_fx, u1, q);
+            warp_append_u32(next, next_cnt, c0, u0);
+            warp_append_u32(next, next_cnt, c1, u1);
+        }
+    }
+
+    // (3) dangling mass -> source (J/Forward_Push.java:101-113)
+    if (gtid == 0) {
+        u64 dsum = *(volatile u64*)&ctl->dang[par];
+        if (dsum) {
+            u64 old = atomicAdd((ull*)&A.r[A.src], (ull)dsum);
+            u64 th = thr_fwd(rmax_fx, A.out_deg[A.src]);
+            if (old < th && old + dsum >= th) { u32 idx = atomicAdd(next_cnt, 1u); next[idx] = (u32)A.src; }
+        }
+        ctl->iters += 1;
+    }
+}
+
+// --------------------------------------------------------------------------------- block-level helpers (walk preparation)
+__device__ __forceinline__ u64 block_sum_u64(u64 v, u64* sm /*>= 32 entries*/) {
+    v = warp_sum_u64(v);
+    __syncthreads();
+    if (lane_id() == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    u64 t = 0;
+    if (threadIdx.x < 32) {
+        t = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0;
+        t = warp_sum_u64(t);
+        if (threadIdx.x == 0) sm[0] = t;
+    }
+    __syncthreads();
+    t = sm[0];
+    __syncthreads();
+    return t;
+}
+
+// exclusive scan of (a, b) pairs over the block; returns this thread's exclusive prefix and the block totals
+__device__ __forceinline__ void block_excl_scan2(u64 a, u64 b, u64* sm /*>= 64 entries*/, u64& ea, u64& eb, u64& ta, u64& tb) {
+    const u32 lane = lane_id(), w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    u64 ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 xa = __shfl_up_sync(0xffffffffu, ia, o), xb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += xa; ib += xb; }
+    }
+    __syncthreads();
+    if (lane == 31) { sm[w] = ia; sm[32 + w] = ib; }
+    __syncthreads();
+    u64 wa = 0, wb = 0;
+    ta = 0; tb = 0;
+    for (u32 k = 0; k < nw; k++) {
+        u64 xa = sm[k], xb = sm[32 + k];
+        if (k < w) { wa += xa; wb += xb; }
+        ta += xa; tb += xb;
+    }
+    ea = wa + ia - a;
+    eb = wb + ib - b;
+    __syncthreads();
+}
+
+// --------------------------------------------------------------------------------- walk preparation (inside the cooperative kernel)
+// FORA whole graph, J/Fora_Whole_Graph.java:116-131: every vertex with residue x moves mulhi(x,alpha)
+// into its reserve, y = x - that; N = (long)(omega * r_sum); omega_v = ceil(y / r_sum * N); each of its
+// walks carries y / omega_v (remainder on walk 0).  Dangling starts return themselves without a draw
+// (J/Monte_Carlo.java:106-108), so their y goes straight to reserve[v].
+// FORA top-k, J/Fora_Topk.java:148-160: no alpha split, N = (long)(omega * r_sum * (1-alpha)),
+// omega_v = ceil(x * N), estimate = copy of the push reserve plus walk contributions; residues stay.
+// Output: compacted walk sources in ascending vertex order with the exclusive prefix of walk counts.
+template <bool TOPK>
+__device__ void walk_prep(const PushArgs& A, cg::grid_group& grid, u64* sm) {
+    PushCtl* ctl = A.ctl;
+    const i64 n = A.n;
+    const i64 per = (n + gridDim.x - 1) / gridDim.x;
+    const i64 v_lo = min(n, (i64)blockIdx.x * per), v_hi = min(n, v_lo + per);
+    u64* target = TOPK ? A.est : A.reserve;
+
+    double rsum_d;
+    i64 N;
+    if (!TOPK) {
+        u64 sy = 0;
+        for (i64 v = v_lo + threadIdx.x; v < v_hi; v += blockDim.x) {
+            u64 x = A.r[v];
+            if (x) sy += x - mulhi64(x, A.alpha_q64);
+        }
+        sy = block_sum_u64(sy, sm);
+        if (threadIdx.x == 0 && sy) atomicAdd((ull*)&ctl->rsum_fx, (ull)sy);
+        grid.sync();
+        u64 rsum_fx = *(volatile u64*)&ctl->rsum_fx;
+        rsum_d = __dmul_rn((double)rsum_fx, FX_INV);
+        N = (i64)__dmul_rn(A.omega, rsum_d);
+    } else {
+        u64 rsum_fx = FX_ONE - *(volatile u64*)&ctl->reserve_total;
+        rsum_d = __dmul_rn((double)rsum_fx, FX_INV);
+        double rsum_rw = __dmul_rn(rsum_d, 1.0 - A.alpha);
+        N = (i64)__dmul_rn(A.omega, rsum_rw);
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->rsum_fx = rsum_fx;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->N = N;
+
+    // pass 2: per-CTA totals of (sources, walks)
+    u64 c_src = 0, c_w = 0;
+    for (i64 v = v_lo + threadIdx.x; v < v_hi; v += blockDim.x) {
+        u64 x = A.r[v];
+        if (x && N > 0 && A.out_deg[v] != 0) {
+            u64 y = TOPK ? x : x - mulhi64(x, A.alpha_q64);
+            double yd = __dmul_rn((double)y, FX_INV);
+            double t = TOPK ? __dmul_rn(yd, (double)N) : __dmul_rn(__ddiv_rn(yd, rsum_d), (double)N);
+            i64 w = (i64)ceil(t);
+            if (w > 0) { c_src += 1; c_w += (u64)w; }
+        }
+    }
+    c_src = block_sum_u64(c_src, sm);
+    c_w = block_sum_u64(c_w, sm);
+    if (threadIdx.x == 0) { A.blk_a[blockIdx.x] = c_src; A.blk_b[blockIdx.x] = c_w; }
+    grid.sync();
+
+    // pass 3: CTA offsets, then ordered compaction of the chunk
+    u64 o_src = 0, o_w = 0;
+    for (u32 b = threadIdx.x; b < blockIdx.x; b += blockDim.x) { o_src += A.blk_a[b]; o_w += A.blk_b[b]; }
+    o_src = block_sum_u64(o_src, sm);
+    o_w = block_sum_u64(o_w, sm);
+    for (i64 tile = v_lo; tile < v_hi; tile += blockDim.x) {
+        i64 v = tile + threadIdx.x;
+        u64 has = 0, w = 0, y = 0;
+        if (v < v_hi) {
+            u64 x = A.r[v];
+            u64 base = A.reserve[v];
+            if (x) {
+                u64 a = TOPK ? 0 : mulhi64(x, A.alpha_q64);
+                y = x - a;
+                if (!TOPK) { if (A.prep_adds_push_part) base += a; A.r[v] = 0; }
+                if (N > 0) {
+                    if (A.out_deg[v] == 0) { if (A.prep_adds_push_part) base += y; }
+                    else {
+                        double yd = __dmul_rn((double)y, FX_INV);
+                        double t = TOPK ? __dmul_rn(yd, (double)N) : __dmul_rn(__ddiv_rn(yd, rsum_d), (double)N);
+                        i64 wi = (i64)ceil(t);
+                        if (wi > 0) { has = 1; w = (u64)wi; }
+                    }
+                }
+            }
+            if (TOPK || x) target[v] = base;
+        }
+        u64 e_src, e_w, t_src, t_w;
+        block_excl_scan2(has, w, sm, e_src, e_w, t_src, t_w);
+        if (has) {
+            u64 slot = o_src + e_src;
+            u64 inc = y / w;
+            A.ws_v[slot] = (u32)v;
+            A.ws_begin[slot] = o_w + e_w;
+            A.ws_inc[slot] = inc;
+            A.ws_rem[slot] = y - inc * w;
+        }
+        o_src += t_src; o_w += t_w;
+    }
+    if (blockIdx.x == gridDim.x - 1) {  // totals + sentinels for the walk kernel's 33-entry windows
+        for (u32 k = threadIdx.x; k < 40; k += blockDim.x) A.ws_begin[o_src + k] = o_w;
+        if (threadIdx.x == 0) { ctl->total_walks = o_w; ctl->n_sources = (u32)o_src; }
+    }
+}
+
+// --------------------------------------------------------------------------------- the persistent query kernel
+__global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ u64 sm_excl[(PUSH_THREADS / 32) * 32];
+    __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
+    __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
+    PushCtl* ctl = A.ctl;
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 gsize = (i64)gridDim.x * blockDim.x;
+
+    if (A.init) {
+        for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
+        if (gtid == 0) {
+            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
+            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
+            ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
+            ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
+            ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0;
+        }
+        grid.sync();
+    }
+    if (gtid == 0) {
+        ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0;
+        if (!A.init) {  // top-k round: host supplied the round's rmax; counters of both parities must be clean
+            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
+            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
+            ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
+        }
+    }
+    const bool dangling_src = A.out_deg[A.src] == 0;  // J/Forward_Push.java:72-76, J/Fora_Topk.java:128-132
+    if (dangling_src) {
+        if (gtid == 0) {
+            A.reserve[A.src] = A.prep_adds_push_part ? FX_ONE : 0;
+            ctl->reserve_total = FX_ONE;
+            ctl->src_dangling = 1;
+        }
+        if (A.mode == PMODE_TOPK) {
+            grid.sync();
+            for (i64 v = gtid; v < A.n; v += gsize) A.est[v] = A.reserve[v];
+        }
+        return;
+    }
+    if (A.init && gtid == 0) A.r[A.src] = FX_ONE;
+    grid.sync();
+
+    int par = 0;
+    for (;;) {
+        const u64 rmax_fx = *(volatile u64*)&ctl->rmax_fx;
+        push_scan(A, par, rmax_fx, gtid, gsize);
+        grid.sync();
+        for (;;) {
+            if (*(volatile u32*)&ctl->cnt[par] == 0) break;
+            push_phase_a(A, par, gtid, gsize);
+            grid.sync();
+            push_phase_b(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
+            grid.sync();
+            par ^= 1;
+        }
+        if (gtid == 0) {
+            // deterministic stand-in for the wall-clock balancer of J/Fora_Whole_Graph.java:93-103
+            u64 rsum_fx = FX_ONE - ctl->reserve_total;
+            double rsum_w = __dmul_rn(__dmul_rn((double)rsum_fx, FX_INV), 1.0 - A.alpha);
+            double cost = (double)(ctl->pushes + ctl->edges);
+            double rmax = __dmul_rn(ctl->rmax, 0.5);
+            u64 rounds = ctl->rounds + 1;
+            ctl->rounds = rounds;
+            bool cont = A.mode == PMODE_FORA && cost < __dmul_rn(__dmul_rn(A.walk_cost, rsum_w), A.omega) &&
+                        rounds < (u64)A.max_rounds;
+            ctl->rmax = rmax;
+            if (cont) ctl->rmax_fx = rmax_to_fx_dev(rmax);
+            ctl->cont = cont ? 1u : 0u;
+        }
+        grid.sync();
+        if (*(volatile u32*)&ctl->cont == 0) break;
+    }
+
+    if (A.mode == PMODE_PUSH) return;
+    if (A.zero_reserve_after_push) {
+        for (i64 v = gtid; v < A.n; v += gsize) A.reserve[v] = 0;
+        grid.sync();
+    }
+    if (A.mode == PMODE_FORA) walk_prep<false>(A, grid, sm_excl);
+    else walk_prep<true>(A, grid, sm_excl);
+}
+
+// --------------------------------------------------------------------------------- stepped wrappers (trace API)
+__global__ void __launch_bounds__(PUSH_THREADS) k_step_init(PushArgs A) {
+    PushCtl* ctl = A.ctl;
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
+    if (gtid == 0) {
+        ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
+        ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
+        ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
+        ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
+        ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0;
+        ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0;
+    }
+}
+__global__ void __launch_bounds__(PUSH_THREADS) k_step_seed(PushArgs A) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (A.out_deg[A.src] == 0) { A.reserve[A.src] = FX_ONE; A.ctl->reserve_total = FX_ONE; A.ctl->src_dangling = 1; }
+        else A.r[A.src] = FX_ONE;
+    }
+}
+__global__ void __launch_bounds__(PUSH_THREADS) k_step_scan(PushArgs A, int par) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    push_scan(A, par, A.ctl->rmax_fx, gtid, gsize);
+}
+__global__ void __launch_bounds__(PUSH_THREADS) k_step_a(PushArgs A, int par) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    push_phase_a(A, par, gtid, gsize);
+}
+__global__ void __launch_bounds__(PUSH_THREADS) k_step_b(PushArgs A, int par) {
+    __shared__ u64 sm_excl[(PUSH_THREADS / 32) * 32];
+    __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
+    __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    push_phase_b(A, par, A.ctl->rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
+}

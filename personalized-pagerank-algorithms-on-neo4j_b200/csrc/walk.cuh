@@ -1,0 +1,187 @@
+// walk.cuh -- alpha-terminating random walks (Monte-Carlo and FORA's walk phase) for sm_100a.
+//
+// Replaces Monte_Carlo.random_walk / random_walk_no_zero_hop (J/Monte_Carlo.java:60-133) and the walk
+// loops of J/Monte_Carlo.java:149-154, J/Fora_Whole_Graph.java:133-139, J/Fora_Topk.java:161-167.
+//
+// One walk per lane.  Randomness is counter based (Philox4x32-10, key = seed, counter = (start vertex,
+// walk index, step)), so the terminal of walk (v, j) is a pure function of its arguments: the CPU
+// replay in oracle/ reproduces every terminal, and the result does not depend on how walks are split
+// over lanes, warps, launches or GPUs.  Contributions are integer (fixed-point increments or counts)
+// and are added with red.global.add.u64.
+//
+// Scheduling: each warp owns a contiguous slice of the global walk index space and refills idle lanes
+// every step (walk lengths are geometric; without refill a warp idles ~70 % of its lanes waiting for
+// the longest of 32 walks).  Walk index -> (source, local index) uses the exclusive prefix ws_begin
+// produced by walk_prep; because a warp's indices are consecutive, the lookup is a 33-entry window
+// of that prefix held in shared memory that slides forward, not a global binary search per walk.
+#pragma once
+#include "common.cuh"
+
+struct WalkArgs {
+    const u64* out_vtx;
+    const i32* col_idx;
+    const u32* ws_v;
+    const u64* ws_begin;
+    const u64* ws_inc;
+    const u64* ws_rem;
+    u64* target;       // vector receiving the contributions
+    PushCtl* ctl;
+    u64 shard, nshards;
+    u32 k0, k1;        // Philox key
+    u64 tstop;         // ceil(alpha * 2^53)
+    i32 src;           // query source (restart target when restart_at_source)
+    int restart_at_source;
+    int no_zero_hop;
+};
+
+struct WalkState {
+    u32 start, cur, restart, step;
+    u64 j;
+    bool first;  // next step is the mandatory first move of random_walk_no_zero_hop
+};
+
+// One step of a walk.  Returns true when the walk has stopped (w.cur is the terminal).
+//   J/Monte_Carlo.java:75-90: draw U; U < alpha -> stop; else move to a uniform out-neighbour, or to the
+//   restart vertex when the current vertex is dangling (no neighbour draw in that case).
+//   J/Monte_Carlo.java:110-112: the first move of the no-zero-hop variant is unconditional.
+__device__ __forceinline__ bool walk_step(WalkState& w, const u64* __restrict__ out_vtx, const i32* __restrict__ col_idx,
+                                          u32 k0, u32 k1, u64 tstop, u64& steps) {
+    Philox4 x = philox4x32_10(w.start, (u32)w.j, (u32)(w.j >> 32), w.step, k0, k1);
+    w.step++;
+    if (!w.first) {
+        u64 u53 = ((u64)x.x0 << 21) | (u64)(x.x1 >> 11);
+        if (u53 < tstop) return true;
+    }
+    w.first = false;
+    u64 pk = __ldg(&out_vtx[w.cur]);
+    u32 d = vtx_deg(pk);
+    if (d) {
+        u64 rnd = ((u64)x.x2 << 32) | (u64)x.x3;
+        w.cur = (u32)__ldg(&col_idx[vtx_begin(pk) + mulhi64(rnd, (u64)d)]);
+    } else {
+        w.cur = w.restart;
+    }
+    steps++;
+    return false;
+}
+
+__device__ __forceinline__ u64 mul_div_u64(u64 a, u64 b, u64 c) {  // floor(a*b/c) for a*b < 2^64 * c, c < 2^32
+    // a = walk total (< 2^40), b <= nshards or warp index (< 2^24): the product fits in 64 bits
+    return (a * b) / c;
+}
+
+__global__ void __launch_bounds__(WALK_THREADS, 4) k_walk(WalkArgs A) {
+    __shared__ u64 win[WALK_THREADS / 32][34];
+    PushCtl* ctl = A.ctl;
+    const u64 W = ctl->total_walks;
+    const u32 nsrc = ctl->n_sources;
+    if (W == 0 || nsrc == 0) return;
+    const u64 lo = mul_div_u64(W, A.shard, A.nshards), hi = mul_div_u64(W, A.shard + 1, A.nshards);
+    const u64 nw = ((u64)gridDim.x * blockDim.x) >> 5;
+    const u64 gw = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 span = hi - lo;
+    const u64 wl = lo + mul_div_u64(span, gw, nw), wh = lo + mul_div_u64(span, gw + 1, nw);
+    if (wl >= wh) return;
+    const u32 lane = lane_id();
+    u64* mywin = win[threadIdx.x >> 5];
+
+    // source containing wl: largest s in [0, nsrc) with ws_begin[s] <= wl
+    u32 scur;
+    {
+        u32 a = 0, b = nsrc;  // invariant: ws_begin[a] <= wl < ws_begin[b] (ws_begin[nsrc] = W > wl)
+        while (b - a > 1) {
+            u32 mid = a + ((b - a) >> 1);
+            if (__ldg(&A.ws_begin[mid]) <= wl) a = mid; else b = mid;
+        }
+        scur = a;
+    }
+    u64 wnext = wl;
+    bool active = false;
+    WalkState w; w.start = w.cur = w.restart = w.step = 0; w.j = 0; w.first = false;
+    u64 inc = 0, steps = 0, done = 0;
+
+    for (;;) {
+        u32 needy = __ballot_sync(0xffffffffu, !active);
+        if (needy && wnext < wh) {
+            mywin[lane] = A.ws_begin[scur + lane];
+            if (lane < 2) mywin[32 + lane] = A.ws_begin[scur + 32 + lane];
+            __syncwarp();
+            u32 rank = __popc(needy & lanemask_lt());
+            u64 idx = wnext + rank;
+            if (!active && idx < wh) {
+                int o = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) { int p = o + s; if (mywin[p] <= idx) o = p; }
+                u32 si = scur + o;
+                w.start = A.ws_v[si];
+                w.j = idx - mywin[o];
+                inc = A.ws_inc[si] + (w.j == 0 ? A.ws_rem[si] : 0);
+                w.cur = w.start;
+                w.restart = A.restart_at_source ? (u32)A.src : w.start;
+                w.step = 0;
+                w.first = A.no_zero_hop != 0;
+                active = true;
+            }
+            u64 take = min((u64)__popc(needy), wh - wnext);
+            wnext += take;
+            if (wnext < wh) {  // slide the window: source containing wnext (offset may be 32)
+                int o = 0;
+#pragma unroll
+                for (int s = 32; s > 0; s >>= 1) { int p = o + s; if (p <= 32 && mywin[p] <= wnext) o = p; }
+                scur += (u32)o;
+            }
+            __syncwarp();
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active) {
+            if (walk_step(w, A.out_vtx, A.col_idx, A.k0, A.k1, A.tstop, steps)) {
+                atomicAdd((ull*)&A.target[w.cur], (ull)inc);
+                active = false;
+                done++;
+            }
+        }
+    }
+    steps = warp_sum_u64(steps);
+    done = warp_sum_u64(done);
+    if (lane == 0) {
+        atomicAdd((ull*)&ctl->steps, (ull)steps);
+        atomicAdd((ull*)&ctl->walks_done, (ull)done);
+    }
+}
+
+// Monte-Carlo setup: one source (the query vertex) with W = floor(omega) unit-weight walks
+// (J/Monte_Carlo.java:145-154).  A dangling source yields W walks that all return it without a draw.
+__global__ void k_mc_setup(u64* counts, i64 n, u32* ws_v, u64* ws_begin, u64* ws_inc, u64* ws_rem, PushCtl* ctl,
+                           const u32* out_deg, i32 src, u64 W, u64 shard, u64 nshards) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    for (i64 v = gtid; v < n; v += gsize) counts[v] = 0;
+    if (gtid == 0) {
+        ctl->steps = 0; ctl->walks_done = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
+        ctl->rsum_fx = 0; ctl->N = (i64)W; ctl->err = 0; ctl->rmax_fx = 0; ctl->reserve_total = 0;
+        bool dangling = out_deg[src] == 0;
+        ctl->src_dangling = dangling ? 1u : 0u;
+        ws_v[0] = (u32)src; ws_inc[0] = 1; ws_rem[0] = 0; ws_begin[0] = 0;
+        for (int k = 1; k < 40; k++) ws_begin[k] = W;
+        ctl->total_walks = dangling ? 0 : W;
+        ctl->n_sources = dangling ? 0u : 1u;
+    }
+}
+__global__ void k_mc_dangling(u64* counts, PushCtl* ctl, i32 src, u64 W, u64 shard, u64 nshards) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ctl->src_dangling) {
+        u64 lo = (W * shard) / nshards, hi = (W * (shard + 1)) / nshards;
+        counts[src] = hi - lo;
+        ctl->walks_done = hi - lo;
+    }
+}
+
+// Terminals of consecutive walks, one per thread (test / replay API; same walk_step as k_walk).
+__global__ void k_walk_terminals(const u64* out_vtx, const i32* col_idx, u32 start, u32 restart, u64 j0, i64 count,
+                                 u32 k0, u32 k1, u64 tstop, int no_zero_hop, i32* out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (vtx_deg(out_vtx[start]) == 0) { out[i] = (i32)start; return; }  // J/Monte_Carlo.java:70-72
+    WalkState w; w.start = start; w.cur = start; w.restart = restart; w.step = 0; w.j = j0 + (u64)i; w.first = no_zero_hop != 0;
+    u64 steps = 0;
+    while (!walk_step(w, out_vtx, col_idx, k0, k1, tstop, steps)) {}
+    out[i] = (i32)w.cur;
+}

@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library loads, exports every symbol include/pprb200.h declares, and fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "pprb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ppr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(pkg):
+    L = pkg.load()
+    syms = header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(L, s), "libpprb200.so does not export " + s
+    assert sorted(pkg._native.EXPORTS) == syms
+
+
+def test_library_is_sm100a_cuda(pkg):
+    # the shipped binary carries sm_100a SASS (no PTX-only / other-arch build)
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", pkg._native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_stats_struct_layout(pkg):
+    assert ctypes.sizeof(pkg._native.Stats) == 112 and ctypes.sizeof(pkg._native.Conf) == 24
+
+
+def test_rmat_generator(pkg):
+    rp, ci = pkg.rmat(1 << 10, 1 << 14, seed=3)
+    rp2, ci2 = pkg.rmat(1 << 10, 1 << 14, seed=3)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
+    assert rp[0] == 0 and rp[-1] == 1 << 14 and (np.diff(rp) >= 0).all() and ci.min() >= 0 and ci.max() < 1 << 10
+    for v in range(1 << 10):
+        assert (np.diff(ci[rp[v]:rp[v + 1]]) >= 0).all()
+    rp3, ci3 = pkg.rmat(1 << 10, 1 << 14, seed=4)
+    assert not np.array_equal(ci, ci3)
+    # skew: R-MAT's heaviest vertex owns far more than the mean degree
+    assert np.diff(rp).max() > 20 * 16
+    rp, ci = pkg.rmat(1000, 16000, seed=3, symmetric=True)   # non power of two + symmetrised
+    src = np.repeat(np.arange(1000), np.diff(rp))
+    fwd = np.sort(src * 1000 + ci)
+    bwd = np.sort(ci.astype(np.int64) * 1000 + src)
+    assert np.array_equal(fwd, bwd)
+    with pytest.raises(pkg.PPRError):
+        pkg.rmat(1000, 15, symmetric=True)
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only behaviour")
+def test_no_cpu_fallback(pkg):
+    with pytest.raises(pkg.PPRError) as e:
+        pkg.Context(0)
+    assert e.value.code == pkg._native.PPR_E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle(pkg):
+    pkg_dir = os.path.dirname(pkg.__file__)
+    for root, _, files in os.walk(pkg_dir):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(root, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "ppr_oracle" not in txt, fn
