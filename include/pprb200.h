@@ -94,6 +94,14 @@ int32_t ppr_device_info(ppr_ctx* ctx, int32_t* sm_count, int64_t* total_mem, cha
  * rounds < max_rounds.  Defaults: walk_cost = 32, max_rounds = 64. */
 int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_rounds);
 
+/* Measurement helpers (bench.py): CUDA events on the context's compute stream, the stream every kernel
+ * of this library is launched on (after joining the download stream), and an L2 flush (a write of a
+ * 256 MiB scratch buffer, larger than the 126 MB L2).  slot is 0..3. */
+int32_t ppr_timer_record(ppr_ctx* ctx, int32_t slot);
+int32_t ppr_timer_elapsed_ms(ppr_ctx* ctx, int32_t slot_a, int32_t slot_b, float* ms_out); /* synchronises */
+int32_t ppr_flush_l2(ppr_ctx* ctx);
+int32_t ppr_device_sync(ppr_ctx* ctx);
+
 /* Pinned host memory for result buffers (optional). */
 int32_t ppr_host_alloc(ppr_ctx* ctx, int64_t bytes, void** out);
 int32_t ppr_host_free(ppr_ctx* ctx, void* p);

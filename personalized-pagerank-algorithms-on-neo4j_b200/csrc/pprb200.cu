@@ -114,6 +114,43 @@ extern "C" int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_r
     return PPR_OK;
 }
 
+static cudaEvent_t g_timer_ev[4];
+static bool g_timer_init = false;
+static void* g_flush_buf = nullptr;
+extern "C" int32_t ppr_timer_record(ppr_ctx* ctx, int32_t slot) {
+    if (!ctx || slot < 0 || slot > 3) return PPR_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (!g_timer_init) { for (int i = 0; i < 4; i++) cudaEventCreate(&g_timer_ev[i]); g_timer_init = true; }
+    cudaEvent_t join;  // the compute stream waits for everything queued on the download stream
+    CUDA_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    cudaEventRecord(join, ctx->copy);
+    cudaStreamWaitEvent(ctx->stream, join, 0);
+    cudaEventDestroy(join);
+    CUDA_TRY(cudaEventRecord(g_timer_ev[slot], ctx->stream));
+    return PPR_OK;
+}
+extern "C" int32_t ppr_timer_elapsed_ms(ppr_ctx* ctx, int32_t a, int32_t b, float* ms_out) {
+    if (!ctx || a < 0 || a > 3 || b < 0 || b > 3 || !ms_out || !g_timer_init) return PPR_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(cudaEventSynchronize(g_timer_ev[b]));
+    CUDA_TRY(cudaEventElapsedTime(ms_out, g_timer_ev[a], g_timer_ev[b]));
+    return PPR_OK;
+}
+extern "C" int32_t ppr_flush_l2(ppr_ctx* ctx) {
+    if (!ctx) return PPR_E_INVALID;
+    cudaSetDevice(ctx->device);
+    const size_t bytes = (size_t)256 << 20;
+    if (!g_flush_buf) CUDA_TRY(cudaMalloc(&g_flush_buf, bytes));
+    CUDA_TRY(cudaMemsetAsync(g_flush_buf, 0x5a, bytes, ctx->stream));
+    return PPR_OK;
+}
+extern "C" int32_t ppr_device_sync(ppr_ctx* ctx) {
+    if (!ctx) return PPR_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    return PPR_OK;
+}
+
 extern "C" int32_t ppr_host_alloc(ppr_ctx* ctx, int64_t bytes, void** out) {
     if (!ctx || !out || bytes < 0) return PPR_E_INVALID;
     cudaSetDevice(ctx->device);

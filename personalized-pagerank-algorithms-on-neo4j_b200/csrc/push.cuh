@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
             A.reserve[A.src] = A.prep_adds_push_part ? FX_ONE : 0;
             ctl->reserve_total = FX_ONE;
             ctl->src_dangling = 1;
+            ctl->rmax_fx = 0;
         }
         if (A.mode == PMODE_TOPK) {
             grid.sync();

@@ -1,0 +1,116 @@
+"""GPU (-m gpu): the reference-facing host mirror (class names / harness protocol) and full-size properties."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ALPHA, EPS = 0.15, 0.5
+
+
+@pytest.fixture(scope="module")
+def G(pkg, ctx, got):
+    g = pkg.Graph(ctx, got[0], got[1])
+    yield g
+    g.close()
+
+
+def test_algorithm_classes_like_the_harness_uses_them(pkg, G, O, got):
+    og = O.OGraph(got[0], got[1])
+    ac = pkg.Algo_Conf(ALPHA, "name")
+    n, m = G.nodeCount(), G.relCount()
+    pm = ac.set_conf_power_method(None, G, "got.db")
+    for algo, param in ((ac.set_conf_fora_whole_graph(n, m, None, G, "got.db"), 0.5), (ac.set_conf_fwdpush(n, m, None, G, "got.db"), 1e-6),
+                        (ac.set_conf_mc(n, m, None, G, "got.db"), 0.5)):
+        algo.computeWholeGraphPPR(63, param)
+        pm.computeWholeGraphPPR(63, None)
+        res = algo.getWholeGraphPPR()
+        assert abs(sum(res.values()) - 1) < 1e-3 and all(v > 0 for v in res.values())
+        err = pkg.compute_error(algo, pm, "MAX_ERR", -1)
+        assert err == O.max_err(pm.reserve, res.dense) and err < 0.02
+    tk = ac.set_conf_fora_topk(n, m, 10, None, G, "got.db")
+    tk.computeTopKPPR(63, 10, 0.5)
+    pm.computeTopKPPR(63, 10, None)
+    exact = O.power_method(og, 63, ALPHA)
+    assert np.array_equal(pm.getTopKNodeIds(10), O.topk_select(pm.reserve, 10))
+    m_ = O.topk_metrics(pm.reserve, 10, tk.getTopKNodeIds(10))
+    assert abs(pkg.compute_error(tk, pm, "PRECISION", 10) - m_["precision"]) < 1e-15
+    assert abs(pkg.compute_error(tk, pm, "NDCG", 10) - m_["ndcg"]) < 1e-12
+    assert np.abs(pm.reserve - exact).max() < 1e-13
+    mc = ac.set_conf_mc(n, m, None, G, "got.db")
+    assert mc.random_walk(71) == 71 and mc.random_walk_no_zero_hop(71) == 71   # dangling start (J/Monte_Carlo.java:70-72)
+    assert 0 <= mc.random_walk_no_zero_hop(63) < n
+    bs = pkg.Backward_Search(ALPHA, 1e-3, n, None, G)
+    bs.backward_search_whole_graph(5)
+    assert np.array_equal(bs.reserve, O.b_backward_search(og, 5, ALPHA, 1e-3)[0] * O.FX_INV)
+
+
+def test_base_whole_graph_store(pkg, G, O, got, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    og = O.OGraph(got[0], got[1])
+    base = pkg.Algo_Conf(ALPHA).set_conf_base_whole_graph(107, 352, None, G, "got.db")
+    base.preprocessing(1e-3, -1)
+    assert os.path.isdir(os.path.join("BASE_ppr_results", "got.db", "0.001_-1")) and base.getPrepSize() > 0
+    optr, otgt, oval, _ = O.b_base_all_pairs(og, ALPHA, 1e-3)
+    for v in (0, 5, 63):
+        base.computeWholeGraphPPR(v, None)
+        row = base.getWholeGraphPPR()
+        assert list(row.keys()) == [int(t) for t in otgt[optr[v]:optr[v + 1]]]
+        assert list(row.values()) == [float(x) * O.FX_INV for x in oval[optr[v]:optr[v + 1]]]   # text round trip is exact
+    base.deletePrepDir()
+
+
+def test_harness_rows(pkg, ctx, got, tmp_path):
+    t = pkg.PPR()
+    t.ctx, t.dir_db = ctx, "got.db"
+    t.adjM = pkg.Graph(ctx, got[0], got[1])
+    t.set_configuration(ALPHA, EPS, "name", "Person", "Relation")
+    with open(tmp_path / "rows.txt", "w") as fw:
+        t.fw = fw
+        r1 = t.algo_perf_test("FORA_WHOLE_GRAPH", 10, -1, 0.5, -1.0, False, "WHOLE_GRAPH")
+        r2 = t.algo_perf_test("FORA_TOPK", 10, 10, 0.5, -1.0, False, "TOPK")
+        r3 = t.algo_perf_test("FWDPUSH", 10, -1, 1e-6, -1.0, False, "WHOLE_GRAPH")
+    lines = open(tmp_path / "rows.txt").read().splitlines()
+    assert lines[0].startswith("0.5,") and lines[1].startswith("0.5,10,") and lines[2].startswith("1.0E-6,")
+    assert r1["max_err"] < 0.05 and r2["precision"] > 0.8 and r2["ndcg"] > 0.97 and r3["max_err"] < 1e-4
+    t.adjM.close()
+
+
+def test_full_size_properties(pkg, ctx):
+    """R-MAT scale-20 (config 2): no oracle at this size; size-independent properties instead."""
+    rp, ci = pkg.rmat(1 << 20, 1 << 24, seed=42)
+    g = pkg.Graph(ctx, rp, ci)
+    deg = np.diff(rp)
+    try:
+        src = int(np.flatnonzero(deg > 0)[1234])
+        # push: exact mass conservation and the exit condition r < rmax * d everywhere
+        _, _, rsum, st = g.forward_push(src, ALPHA, 1e-7, want_residue=False)
+        res, r = g.last_raw()
+        assert int(res.sum(dtype=np.uint64)) + int(r.sum(dtype=np.uint64)) == pkg.FX_ONE
+        rfx = int(1e-7 * 2.0 ** 62)
+        nz = np.flatnonzero(r)
+        assert (r[nz].astype(object) < np.where(deg[nz] == 0, 1, rfx * deg[nz].astype(object))).all()
+        # idempotence: same call, same bits
+        g.forward_push(src, ALPHA, 1e-7, want_residue=False)
+        res2, r2 = g.last_raw()
+        assert np.array_equal(res, res2) and np.array_equal(r, r2)
+        # FORA: all mass ends in the estimate; shards sum to the unsharded vector; seeds matter
+        ppr, st = g.fora(src, ALPHA, EPS, 11)
+        raw = g.last_raw(False)[0]
+        assert int(raw.sum(dtype=np.uint64)) == pkg.FX_ONE and st["walks"] == st["walks_total"] > 0
+        acc = np.zeros_like(raw)
+        for rk in range(2):
+            g.fora_shard(src, ALPHA, EPS, 11, rk, 2)
+            acc += g.last_raw(False)[0]
+        assert np.array_equal(acc, raw)
+        g.fora(src, ALPHA, EPS, 12)
+        assert not np.array_equal(g.last_raw(False)[0], raw)
+        # Monte-Carlo: counts add up to floor(omega)
+        _, st = g.monte_carlo(src, ALPHA, 2.0, 3)
+        assert int(g.last_raw(False)[0].sum(dtype=np.uint64)) == st["walks_total"] == int(np.floor(st["omega"]))
+        # top-k of the FORA estimate is sorted, tie-inclusive and consistent with the dense vector
+        ids, vals, _ = ctx.topk(ppr, 500)
+        assert len(ids) >= 500 and (np.diff(vals) <= 0).all() and np.array_equal(vals, ppr[ids])
+        assert (ppr[np.setdiff1d(np.arange(len(ppr)), ids)] < vals[-1]).all()
+    finally:
+        g.close()

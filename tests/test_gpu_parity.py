@@ -1,0 +1,349 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the golden fixtures.
+
+Integer / fixed-point / index results are compared bit for bit.  Floating-point outputs are the exact
+images of those integers (value * 2^-62), so they are compared with == as well; the only tolerance in
+this file is the FORA (eps, delta, p_f) guarantee against the exact power iteration, written where it
+is used.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "got_golden.npz")
+ALPHA, EPS, SEED, K = 0.15, 0.5, 7, 10
+
+
+@pytest.fixture(scope="module")
+def G(pkg, ctx, got):
+    g = pkg.Graph(ctx, got[0], got[1])
+    yield g
+    g.close()
+
+
+@pytest.fixture(scope="module")
+def OG(O, got):
+    return O.OGraph(got[0], got[1])
+
+
+@pytest.fixture(scope="module")
+def R12(pkg, ctx, O, rmat12):
+    g = pkg.Graph(ctx, *rmat12)
+    yield g, O.OGraph(*rmat12)
+    g.close()
+
+
+@pytest.fixture(scope="module")
+def R16(pkg, ctx, O, rmat16):
+    g = pkg.Graph(ctx, *rmat16)
+    yield g, O.OGraph(*rmat16)
+    g.close()
+
+
+def sources(og, k, seed=1234):
+    rng = np.random.default_rng(seed)
+    return [int(x) for x in rng.integers(0, og.n, size=k)]
+
+
+# ------------------------------------------------------------------ graph export
+def test_graph_export(G, OG, pkg, ctx):
+    assert G.nodeCount() == 107 and G.relCount() == 352
+    cp, ri = G.export_csc()
+    src = np.repeat(np.arange(OG.n), np.diff(OG.rp))
+    order = np.lexsort((src, OG.ci))
+    assert np.array_equal(ri, src[order].astype(np.int32))
+    assert np.array_equal(np.diff(cp), np.bincount(OG.ci, minlength=OG.n))
+    with pytest.raises(pkg.PPRError) as e:
+        pkg.Graph(ctx, np.array([0, 2, 1]), np.array([0, 1], np.int32))
+    assert e.value.code == pkg._native.PPR_E_INVALID
+    with pytest.raises(pkg.PPRError):
+        pkg.Graph(ctx, np.array([0, 1]), np.array([5], np.int32))
+
+
+# ------------------------------------------------------------------ forward push
+def test_forward_push_got_all_sources(G, OG, O):
+    for s in range(OG.n):
+        reserve, residue, rsum, st = G.forward_push(s, ALPHA, 1e-6)
+        raw_res, raw_r = G.last_raw()
+        ores, orr, ost = O.b_forward_push(OG, s, ALPHA, 1e-6)
+        assert np.array_equal(raw_res, ores) and np.array_equal(raw_r, orr), "source %d" % s
+        assert (st["pushes"], st["edges"], st["iters"]) == (ost["pushes"], ost["edges"], ost["iters"])
+        assert np.array_equal(reserve, ores * O.FX_INV) and np.array_equal(residue, orr * O.FX_INV)
+        assert rsum == float(int(orr.sum())) * O.FX_INV
+        assert int(raw_res.sum()) + int(raw_r.sum()) == O.FX_ONE
+
+
+def test_forward_push_reference_grid(G, OG, O):
+    for rmax in (1e-4, 1e-5, 1e-6, 1e-7, 1e-8):               # J/Gen_Util.java:464
+        for s in (0, 63, 71):
+            G.forward_push(s, ALPHA, rmax)
+            raw_res, raw_r = G.last_raw()
+            ores, orr, _ = O.b_forward_push(OG, s, ALPHA, rmax)
+            assert np.array_equal(raw_res, ores) and np.array_equal(raw_r, orr)
+
+
+def test_forward_push_golden(G):
+    gold = np.load(GOLD)
+    for s in gold["sources"]:
+        G.forward_push(int(s), ALPHA, 1e-6)
+        raw_res, raw_r = G.last_raw()
+        assert np.array_equal(raw_res, gold["push_reserve_%d" % s]) and np.array_equal(raw_r, gold["push_residue_%d" % s])
+
+
+def test_forward_push_frontier_sequence(G, OG, O, R12):
+    for g, og, srcs, rmax in ((G, OG, (0, 63, 5), 1e-6), (R12[0], R12[1], sources(R12[1], 3), 1e-7)):
+        for s in srcs:
+            fr = g.push_trace(s, ALPHA, rmax)
+            raw_res, raw_r = g.last_raw()
+            ores, orr, ost = O.b_forward_push(og, s, ALPHA, rmax, trace=True)
+            assert len(fr) == len(ost["frontiers"])
+            for a, b in zip(fr, ost["frontiers"]):
+                assert np.array_equal(a, b)
+            assert np.array_equal(raw_res, ores) and np.array_equal(raw_r, orr)
+
+
+def test_forward_push_rmat(R12, R16, O):
+    for (g, og), rmaxs, nsrc in ((R12, (1e-5, 1e-7, 1e-9), 6), (R16, (1e-6, 1e-8), 4)):
+        deg = np.diff(og.rp)
+        for s in sources(og, nsrc) + [int(deg.argmax()), int(np.flatnonzero(deg == 0)[0])]:
+            for rmax in rmaxs:
+                _, _, _, st = g.forward_push(s, ALPHA, rmax, want_residue=False)
+                raw_res, raw_r = g.last_raw()
+                ores, orr, ost = O.b_forward_push(og, s, ALPHA, rmax)
+                assert np.array_equal(raw_res, ores) and np.array_equal(raw_r, orr), (s, rmax)
+                assert (st["pushes"], st["edges"], st["iters"]) == (ost["pushes"], ost["edges"], ost["iters"])
+
+
+# ------------------------------------------------------------------ walks / Monte-Carlo
+def test_walk_terminals(G, OG, O, R12):
+    gold = np.load(GOLD)
+    assert np.array_equal(G.walk_terminals(63, 63, 0, 256, SEED, 0, ALPHA, True), gold["walk_terminals_63"])
+    for g, og in ((G, OG), R12):
+        deg = np.diff(og.rp)
+        starts = sources(og, 4) + [int(np.flatnonzero(deg == 0)[0])]
+        for s in starts:
+            for nzh in (False, True):
+                for restart in (s, 0):
+                    got = g.walk_terminals(s, restart, 5, 300, SEED, 2, ALPHA, nzh)
+                    exp = [O.walk(og, s, restart, 5 + j, SEED, 2, ALPHA, nzh)[0] for j in range(300)]
+                    assert list(got) == exp
+
+
+def test_monte_carlo(G, OG, O, R12):
+    for g, og, srcs in ((G, OG, (0, 63, 71)), (R12[0], R12[1], sources(R12[1], 2))):
+        for s in srcs:
+            ppr, st = g.monte_carlo(s, ALPHA, EPS, SEED)
+            cnt, _ = g.last_raw(False)
+            ocnt, ost = O.b_monte_carlo(og, s, ALPHA, EPS, SEED)
+            assert np.array_equal(cnt, ocnt)
+            assert st["walks_total"] == ost["walks"] and st["steps"] == ost["steps"] and st["omega"] == ost["omega"]
+            assert np.array_equal(ppr, ocnt / ost["omega"])
+            oa, _ = O.a_monte_carlo(og, s, ALPHA, EPS, SEED)
+            assert np.array_equal(ppr, oa)
+    gold = np.load(GOLD)
+    G.monte_carlo(63, ALPHA, EPS, SEED)
+    assert np.array_equal(G.last_raw(False)[0], gold["mc_63"])
+
+
+def test_monte_carlo_shards(G, OG, O):
+    full, _ = O.b_monte_carlo(OG, 0, ALPHA, 0.3, SEED)
+    for world in (2, 3, 8):
+        acc = np.zeros(OG.n, np.uint64)
+        for r in range(world):
+            G.monte_carlo_shard(0, ALPHA, 0.3, SEED, r, world)
+            part = G.last_raw(False)[0]
+            assert np.array_equal(part, O.b_monte_carlo(OG, 0, ALPHA, 0.3, SEED, r, world)[0])
+            acc += part
+        assert np.array_equal(acc, full)
+
+
+# ------------------------------------------------------------------ FORA
+def check_fora(g, og, O, s, eps, flags=0, walk_cost=32.0):
+    ppr, st = g.fora(s, ALPHA, eps, SEED, flags)
+    raw, r = g.last_raw()
+    oraw, ost = O.b_fora(og, s, ALPHA, eps, SEED, walk_cost=walk_cost, restart_at_source=bool(flags & 1))
+    assert np.array_equal(raw, oraw), (s, eps)
+    for k in ("pushes", "edges", "iters", "rounds", "walk_sources", "steps"):
+        assert st[k] == ost[k], (k, st[k], ost[k])
+    assert st["walks_total"] == ost["walks"] and st["walks"] == ost["walks"]
+    assert st["rmax_fx"] == ost["rmax_fx_final"] and st["rsum_fx"] == ost["rsum_fx"]
+    assert np.array_equal(ppr, oraw * O.FX_INV)
+    return ppr, raw, r, st
+
+
+def test_fora_got(G, OG, O):
+    for s in range(0, OG.n, 3):
+        ppr, raw, r, st = check_fora(G, OG, O, s, EPS)
+        assert int(raw.sum()) == O.FX_ONE and not r.any()      # every unit of mass lands in the estimate
+    for eps in (10.0, 5.0, 0.5, 0.1, 0.05):                    # J/Gen_Util.java:463
+        check_fora(G, OG, O, 63, eps)
+    gold = np.load(GOLD)
+    for s in gold["sources"]:
+        G.fora(int(s), ALPHA, EPS, SEED)
+        assert np.array_equal(G.last_raw(False)[0], gold["fora_%d" % s])
+
+
+def test_fora_rmat(R12, R16, O):
+    for (g, og), nsrc in ((R12, 5), (R16, 2)):
+        deg = np.diff(og.rp)
+        for s in sources(og, nsrc) + [int(np.flatnonzero(deg == 0)[0])]:
+            for flags in (0, 1):
+                ppr, raw, r, st = check_fora(g, og, O, s, EPS, flags)
+                assert int(raw.sum()) == O.FX_ONE
+
+
+def test_fora_balance_knobs(pkg, ctx, G, OG, O):
+    ctx.set_balance(4.0, 3)
+    try:
+        ppr, st = G.fora(63, ALPHA, EPS, SEED)
+        oraw, ost = O.b_fora(OG, 63, ALPHA, EPS, SEED, walk_cost=4.0, max_rounds=3)
+        assert np.array_equal(G.last_raw(False)[0], oraw) and st["rounds"] == ost["rounds"] <= 3
+    finally:
+        ctx.set_balance(32.0, 64)
+
+
+def test_fora_guarantee(G, OG, R12, O):
+    # FORA's guarantee (Dissertation p.14): |est - pi| <= eps * pi for every pi > delta = 1/n, w.p. 1 - 1/n.
+    # Tolerance: exactly eps = 0.5 relative; the exact answer is the power iteration run to 1e-17.
+    for g, og, srcs in ((G, OG, (0, 63, 5, 100)), (R12[0], R12[1], sources(R12[1], 3))):
+        for s in srcs:
+            ppr, _ = g.fora(s, ALPHA, EPS, SEED, 1)
+            exact = O.power_method(og, s, ALPHA, 3000, 1e-17)
+            big = exact > 1.0 / og.n
+            assert (np.abs(ppr - exact)[big] <= EPS * exact[big]).all()
+
+
+def test_fora_walk_shards(G, OG, R12, O):
+    for g, og, s in ((G, OG, 63), (R12[0], R12[1], sources(R12[1], 1)[0])):
+        g.fora(s, ALPHA, EPS, SEED)
+        full = g.last_raw(False)[0]
+        for world in (2, 4, 8):
+            acc = np.zeros(og.n, np.uint64)
+            for r in range(world):
+                g.fora_shard(s, ALPHA, EPS, SEED, r, world)
+                part = g.last_raw(False)[0]
+                assert np.array_equal(part, O.b_fora(og, s, ALPHA, EPS, SEED, shard=r, nshards=world)[0])
+                acc += part
+            assert np.array_equal(acc, full)
+
+
+def test_fora_batch_equals_single(R12, O):
+    g, og = R12
+    srcs = sources(og, 5)
+    out, stats = g.fora_batch(srcs, ALPHA, EPS, 100)
+    for q, s in enumerate(srcs):
+        one, _ = g.fora(s, ALPHA, EPS, 100 + q)
+        assert np.array_equal(out[q], one)
+        assert np.array_equal(out[q], O.b_fora(og, s, ALPHA, EPS, 100 + q)[0] * O.FX_INV)
+        assert stats[q]["ms_push"] > 0
+
+
+# ------------------------------------------------------------------ top-k
+def test_topk_select(ctx, O):
+    rng = np.random.default_rng(5)
+    v = rng.random(5000)
+    v[rng.integers(0, 5000, 2500)] = 0.0
+    v[10] = v[20] = v[30] = 0.77                               # ties at the cut
+    for k in (1, 3, 10, 500, 2400, 4999):
+        ids, vals, kth = ctx.topk(v, k)
+        exp = O.topk_select(v, k)
+        assert np.array_equal(ids, exp) and np.array_equal(vals, v[exp])
+        okth = O.kth_ppr(v[v > 0], k)
+        assert kth == (okth if okth is not None else 0.0)
+    kcut = int((v > 0.77).sum()) + 1
+    ids, _, kth = ctx.topk(v, kcut)
+    assert kth == 0.77 and len(ids) == kcut + 2                # "might include more than k nodes"
+
+
+def test_fora_topk(G, OG, R12, O):
+    gold = np.load(GOLD)
+    for g, og, srcs, k in ((G, OG, list(range(0, 107, 7)) + [71], K), (R12[0], R12[1], sources(R12[1], 3), 50)):
+        for s in srcs:
+            ids, vals, st = g.fora_topk(s, ALPHA, EPS, k, SEED)
+            est = g.last_raw(False)[0]
+            oest, ost = O.b_fora_topk(og, s, ALPHA, EPS, k, SEED)
+            assert np.array_equal(est, oest), s
+            oids = O.topk_select(oest, k)
+            assert np.array_equal(ids, oids) and np.array_equal(vals, oest[oids] * O.FX_INV)
+            assert st["rounds"] == ost["rounds"] and st["pushes"] == ost["pushes"] and st["edges"] == ost["edges"]
+    for s in gold["sources"]:
+        ids, _, _ = G.fora_topk(int(s), ALPHA, EPS, K, SEED)
+        assert np.array_equal(ids, gold["topk_ids_%d" % s])
+
+
+def test_fora_topk_overlap_with_reference_order(G, OG, O):
+    # top-k set overlap against the reference-order (mode A) replay and the exact answer, as the harness reports it
+    prec = []
+    for s in range(0, 107, 5):
+        ids, _, _ = G.fora_topk(s, ALPHA, EPS, K, SEED)
+        exact = O.power_method(OG, s, ALPHA)
+        prec.append(O.topk_metrics(exact, K, ids)["precision"])
+        a, _ = O.a_fora_topk(OG, s, ALPHA, EPS, K, SEED)
+        a_ids = set(O.topk_select(a, K).tolist())
+        assert len(a_ids & set(ids.tolist())) >= 0.7 * min(len(a_ids), len(ids))
+    assert np.mean(prec) >= 0.9
+
+
+# ------------------------------------------------------------------ backward search / all pairs
+def test_backward_search(G, OG, R12, O):
+    for g, og, ts, rmax in ((G, OG, range(0, 107, 4), 1e-3), (G, OG, (5, 63), 5e-7), (R12[0], R12[1], sources(R12[1], 4), 1e-4)):
+        for t in ts:
+            res, st = g.backward_search(int(t), ALPHA, rmax)
+            raw, r = g.last_raw()
+            ores, orr, ost = O.b_backward_search(og, int(t), ALPHA, rmax)
+            assert np.array_equal(raw, ores) and np.array_equal(r, orr), t
+            assert (st["pushes"], st["edges"], st["iters"]) == (ost["pushes"], ost["edges"], ost["iters"])
+            assert np.array_equal(res, ores * O.FX_INV)
+
+
+def test_all_pairs(G, OG, R12, O):
+    gold = np.load(GOLD)
+    for thr in (1e-3, 5e-5):
+        ptr, tgt, val, st = G.backward_all_pairs(ALPHA, thr, raw=True)
+        assert np.array_equal(ptr, gold["ap_ptr_%g" % thr]) and np.array_equal(tgt, gold["ap_tgt_%g" % thr])
+        assert np.array_equal(val, gold["ap_val_%g" % thr])
+    g, og = R12
+    optr, otgt, oval, ost = O.b_base_all_pairs(og, ALPHA, 1e-3)
+    ptr, tgt, val, st = g.backward_all_pairs(ALPHA, 1e-3, raw=True)
+    assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval)
+    assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"])
+    # block partition of the targets (multi-GPU layout) merges to the same index
+    from importlib import import_module
+    D = import_module("personalized-pagerank-algorithms-on-neo4j_b200").dist
+    parts = [g.backward_all_pairs(ALPHA, 1e-3, -1, lo, hi, raw=True)[:3] for lo, hi in D.target_blocks(og.n, 4)]
+    mptr, mtgt, mval = D.merge_pairs(parts, og.n)
+    assert np.array_equal(mptr, optr) and np.array_equal(mtgt, otgt) and np.array_equal(mval, oval)
+
+
+def test_all_pairs_topk_rows(G, OG, O):
+    ptr, tgt, val, _ = G.backward_all_pairs(ALPHA, 1e-3, 3, raw=True)
+    fptr, ftgt, fval, _ = O.b_base_all_pairs(OG, ALPHA, 1e-3)
+    for v in range(OG.n):
+        row_t, row_v = ftgt[fptr[v]:fptr[v + 1]], fval[fptr[v]:fptr[v + 1]]
+        keep = O.topk_select(row_v, 3) if len(row_v) else np.zeros(0, np.int32)   # >= 3rd largest, descending, stable
+        assert np.array_equal(tgt[ptr[v]:ptr[v + 1]], row_t[keep]) and np.array_equal(val[ptr[v]:ptr[v + 1]], row_v[keep])
+
+
+# ------------------------------------------------------------------ power iteration
+def test_power_iteration(G, OG, R12, O):
+    # double arithmetic; identical summation order except for the dangling-mass term of the source,
+    # tolerance 1e-13 absolute (values are <= 1)
+    for g, og, srcs in ((G, OG, (0, 63, 71)), (R12[0], R12[1], sources(R12[1], 2))):
+        for s in srcs:
+            pm = g.power_iteration(s, ALPHA, 100)
+            assert np.abs(pm - O.power_method(og, s, ALPHA, 100)).max() < 1e-13
+    gold = np.load(GOLD)
+    assert np.abs(G.power_iteration(0, ALPHA, 100) - gold["pm_0"]).max() < 1e-13
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_error_codes(pkg, G):
+    E = pkg._native
+    for call in (lambda: G.fora(-1, ALPHA, EPS, 1), lambda: G.fora(107, ALPHA, EPS, 1), lambda: G.fora(0, 1.5, EPS, 1),
+                 lambda: G.fora(0, ALPHA, 0.0, 1), lambda: G.forward_push(0, ALPHA, -1.0), lambda: G.fora_topk(0, ALPHA, EPS, 0, 1),
+                 lambda: G.fora_shard(0, ALPHA, EPS, 1, 3, 2), lambda: G.backward_all_pairs(ALPHA, 1e-3, -1, 5, 2)):
+        with pytest.raises(pkg.PPRError) as e:
+            call()
+        assert e.value.code == E.PPR_E_INVALID
+    G.fora(0, ALPHA, EPS, 1)                                   # the context stays usable after errors
