@@ -207,6 +207,10 @@ int32_t ppr_last_raw(ppr_graph* g, uint64_t* reserve_fx, uint64_t* residue_fx);
 int32_t ppr_push_trace_begin(ppr_graph* g, int32_t src, double alpha, double rmax);
 int32_t ppr_push_trace_step(ppr_graph* g, int32_t* frontier_out, int64_t cap, int64_t* count_out);
 
+/* Per-iteration timeline of the last push kernel (profiling aid): 6 uint64 per synchronous iteration =
+ * {t_start, t_after_phase_A, t_after_phase_B (GPU globaltimer, ns), frontier size, cumulative edges relaxed, mode}. */
+int32_t ppr_debug_timeline(ppr_graph* g, uint64_t* out, int64_t cap_entries, int64_t* count_out);
+
 /* Terminal vertex of walk `j` started at `start` (Monte_Carlo.random_walk / random_walk_no_zero_hop,
  * J/Monte_Carlo.java:60-133), for `count` consecutive walk indices starting at j0; runs the walk
  * kernel's device function one walk per thread. */

@@ -26,7 +26,7 @@ EXPORTS = [
     "ppr_graph_export_csc", "ppr_forward_push", "ppr_monte_carlo", "ppr_fora", "ppr_fora_topk", "ppr_topk",
     "ppr_power_iteration", "ppr_fora_batch", "ppr_backward_search", "ppr_backward_all_pairs", "ppr_pairs_count",
     "ppr_pairs_export", "ppr_pairs_destroy", "ppr_fora_shard", "ppr_monte_carlo_shard", "ppr_result_devptr",
-    "ppr_result_export", "ppr_last_raw", "ppr_push_trace_begin", "ppr_push_trace_step", "ppr_walk_terminals",
+    "ppr_result_export", "ppr_last_raw", "ppr_push_trace_begin", "ppr_push_trace_step", "ppr_walk_terminals", "ppr_debug_timeline",
     "ppr_rmat_generate", "ppr_version",
 ]
 
@@ -119,6 +119,7 @@ def load():
         "ppr_push_trace_begin": (i32, [vp, i32, f64, f64]),
         "ppr_push_trace_step": (i32, [vp, vp, i64, C.POINTER(i64)]),
         "ppr_walk_terminals": (i32, [vp, i32, i32, u64, i64, u64, u64, f64, i32, vp]),
+        "ppr_debug_timeline": (i32, [vp, vp, i64, C.POINTER(i64)]),
         "ppr_rmat_generate": (i32, [i64, i64, f64, f64, f64, u64, i32, i32, vp, vp]),
         "ppr_version": (C.c_char_p, []),
     }
@@ -339,6 +340,12 @@ class Graph:
                 break
             out.append(np.sort(buf[:cnt.value]))
         return out
+
+    def debug_timeline(self):
+        buf = np.zeros((4096, 6), np.uint64)
+        cnt = C.c_int64()
+        self.ctx.check(self.L.ppr_debug_timeline(self.h, _ptr(buf), 4096, C.byref(cnt)))
+        return buf[:cnt.value]
 
     def walk_terminals(self, start, restart, j0, count, seed, tag, alpha, no_zero_hop):
         out = np.zeros(max(count, 1), np.int32)

@@ -34,6 +34,8 @@ typedef unsigned long long ull;
 #define PUSH_SMALL_MAX 64   // degree <= this: warp-cooperative gather over 32 vertices
 #define PUSH_CHUNK 1024     // larger rows are cut into chunks of this many edges, one warp per chunk
 
+#define DBG_ITERS 4096
+#define DBG_FIELDS 6   // t_start, t_after_A, t_after_B (globaltimer ns), frontier size, cumulative edges, mode
 #define PUSH_THREADS 256
 #define WALK_THREADS 256
 
@@ -112,6 +114,8 @@ struct PushCtl {
     u32 src_dangling;  // 1 = the query source has no out-edges (result is {src: 1})
     u32 err_a;         // error raised during a phase A (kept apart from err so each flag is only read behind a barrier)
     u32 pad2;
+    u32 dbg_count;     // timeline entries written
+    u32 pad3;
     u64 pairs;         // all-pair backward search: (v, t) pairs written by the batch
     u64 pairs_needed;  // ... and the number that qualified (> capacity means the batch must be rerun)
 };
@@ -155,6 +159,7 @@ struct Workspace {
     double* out_f64;   // conversion buffer for downloads
     u32* hist;         // radix-select histograms
     i32* sel_ids; u64* sel_vals; i64 sel_cap;
+    u64* dbg;          // per-iteration timeline of the last push kernel: DBG_FIELDS u64 per iteration
     PushCtl* ctl;      // device
     PushCtl* ctl_host; // pinned mirror
     int coop_blocks;   // grid size of the cooperative kernels

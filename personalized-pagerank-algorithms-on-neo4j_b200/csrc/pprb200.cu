@@ -172,7 +172,7 @@ static void ws_free(Workspace& w) {
     cudaFree(w.s_pack); cudaFree(w.s_q); cudaFree(w.l_pack); cudaFree(w.l_q); cudaFree(w.chunks);
     cudaFree(w.ws_v); cudaFree(w.ws_begin); cudaFree(w.ws_inc); cudaFree(w.ws_rem);
     cudaFree(w.blk_a); cudaFree(w.blk_b); cudaFree(w.blk_c); cudaFree(w.out_f64); cudaFree(w.hist);
-    cudaFree(w.sel_ids); cudaFree(w.sel_vals); cudaFree(w.ctl);
+    cudaFree(w.sel_ids); cudaFree(w.sel_vals); cudaFree(w.ctl); cudaFree(w.dbg);
     if (w.ctl_host) cudaFreeHost(w.ctl_host);
     memset(&w, 0, sizeof w);
 }
@@ -202,6 +202,7 @@ static int32_t ws_alloc(ppr_ctx* ctx, Workspace& w, i64 n, i64 chunk_cap) {
     CUDA_TRY(dalloc(&w.hist, (size_t)9 * 256));
     w.sel_cap = std::min<i64>(n, (i64)1 << 22);
     CUDA_TRY(dalloc(&w.sel_ids, (size_t)w.sel_cap)); CUDA_TRY(dalloc(&w.sel_vals, (size_t)w.sel_cap));
+    CUDA_TRY(dalloc(&w.dbg, (size_t)DBG_ITERS * DBG_FIELDS));
     CUDA_TRY(dalloc(&w.ctl, 1));
     CUDA_TRY(cudaMemset(w.ctl, 0, sizeof(PushCtl)));
     CUDA_TRY(cudaHostAlloc((void**)&w.ctl_host, sizeof(PushCtl), cudaHostAllocDefault));
@@ -373,7 +374,7 @@ static void fill_push_args(PushArgs& A, ppr_graph* g, Workspace& w) {
     A.r = w.r; A.reserve = w.reserve; A.est = w.est; A.front[0] = w.front[0]; A.front[1] = w.front[1];
     A.s_pack = w.s_pack; A.s_q = w.s_q; A.l_pack = w.l_pack; A.l_q = w.l_q; A.chunks = w.chunks;
     A.ws_v = w.ws_v; A.ws_begin = w.ws_begin; A.ws_inc = w.ws_inc; A.ws_rem = w.ws_rem;
-    A.blk_a = w.blk_a; A.blk_b = w.blk_b; A.ctl = w.ctl;
+    A.blk_a = w.blk_a; A.blk_b = w.blk_b; A.ctl = w.ctl; A.dbg = w.dbg;
     A.prep_adds_push_part = 1;
 }
 
@@ -691,6 +692,21 @@ extern "C" int32_t ppr_last_raw(ppr_graph* g, uint64_t* reserve_fx, uint64_t* re
     if (reserve_fx) CUDA_TRY(cudaMemcpyAsync(reserve_fx, g->last_kind == 2 ? w.est : w.reserve, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (residue_fx) CUDA_TRY(cudaMemcpyAsync(residue_fx, w.r, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_debug_timeline(ppr_graph* g, uint64_t* out, int64_t cap_entries, int64_t* count_out) {
+    if (!g || !count_out) return PPR_E_INVALID;
+    ppr_ctx* ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    Workspace& w = g->ws[g->last_ws];
+    int32_t rc = read_ctl(g, w); if (rc) return rc;
+    i64 cnt = std::min<i64>(w.ctl_host->dbg_count, DBG_ITERS);
+    *count_out = cnt;
+    if (out && cnt) {
+        i64 c = std::min<i64>(cnt, cap_entries);
+        CUDA_TRY(cudaMemcpy(out, w.dbg, (size_t)c * DBG_FIELDS * sizeof(u64), cudaMemcpyDeviceToHost));
+    }
     return PPR_OK;
 }
 

@@ -40,6 +40,7 @@ struct PushArgs {
     u32* ws_v; u64* ws_begin; u64* ws_inc; u64* ws_rem;
     u64* blk_a; u64* blk_b;
     PushCtl* ctl;
+    u64* dbg;
     // query
     i32 src;
     u64 alpha_q64;
@@ -69,6 +70,8 @@ __device__ __forceinline__ void warp_append_u32(u32* list, u32* counter, bool pr
         if (pred) list[base + __popc(mask & lanemask_lt())] = value;
     }
 }
+
+__device__ __forceinline__ u64 globaltimer_ns() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 __device__ __forceinline__ u64 rmax_to_fx_dev(double rmax) {
     double x = __dmul_rn(rmax, FX_SCALE);
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
             ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
             ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
-            ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0;
+            ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0; ctl->dbg_count = 0;
         }
         grid.sync();
     }
@@ -433,11 +436,23 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
         push_scan(A, par, rmax_fx, gtid, gsize);
         grid.sync();
         for (;;) {
-            if (*(volatile u32*)&ctl->cnt[par] == 0) break;
+            const u32 fcnt = *(volatile u32*)&ctl->cnt[par];
+            if (fcnt == 0) break;
+            u64 t0 = 0, t1 = 0;
+            if (gtid == 0) t0 = globaltimer_ns();
             push_phase_a(A, par, gtid, gsize);
             grid.sync();
+            if (gtid == 0) t1 = globaltimer_ns();
             push_phase_b(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
             grid.sync();
+            if (gtid == 0) {
+                u32 k = ctl->dbg_count;
+                if (k < DBG_ITERS) {
+                    u64* d = A.dbg + (size_t)k * DBG_FIELDS;
+                    d[0] = t0; d[1] = t1; d[2] = globaltimer_ns(); d[3] = fcnt; d[4] = ctl->edges; d[5] = 0;
+                    ctl->dbg_count = k + 1;
+                }
+            }
             par ^= 1;
         }
         if (gtid == 0) {
