@@ -94,6 +94,12 @@ int32_t ppr_device_info(ppr_ctx* ctx, int32_t* sm_count, int64_t* total_mem, cha
  * rounds < max_rounds.  Defaults: walk_cost = 32, max_rounds = 64. */
 int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_rounds);
 
+/* Frontier-mode switch of the push kernels: an iteration whose frontier has at least this many out-edges
+ * scatters with plain reductions and the next frontier is found by a dense sweep; smaller frontiers use
+ * returning atomics and exact threshold-crossing detection.  Results are bit-identical either way.
+ * < 0 restores the default (n); 0 = always sweep; INT64_MAX = never sweep. */
+int32_t ppr_set_tuning(ppr_ctx* ctx, int64_t scan_threshold_edges);
+
 /* Measurement helpers (bench.py): CUDA events on the context's compute stream, the stream every kernel
  * of this library is launched on (after joining the download stream), and an L2 flush (a write of a
  * 256 MiB scratch buffer, larger than the 126 MB L2).  slot is 0..3. */

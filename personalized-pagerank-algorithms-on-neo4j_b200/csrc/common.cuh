@@ -32,7 +32,7 @@ typedef unsigned long long ull;
 
 // Forward-push work classes
 #define PUSH_SMALL_MAX 64   // degree <= this: warp-cooperative gather over 32 vertices
-#define PUSH_CHUNK 1024     // larger rows are cut into chunks of this many edges, one warp per chunk
+#define PUSH_CHUNK 256      // larger rows are cut into chunks of this many edges, one warp per chunk
 
 #define DBG_ITERS 4096
 #define DBG_FIELDS 6   // t_start, t_after_A, t_after_B (globaltimer ns), frontier size, cumulative edges, mode
@@ -93,6 +93,8 @@ struct PushCtl {
     u32 nl[2];         // staged large items
     u32 nchunks[2];    // chunk descriptors
     u64 dang[2];       // dangling mass headed for the source
+    u32 fcnt[2];       // vertices pushed by the iteration (both frontier modes)
+    u64 fedges[2];     // edges relaxed by the iteration
     // work counters
     u64 reserve_total; // sum of everything moved into reserve by pushes
     u64 pushes, edges, iters, rounds;
@@ -132,6 +134,7 @@ struct ppr_ctx {
     cudaEvent_t ev[8];
     double walk_cost;
     int max_rounds;
+    i64 scan_threshold;    // < 0: default (n)
 };
 
 struct DevGraph {

@@ -65,6 +65,7 @@ extern "C" int32_t ppr_init(int32_t device, ppr_ctx** out) {
     ctx->device = device;
     ctx->walk_cost = 32.0;
     ctx->max_rounds = 64;
+    ctx->scan_threshold = -1;
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
         delete ctx;
@@ -111,6 +112,12 @@ extern "C" int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_r
     if (!(walk_cost >= 0) || max_rounds < 1) return ctx_fail(ctx, PPR_E_INVALID, "ppr_set_balance: walk_cost >= 0, max_rounds >= 1");
     ctx->walk_cost = walk_cost;
     ctx->max_rounds = max_rounds;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_set_tuning(ppr_ctx* ctx, int64_t scan_threshold_edges) {
+    if (!ctx) return PPR_E_INVALID;
+    ctx->scan_threshold = scan_threshold_edges;
     return PPR_OK;
 }
 
@@ -376,6 +383,7 @@ static void fill_push_args(PushArgs& A, ppr_graph* g, Workspace& w) {
     A.ws_v = w.ws_v; A.ws_begin = w.ws_begin; A.ws_inc = w.ws_inc; A.ws_rem = w.ws_rem;
     A.blk_a = w.blk_a; A.blk_b = w.blk_b; A.ctl = w.ctl; A.dbg = w.dbg;
     A.prep_adds_push_part = 1;
+    A.scan_threshold = g->ctx->scan_threshold < 0 ? g->d.n : g->ctx->scan_threshold;
 }
 
 static cudaError_t launch_push(ppr_ctx* ctx, Workspace& w, PushArgs& A) {

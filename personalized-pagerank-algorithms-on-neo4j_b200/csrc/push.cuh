@@ -15,6 +15,12 @@
 // coalesced 128-byte neighbour loads.  Dangling vertices reduce their mass per CTA and one thread adds
 // it to r[source] (J/Forward_Push.java:101-115).
 //
+// Two ways to find the next frontier, chosen per iteration from the size of the current one:
+//   LIST mode (sparse frontiers): phase B uses the returning atomic and the crossing test above;
+//   SCAN mode (frontier edges >= scan_threshold, default n): phase B issues plain red.global.add.u64
+//            (no return value, no degree load, no append) and the next phase A sweeps r[] densely,
+//            capturing every vertex above threshold on the fly.  Both produce the same state bits.
+//
 // The whole query (all iterations, FORA's rmax-halving rounds and the walk-source scan) runs as ONE
 // cooperative persistent kernel: frontier sizes never travel to the host.  The same device functions
 // are also wrapped as plain kernels for the stepped/trace API used by the schedule tests.
@@ -53,6 +59,7 @@ struct PushArgs {
     int init;           // 1: reset state and seed r[src] = 1
     int zero_reserve_after_push;  // shard != 0 of a multi-GPU FORA: drop the push reserve before the walk prep
     int prep_adds_push_part;      // shard == 0
+    i64 scan_threshold;           // frontier edges >= this: next frontier is found by a dense sweep (SCAN mode)
 };
 
 #define PMODE_PUSH 0
@@ -97,35 +104,48 @@ __device__ void push_scan(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64
 }
 
 // --------------------------------------------------------------------------------- phase A
-__device__ void push_phase_a(const PushArgs& A, int par, i64 gtid, i64 gsize) {
+// Per-vertex capture shared by both frontier modes.  SCAN = true sweeps all vertices (coalesced reads of
+// r[] and the vertex table) and keeps those at or above threshold; SCAN = false walks the frontier list.
+template <bool SCAN>
+__device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize) {
     PushCtl* ctl = A.ctl;
-    const u32 cnt = *(volatile u32*)&ctl->cnt[par];
+    const i64 cnt = SCAN ? A.n : (i64)*(volatile u32*)&ctl->cnt[par];
     if (gtid == 0) {  // recycle the other parity's counters (last read before the preceding barrier)
         ctl->cnt[par ^ 1] = 0; ctl->ns[par ^ 1] = 0; ctl->nl[par ^ 1] = 0; ctl->nchunks[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
-        ctl->pushes += cnt;
+        ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0;
     }
     u64 edges_local = 0, resv_local = 0, dang_local = 0;
+    u32 pushed_local = 0;
     const u32* F = A.front[par];
     for (i64 base = 0; base < cnt; base += gsize) {
         i64 i = base + gtid;
         bool is_small = false, is_large = false;
         u64 pk = 0, q = 0;
         if (i < cnt) {
-            u32 v = F[i];
-            pk = A.out_vtx[v];
-            u32 d = vtx_deg(pk);
+            u32 v = SCAN ? (u32)i : F[i];
             u64 x = A.r[v];
-            u64 a = mulhi64(x, A.alpha_q64);
-            u64 y = x - a;
-            u64 left;
-            if (d == 0) { q = y; left = 0; dang_local += y; }
-            else { q = y / (u64)d; left = y - q * (u64)d; }
-            A.r[v] = left;
-            A.reserve[v] += a;
-            resv_local += a;
-            edges_local += d;
-            is_small = d > 0 && d <= PUSH_SMALL_MAX;
-            is_large = d > PUSH_SMALL_MAX;
+            bool take = true;
+            if (SCAN) {
+                take = false;
+                if (x) { pk = A.out_vtx[v]; take = x >= thr_fwd(rmax_fx, vtx_deg(pk)); }
+            } else {
+                pk = A.out_vtx[v];
+            }
+            if (take) {
+                u32 d = vtx_deg(pk);
+                u64 a = mulhi64(x, A.alpha_q64);
+                u64 y = x - a;
+                u64 left;
+                if (d == 0) { q = y; left = 0; dang_local += y; }
+                else { q = y / (u64)d; left = y - q * (u64)d; }
+                A.r[v] = left;
+                A.reserve[v] += a;
+                resv_local += a;
+                edges_local += d;
+                pushed_local += 1;
+                is_small = d > 0 && d <= PUSH_SMALL_MAX;
+                is_large = d > PUSH_SMALL_MAX;
+            }
         }
         // staged small items: warp-aggregated append of (pack, q)
         u32 mask = __ballot_sync(0xffffffffu, is_small);
@@ -147,21 +167,30 @@ __device__ void push_phase_a(const PushArgs& A, int par, i64 gtid, i64 gsize) {
     edges_local = warp_sum_u64(edges_local);
     resv_local = warp_sum_u64(resv_local);
     dang_local = warp_sum_u64(dang_local);
+    pushed_local = (u32)warp_sum_u64(pushed_local);
     if (lane_id() == 0) {
-        if (edges_local) atomicAdd((ull*)&ctl->edges, (ull)edges_local);
+        if (pushed_local) atomicAdd(&ctl->fcnt[par], pushed_local);
+        if (edges_local) atomicAdd((ull*)&ctl->fedges[par], (ull)edges_local);
         if (resv_local) atomicAdd((ull*)&ctl->reserve_total, (ull)resv_local);
         if (dang_local) atomicAdd((ull*)&ctl->dang[par], (ull)dang_local);
     }
 }
 
 // --------------------------------------------------------------------------------- phase B
-// One relaxed edge: add q to r[u] and detect the threshold crossing.
+// One relaxed edge.  LIST: returning atomic + crossing test; otherwise a fire-and-forget reduction.
+template <bool LIST>
 __device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32 u, u64 q) {
-    u64 old = atomicAdd((ull*)&A.r[u], (ull)q);
-    u64 th = thr_fwd(rmax_fx, __ldg(&A.out_deg[u]));
-    return old < th && old + q >= th;
+    if (LIST) {
+        u64 old = atomicAdd((ull*)&A.r[u], (ull)q);
+        u64 th = thr_fwd(rmax_fx, __ldg(&A.out_deg[u]));
+        return old < th && old + q >= th;
+    } else {
+        atomicAdd((ull*)&A.r[u], (ull)q);  // result unused: compiles to RED.E.ADD.64
+        return false;
+    }
 }
 
+template <bool LIST>
 __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u64* sm_excl /*[warps][32]*/,
                              u64* sm_beg, u64* sm_q) {
     PushCtl* ctl = A.ctl;
@@ -200,14 +229,14 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
 #pragma unroll
                 for (int s = 16; s > 0; s >>= 1) { int p = o + s; if ((u32)w_excl[p] <= e) o = p; }
                 u = (u32)__ldg(&A.col_idx[w_beg[o] + e]);
-                cross = relax_edge(A, rmax_fx, u, w_q[o]);
+                cross = relax_edge<LIST>(A, rmax_fx, u, w_q[o]);
             }
-            warp_append_u32(next, next_cnt, cross, u);
+            if (LIST) warp_append_u32(next, next_cnt, cross, u);
         }
         __syncwarp();
     }
 
-    // (2) long rows: one warp per PUSH_CHUNK-edge chunk
+    // (2) long rows: one warp per PUSH_CHUNK-edge chunk, four independent edges per lane in flight
     for (i64 c = gwarp; c < nch; c += nwarps) {
         uint2 desc = A.chunks[c];
         u64 pk = A.l_pack[desc.x];
@@ -216,28 +245,31 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
         u32 off = desc.y * PUSH_CHUNK;
         u32 len = min((u32)PUSH_CHUNK, d - off);
         const i32* row = A.col_idx + vtx_begin(pk) + off;
-        for (u32 eb = 0; eb < len; eb += 64) {  // two independent edges per lane in flight
-            u32 e0 = eb + lane, e1 = eb + 32 + lane;
-            u32 u0 = 0, u1 = 0;
-            bool c0 = false, c1 = false;
-            if (e0 < len) u0 = (u32)__ldg(&row[e0]);
-            if (e1 < len) u1 = (u32)__ldg(&row[e1]);
-            if (e0 < len) c0 = relax_edge(A, rmax_fx, u0, q);
-            if (e1 < len) c1 = relax_edge(A, rmax_fx, u1, q);
-            warp_append_u32(next, next_cnt, c0, u0);
-            warp_append_u32(next, next_cnt, c1, u1);
+        for (u32 eb = 0; eb < len; eb += 128) {
+            u32 u[4];
+            bool cr[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { u32 e = eb + 32 * k + lane; u[k] = e < len ? (u32)__ldg(&row[e]) : 0xffffffffu; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], q) : false;
+            if (LIST) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) warp_append_u32(next, next_cnt, cr[k], u[k]);
+            }
         }
     }
 
-    // (3) dangling mass -> source (J/Forward_Push.java:101-113)
+    // (3) dangling mass -> source (J/Forward_Push.java:101-113) and the iteration's bookkeeping
     if (gtid == 0) {
         u64 dsum = *(volatile u64*)&ctl->dang[par];
         if (dsum) {
             u64 old = atomicAdd((ull*)&A.r[A.src], (ull)dsum);
             u64 th = thr_fwd(rmax_fx, A.out_deg[A.src]);
-            if (old < th && old + dsum >= th) { u32 idx = atomicAdd(next_cnt, 1u); next[idx] = (u32)A.src; }
+            if (LIST && old < th && old + dsum >= th) { u32 idx = atomicAdd(next_cnt, 1u); next[idx] = (u32)A.src; }
         }
         ctl->iters += 1;
+        ctl->pushes += *(volatile u32*)&ctl->fcnt[par];
+        ctl->edges += *(volatile u64*)&ctl->fedges[par];
     }
 }
 
@@ -398,7 +430,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
         for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
         if (gtid == 0) {
             ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
-            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
+            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
             ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
             ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0; ctl->dbg_count = 0;
@@ -409,7 +441,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
         ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0;
         if (!A.init) {  // top-k round: host supplied the round's rmax; counters of both parities must be clean
             ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
-            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
+            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
         }
     }
@@ -431,28 +463,37 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
     grid.sync();
 
     int par = 0;
-    for (;;) {
+    for (;;) {  // rounds (FORA: rmax halves between rounds)
         const u64 rmax_fx = *(volatile u64*)&ctl->rmax_fx;
-        push_scan(A, par, rmax_fx, gtid, gsize);
-        grid.sync();
+        bool have_list = false;  // a round starts with a dense sweep: rmax just changed
         for (;;) {
-            const u32 fcnt = *(volatile u32*)&ctl->cnt[par];
-            if (fcnt == 0) break;
             u64 t0 = 0, t1 = 0;
             if (gtid == 0) t0 = globaltimer_ns();
-            push_phase_a(A, par, gtid, gsize);
+            if (have_list) {
+                if (*(volatile u32*)&ctl->cnt[par] == 0) break;
+                push_phase_a<false>(A, par, rmax_fx, gtid, gsize);
+            } else {
+                push_phase_a<true>(A, par, rmax_fx, gtid, gsize);
+            }
             grid.sync();
+            const u32 fcnt = *(volatile u32*)&ctl->fcnt[par];
+            const u64 fedges = *(volatile u64*)&ctl->fedges[par];
+            if (fcnt == 0) break;
+            const bool next_scan = (i64)fedges >= A.scan_threshold;
             if (gtid == 0) t1 = globaltimer_ns();
-            push_phase_b(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
+            if (next_scan) push_phase_b<false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
+            else push_phase_b<true>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
             grid.sync();
             if (gtid == 0) {
                 u32 k = ctl->dbg_count;
                 if (k < DBG_ITERS) {
                     u64* d = A.dbg + (size_t)k * DBG_FIELDS;
-                    d[0] = t0; d[1] = t1; d[2] = globaltimer_ns(); d[3] = fcnt; d[4] = ctl->edges; d[5] = 0;
+                    d[0] = t0; d[1] = t1; d[2] = globaltimer_ns(); d[3] = fcnt; d[4] = ctl->edges;
+                    d[5] = (have_list ? 0 : 1) | (next_scan ? 2 : 0);
                     ctl->dbg_count = k + 1;
                 }
             }
+            have_list = !next_scan;
             par ^= 1;
         }
         if (gtid == 0) {
@@ -471,6 +512,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
         }
         grid.sync();
         if (*(volatile u32*)&ctl->cont == 0) break;
+        // parity is kept: the iteration that ended the round left this parity's counters at zero
     }
 
     if (A.mode == PMODE_PUSH) return;
@@ -489,7 +531,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_init(PushArgs A) {
     for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
     if (gtid == 0) {
         ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
-        ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
+        ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
         ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
         ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
         ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0;
@@ -508,12 +550,12 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_scan(PushArgs A, int par)
 }
 __global__ void __launch_bounds__(PUSH_THREADS) k_step_a(PushArgs A, int par) {
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
-    push_phase_a(A, par, gtid, gsize);
+    push_phase_a<false>(A, par, A.ctl->rmax_fx, gtid, gsize);
 }
 __global__ void __launch_bounds__(PUSH_THREADS) k_step_b(PushArgs A, int par) {
     __shared__ u64 sm_excl[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
-    push_phase_b(A, par, A.ctl->rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
+    push_phase_b<true>(A, par, A.ctl->rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
 }

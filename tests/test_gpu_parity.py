@@ -203,6 +203,24 @@ def test_fora_balance_knobs(pkg, ctx, G, OG, O):
         ctx.set_balance(32.0, 64)
 
 
+def test_frontier_modes_give_identical_bits(ctx, G, OG, R12, O):
+    # LIST (returning atomics + crossing test) and SCAN (plain reductions + dense sweep) frontier discovery
+    try:
+        for thr in (0, 1 << 62, 64, -1):
+            ctx.set_tuning(thr)
+            for g, og, srcs in ((G, OG, (0, 63, 100)), (R12[0], R12[1], sources(R12[1], 2))):
+                for s in srcs:
+                    check_fora(g, og, O, s, EPS)
+                    g.forward_push(s, ALPHA, 1e-7, want_residue=False)
+                    raw_res, raw_r = g.last_raw()
+                    ores, orr, ost = O.b_forward_push(og, s, ALPHA, 1e-7)
+                    assert np.array_equal(raw_res, ores) and np.array_equal(raw_r, orr), (thr, s)
+                    ids, _, st = g.fora_topk(s, ALPHA, EPS, K, SEED)
+                    assert np.array_equal(g.last_raw(False)[0], O.b_fora_topk(og, s, ALPHA, EPS, K, SEED)[0])
+    finally:
+        ctx.set_tuning(-1)
+
+
 def test_fora_guarantee(G, OG, R12, O):
     # FORA's guarantee (Dissertation p.14): |est - pi| <= eps * pi for every pi > delta = 1/n, w.p. 1 - 1/n.
     # Tolerance: exactly eps = 0.5 relative; the exact answer is the power iteration run to 1e-17.
