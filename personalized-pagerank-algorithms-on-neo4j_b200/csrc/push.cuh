@@ -107,7 +107,7 @@ __device__ void push_scan(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64
 // Per-vertex capture shared by both frontier modes.  SCAN = true sweeps all vertices (coalesced reads of
 // r[] and the vertex table) and keeps those at or above threshold; SCAN = false walks the frontier list.
 template <bool SCAN>
-__device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize) {
+__device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u32* sm_cnt /*16 words, 8-byte aligned*/) {
     PushCtl* ctl = A.ctl;
     const i64 cnt = SCAN ? A.n : (i64)*(volatile u32*)&ctl->cnt[par];
     if (gtid == 0) {  // recycle the other parity's counters (last read before the preceding barrier)
@@ -117,10 +117,16 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     u64 edges_local = 0, resv_local = 0, dang_local = 0;
     u32 pushed_local = 0;
     const u32* F = A.front[par];
-    for (i64 base = 0; base < cnt; base += gsize) {
-        i64 i = base + gtid;
+    // One tile = blockDim consecutive items per CTA.  Staging slots are claimed with shared-memory
+    // atomics inside the tile and ONE global atomic per counter per tile: a global counter bumped once
+    // per warp serialises at ~1 op/clk in its L2 slice and used to dominate this phase.
+    for (i64 tile = (i64)blockIdx.x * blockDim.x; tile < cnt; tile += gsize) {
+        if (threadIdx.x < 3) sm_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        i64 i = tile + threadIdx.x;
         bool is_small = false, is_large = false;
         u64 pk = 0, q = 0;
+        u32 loc = 0, loc_c = 0, nch = 0;
         if (i < cnt) {
             u32 v = SCAN ? (u32)i : F[i];
             u64 x = A.r[v];
@@ -145,34 +151,53 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
                 pushed_local += 1;
                 is_small = d > 0 && d <= PUSH_SMALL_MAX;
                 is_large = d > PUSH_SMALL_MAX;
+                nch = (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
             }
         }
-        // staged small items: warp-aggregated append of (pack, q)
         u32 mask = __ballot_sync(0xffffffffu, is_small);
         if (mask) {
             u32 leader = __ffs(mask) - 1, b = 0;
-            if (lane_id() == leader) b = atomicAdd(&ctl->ns[par], (u32)__popc(mask));
+            if (lane_id() == leader) b = atomicAdd(&sm_cnt[0], (u32)__popc(mask));
             b = __shfl_sync(0xffffffffu, b, leader);
-            if (is_small) { u32 slot = b + __popc(mask & lanemask_lt()); A.s_pack[slot] = pk; A.s_q[slot] = q; }
+            loc = b + __popc(mask & lanemask_lt());
         }
+        if (is_large) { loc = atomicAdd(&sm_cnt[1], 1u); loc_c = atomicAdd(&sm_cnt[2], nch); }
+        __syncthreads();
+        if (threadIdx.x < 3 && sm_cnt[threadIdx.x]) {
+            u32* gc = threadIdx.x == 0 ? &ctl->ns[par] : threadIdx.x == 1 ? &ctl->nl[par] : &ctl->nchunks[par];
+            sm_cnt[4 + threadIdx.x] = atomicAdd(gc, sm_cnt[threadIdx.x]);
+        }
+        __syncthreads();
+        if (is_small) { u32 slot = sm_cnt[4] + loc; A.s_pack[slot] = pk; A.s_q[slot] = q; }
         if (is_large) {
-            u32 slot = atomicAdd(&ctl->nl[par], 1u);
+            u32 slot = sm_cnt[5] + loc;
             A.l_pack[slot] = pk; A.l_q[slot] = q;
-            u32 d = vtx_deg(pk);
-            u32 nch = (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
-            u32 cb = atomicAdd(&ctl->nchunks[par], nch);
+            u32 cb = sm_cnt[6] + loc_c;
             for (u32 c = 0; c < nch; c++) A.chunks[cb + c] = make_uint2(slot, c);
         }
+        __syncthreads();
     }
+    // CTA-level totals first (shared-memory atomics), then one global atomic per counter per CTA
+    u64* sm_acc = reinterpret_cast<u64*>(sm_cnt + 8);
+    __syncthreads();
+    if (threadIdx.x < 4) sm_acc[threadIdx.x] = 0;
+    __syncthreads();
     edges_local = warp_sum_u64(edges_local);
     resv_local = warp_sum_u64(resv_local);
     dang_local = warp_sum_u64(dang_local);
-    pushed_local = (u32)warp_sum_u64(pushed_local);
+    u64 pushed64 = warp_sum_u64((u64)pushed_local);
     if (lane_id() == 0) {
-        if (pushed_local) atomicAdd(&ctl->fcnt[par], pushed_local);
-        if (edges_local) atomicAdd((ull*)&ctl->fedges[par], (ull)edges_local);
-        if (resv_local) atomicAdd((ull*)&ctl->reserve_total, (ull)resv_local);
-        if (dang_local) atomicAdd((ull*)&ctl->dang[par], (ull)dang_local);
+        if (pushed64) atomicAdd((ull*)&sm_acc[0], (ull)pushed64);
+        if (edges_local) atomicAdd((ull*)&sm_acc[1], (ull)edges_local);
+        if (resv_local) atomicAdd((ull*)&sm_acc[2], (ull)resv_local);
+        if (dang_local) atomicAdd((ull*)&sm_acc[3], (ull)dang_local);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sm_acc[0]) atomicAdd(&ctl->fcnt[par], (u32)sm_acc[0]);
+        if (sm_acc[1]) atomicAdd((ull*)&ctl->fedges[par], (ull)sm_acc[1]);
+        if (sm_acc[2]) atomicAdd((ull*)&ctl->reserve_total, (ull)sm_acc[2]);
+        if (sm_acc[3]) atomicAdd((ull*)&ctl->dang[par], (ull)sm_acc[3]);
     }
 }
 
@@ -205,11 +230,14 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     u64* w_beg = sm_beg + wib * 32;
     u64* w_q = sm_q + wib * 32;
 
-    // (1) short rows: 32 vertices per warp, lanes sweep the concatenated edge list
-    for (i64 wbase = gwarp * 32; wbase < ns; wbase += nwarps * 32) {
+    // (1) short rows: up to 32 vertices per warp, lanes sweep the concatenated edge list.  When the
+    // frontier is small the batch shrinks so that every warp of the grid gets some rows (a warp works
+    // through its batch serially, one dependent atomic round trip per 32 edges).
+    const i64 bw = min((i64)32, max((i64)1, ((i64)ns + nwarps - 1) / nwarps));
+    for (i64 wbase = gwarp * bw; wbase < ns; wbase += nwarps * bw) {
         i64 item = wbase + lane;
         u64 pk = 0, q = 0;
-        if (item < ns) { pk = A.s_pack[item]; q = A.s_q[item]; }
+        if (lane < bw && item < ns) { pk = A.s_pack[item]; q = A.s_q[item]; }
         u32 d = vtx_deg(pk);
         u32 incl = d;
 #pragma unroll
@@ -422,6 +450,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
     __shared__ u64 sm_excl[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
+    __shared__ __align__(8) u32 sm_cnt[16];
     PushCtl* ctl = A.ctl;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 gsize = (i64)gridDim.x * blockDim.x;
@@ -471,9 +500,9 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
             if (gtid == 0) t0 = globaltimer_ns();
             if (have_list) {
                 if (*(volatile u32*)&ctl->cnt[par] == 0) break;
-                push_phase_a<false>(A, par, rmax_fx, gtid, gsize);
+                push_phase_a<false>(A, par, rmax_fx, gtid, gsize, sm_cnt);
             } else {
-                push_phase_a<true>(A, par, rmax_fx, gtid, gsize);
+                push_phase_a<true>(A, par, rmax_fx, gtid, gsize, sm_cnt);
             }
             grid.sync();
             const u32 fcnt = *(volatile u32*)&ctl->fcnt[par];
@@ -550,7 +579,8 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_scan(PushArgs A, int par)
 }
 __global__ void __launch_bounds__(PUSH_THREADS) k_step_a(PushArgs A, int par) {
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
-    push_phase_a<false>(A, par, A.ctl->rmax_fx, gtid, gsize);
+    __shared__ __align__(8) u32 sm_cnt[16];
+    push_phase_a<false>(A, par, A.ctl->rmax_fx, gtid, gsize, sm_cnt);
 }
 __global__ void __launch_bounds__(PUSH_THREADS) k_step_b(PushArgs A, int par) {
     __shared__ u64 sm_excl[(PUSH_THREADS / 32) * 32];
