@@ -207,7 +207,7 @@ def b_monte_carlo(g, s, alpha, eps, seed, shard=0, nshards=1):
     return counts, {"walks": int(w), "omega": float(om[0]), "steps": int(steps[0])}
 
 
-def b_fora(g, s, alpha, eps, seed, walk_cost=32.0, max_rounds=64, restart_at_source=False, shard=0, nshards=1):
+def b_fora(g, s, alpha, eps, seed, walk_cost=6.0, max_rounds=64, restart_at_source=False, shard=0, nshards=1):
     out, st = np.zeros(g.n, np.uint64), np.zeros(9, np.int64)
     lib().orc_b_fora(*g.args(), s, alpha, eps, seed, walk_cost, max_rounds, int(restart_at_source), shard, nshards, out, st)
     return out, dict(zip(_B_STATS, map(int, st)))
