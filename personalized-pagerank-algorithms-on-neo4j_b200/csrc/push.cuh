@@ -78,6 +78,23 @@ __device__ __forceinline__ void warp_append_u32(u32* list, u32* counter, bool pr
     }
 }
 
+// Four predicated values per lane, one counter round trip for the whole warp.
+__device__ __forceinline__ void warp_append4_u32(u32* list, u32* counter, const bool (&pred)[4], const u32 (&value)[4]) {
+    u32 m[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { m[k] = __ballot_sync(0xffffffffu, pred[k]); tot += __popc(m[k]); }
+    if (tot) {
+        u32 base = 0;
+        if (lane_id() == 0) base = atomicAdd(counter, tot);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (pred[k]) list[base + __popc(m[k] & lanemask_lt())] = value[k];
+            base += __popc(m[k]);
+        }
+    }
+}
+
 __device__ __forceinline__ u64 globaltimer_ns() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 __device__ __forceinline__ u64 rmax_to_fx_dev(double rmax) {
@@ -117,63 +134,78 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     u64 edges_local = 0, resv_local = 0, dang_local = 0;
     u32 pushed_local = 0;
     const u32* F = A.front[par];
-    // One tile = blockDim consecutive items per CTA.  Staging slots are claimed with shared-memory
-    // atomics inside the tile and ONE global atomic per counter per tile: a global counter bumped once
-    // per warp serialises at ~1 op/clk in its L2 slice and used to dominate this phase.
-    for (i64 tile = (i64)blockIdx.x * blockDim.x; tile < cnt; tile += gsize) {
+    // One tile = PA_ITEMS * blockDim consecutive items per CTA.  Staging slots are claimed with
+    // shared-memory atomics inside the tile and ONE global atomic per counter per tile: a global counter
+    // bumped once per warp serialises at ~1 op/clk in its L2 slice and used to dominate this phase.
+    constexpr int PA_ITEMS = 4;
+    const i64 tile_span = (i64)blockDim.x * PA_ITEMS;
+    for (i64 tile = (i64)blockIdx.x * tile_span; tile < cnt; tile += (i64)gridDim.x * tile_span) {
         if (threadIdx.x < 3) sm_cnt[threadIdx.x] = 0;
         __syncthreads();
-        i64 i = tile + threadIdx.x;
-        bool is_small = false, is_large = false;
-        u64 pk = 0, q = 0;
-        u32 loc = 0, loc_c = 0, nch = 0;
-        if (i < cnt) {
-            u32 v = SCAN ? (u32)i : F[i];
-            u64 x = A.r[v];
-            bool take = true;
-            if (SCAN) {
-                take = false;
-                if (x) { pk = A.out_vtx[v]; take = x >= thr_fwd(rmax_fx, vtx_deg(pk)); }
-            } else {
-                pk = A.out_vtx[v];
-            }
-            if (take) {
-                u32 d = vtx_deg(pk);
-                u64 a = mulhi64(x, A.alpha_q64);
-                u64 y = x - a;
-                u64 left;
-                if (d == 0) { q = y; left = 0; dang_local += y; }
-                else { q = y / (u64)d; left = y - q * (u64)d; }
-                A.r[v] = left;
-                A.reserve[v] += a;
-                resv_local += a;
-                edges_local += d;
-                pushed_local += 1;
-                is_small = d > 0 && d <= PUSH_SMALL_MAX;
-                is_large = d > PUSH_SMALL_MAX;
-                nch = (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
+        u64 pk[PA_ITEMS], q[PA_ITEMS];
+        u32 loc[PA_ITEMS], loc_c[PA_ITEMS];
+        u32 cls[PA_ITEMS];  // 0 none, 1 small, 2 large
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) {
+            i64 i = tile + (i64)k * blockDim.x + threadIdx.x;
+            pk[k] = 0; q[k] = 0; cls[k] = 0; loc[k] = 0; loc_c[k] = 0;
+            if (i < cnt) {
+                u32 v = SCAN ? (u32)i : F[i];
+                u64 x = A.r[v];
+                bool take = true;
+                if (SCAN) {
+                    take = false;
+                    if (x) { pk[k] = A.out_vtx[v]; take = x >= thr_fwd(rmax_fx, vtx_deg(pk[k])); }
+                } else {
+                    pk[k] = A.out_vtx[v];
+                }
+                if (take) {
+                    u32 d = vtx_deg(pk[k]);
+                    u64 a = mulhi64(x, A.alpha_q64);
+                    u64 y = x - a;
+                    u64 left;
+                    if (d == 0) { q[k] = y; left = 0; dang_local += y; }
+                    else { q[k] = y / (u64)d; left = y - q[k] * (u64)d; }
+                    A.r[v] = left;
+                    A.reserve[v] += a;
+                    resv_local += a;
+                    edges_local += d;
+                    pushed_local += 1;
+                    cls[k] = d == 0 ? 0u : (d <= PUSH_SMALL_MAX ? 1u : 2u);
+                }
             }
         }
-        u32 mask = __ballot_sync(0xffffffffu, is_small);
-        if (mask) {
-            u32 leader = __ffs(mask) - 1, b = 0;
-            if (lane_id() == leader) b = atomicAdd(&sm_cnt[0], (u32)__popc(mask));
-            b = __shfl_sync(0xffffffffu, b, leader);
-            loc = b + __popc(mask & lanemask_lt());
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) {
+            u32 mask = __ballot_sync(0xffffffffu, cls[k] == 1);
+            if (mask) {
+                u32 leader = __ffs(mask) - 1, b = 0;
+                if (lane_id() == leader) b = atomicAdd(&sm_cnt[0], (u32)__popc(mask));
+                b = __shfl_sync(0xffffffffu, b, leader);
+                if (cls[k] == 1) loc[k] = b + __popc(mask & lanemask_lt());
+            }
+            if (cls[k] == 2) {
+                u32 nch = (vtx_deg(pk[k]) + PUSH_CHUNK - 1) / PUSH_CHUNK;
+                loc[k] = atomicAdd(&sm_cnt[1], 1u);
+                loc_c[k] = atomicAdd(&sm_cnt[2], nch);
+            }
         }
-        if (is_large) { loc = atomicAdd(&sm_cnt[1], 1u); loc_c = atomicAdd(&sm_cnt[2], nch); }
         __syncthreads();
         if (threadIdx.x < 3 && sm_cnt[threadIdx.x]) {
             u32* gc = threadIdx.x == 0 ? &ctl->ns[par] : threadIdx.x == 1 ? &ctl->nl[par] : &ctl->nchunks[par];
             sm_cnt[4 + threadIdx.x] = atomicAdd(gc, sm_cnt[threadIdx.x]);
         }
         __syncthreads();
-        if (is_small) { u32 slot = sm_cnt[4] + loc; A.s_pack[slot] = pk; A.s_q[slot] = q; }
-        if (is_large) {
-            u32 slot = sm_cnt[5] + loc;
-            A.l_pack[slot] = pk; A.l_q[slot] = q;
-            u32 cb = sm_cnt[6] + loc_c;
-            for (u32 c = 0; c < nch; c++) A.chunks[cb + c] = make_uint2(slot, c);
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) {
+            if (cls[k] == 1) { u32 slot = sm_cnt[4] + loc[k]; A.s_pack[slot] = pk[k]; A.s_q[slot] = q[k]; }
+            if (cls[k] == 2) {
+                u32 slot = sm_cnt[5] + loc[k];
+                A.l_pack[slot] = pk[k]; A.l_q[slot] = q[k];
+                u32 cb = sm_cnt[6] + loc_c[k];
+                u32 nch = (vtx_deg(pk[k]) + PUSH_CHUNK - 1) / PUSH_CHUNK;
+                for (u32 c = 0; c < nch; c++) A.chunks[cb + c] = make_uint2(slot, c);
+            }
         }
         __syncthreads();
     }
@@ -248,18 +280,26 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
         w_beg[lane] = vtx_begin(pk) - excl;  // edge address of concatenated position e is w_beg[owner] + e
         w_q[lane] = q;
         __syncwarp();
-        for (u32 eb = 0; eb < total; eb += 32) {
-            u32 e = eb + lane;
-            bool cross = false;
-            u32 u = 0;
-            if (e < total) {
-                int o = 0;
+        for (u32 eb = 0; eb < total; eb += 128) {  // four independent edges per lane in flight
+            u32 u[4];
+            u64 qq[4];
+            bool cr[4];
 #pragma unroll
-                for (int s = 16; s > 0; s >>= 1) { int p = o + s; if ((u32)w_excl[p] <= e) o = p; }
-                u = (u32)__ldg(&A.col_idx[w_beg[o] + e]);
-                cross = relax_edge<LIST>(A, rmax_fx, u, w_q[o]);
+            for (int k = 0; k < 4; k++) {
+                u32 e = eb + 32 * k + lane;
+                u[k] = 0xffffffffu;
+                qq[k] = 0;
+                if (e < total) {
+                    int o = 0;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) { int p = o + s; if ((u32)w_excl[p] <= e) o = p; }
+                    u[k] = (u32)__ldg(&A.col_idx[w_beg[o] + e]);
+                    qq[k] = w_q[o];
+                }
             }
-            if (LIST) warp_append_u32(next, next_cnt, cross, u);
+#pragma unroll
+            for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], qq[k]) : false;
+            if (LIST) warp_append4_u32(next, next_cnt, cr, u);
         }
         __syncwarp();
     }
@@ -280,10 +320,7 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
             for (int k = 0; k < 4; k++) { u32 e = eb + 32 * k + lane; u[k] = e < len ? (u32)__ldg(&row[e]) : 0xffffffffu; }
 #pragma unroll
             for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], q) : false;
-            if (LIST) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) warp_append_u32(next, next_cnt, cr[k], u[k]);
-            }
+            if (LIST) warp_append4_u32(next, next_cnt, cr, u);
         }
     }
 
