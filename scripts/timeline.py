@@ -24,6 +24,9 @@ for s in srcs[2:]:
     print(" it   frontier      edges    A_us    B_us  mode  Medges/s")
     for i, (t0, t1, t2, f, e, mode) in enumerate(tl):
         de = e - prev_e; prev_e = e
-        print("%3d %10d %10d %7.1f %7.1f %4d %9.1f" % (i, f, de, (t1 - t0) / 1e3, (t2 - t1) / 1e3, mode, de / max(t2 - t1, 1) * 1e3))
+        extra = ""
+        if mode >> 8:
+            extra = "  warp busy mean %.1f us max %.1f us" % (((mode >> 8) & ((1 << 28) - 1)) / 1e3, (mode >> 36) / 1e3)
+        print("%3d %10d %10d %7.1f %7.1f %4d %9.1f%s" % (i, f, de, (t1 - t0) / 1e3, (t2 - t1) / 1e3, mode & 255, de / max(t2 - t1, 1) * 1e3, extra))
     tot = (tl[-1, 2] - tl[0, 0]) / 1e6
     print("sum A %.3f ms, sum B %.3f ms, span %.3f ms" % ((tl[:, 1] - tl[:, 0]).sum() / 1e6, (tl[:, 2] - tl[:, 1]).sum() / 1e6, tot))
