@@ -36,7 +36,6 @@ typedef unsigned long long ull;
 
 #define DBG_ITERS 4096
 #define DBG_FIELDS 6   // t_start, t_after_A, t_after_B (globaltimer ns), frontier size, cumulative edges, mode
-#define PUSH_GRAB 2        // work units taken per dispenser atomic in phase B
 #define PUSH_THREADS 256
 #define WALK_THREADS 256
 
@@ -96,7 +95,6 @@ struct PushCtl {
     u64 dang[2];       // dangling mass headed for the source
     u32 fcnt[2];       // vertices pushed by the iteration (both frontier modes)
     u64 fedges[2];     // edges relaxed by the iteration
-    u32 work[2];       // phase-B work-unit dispenser
     // work counters
     u64 reserve_total; // sum of everything moved into reserve by pushes
     u64 pushes, edges, iters, rounds;
@@ -118,7 +116,6 @@ struct PushCtl {
     u32 src_dangling;  // 1 = the query source has no out-edges (result is {src: 1})
     u32 err_a;         // error raised during a phase A (kept apart from err so each flag is only read behind a barrier)
     u32 pad2;
-    u64 prof_sum, prof_max;  // diagnostic builds (-DPUSH_PROFILE_WARPS): per-warp busy time of phase B
     u32 dbg_count;     // timeline entries written
     u32 pad3;
     u64 pairs;         // all-pair backward search: (v, t) pairs written by the batch

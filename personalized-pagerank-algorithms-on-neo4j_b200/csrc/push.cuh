@@ -129,7 +129,7 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     const i64 cnt = SCAN ? A.n : (i64)*(volatile u32*)&ctl->cnt[par];
     if (gtid == 0) {  // recycle the other parity's counters (last read before the preceding barrier)
         ctl->cnt[par ^ 1] = 0; ctl->ns[par ^ 1] = 0; ctl->nl[par ^ 1] = 0; ctl->nchunks[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
-        ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0; ctl->work[par ^ 1] = 0;
+        ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0;
     }
     u64 edges_local = 0, resv_local = 0, dang_local = 0;
     u32 pushed_local = 0;
@@ -258,96 +258,72 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     const int wib = threadIdx.x >> 5;
     u32* next = A.front[par ^ 1];
     u32* next_cnt = &ctl->cnt[par ^ 1];
-#ifdef PUSH_PROFILE_WARPS
-    const u64 wt0 = globaltimer_ns();
-#endif
     u64* w_excl = sm_excl + wib * 32;
     u64* w_beg = sm_beg + wib * 32;
     u64* w_q = sm_q + wib * 32;
 
-    // Work units: [0, nb) are batches of bw short rows (lanes sweep the concatenated edge list of the
-    // batch), [nb, nb + nch) are PUSH_CHUNK-edge chunks of long rows.  When the frontier is small the
-    // batch width shrinks so that every warp of the grid gets some rows.  Units are handed out
-    // dynamically (one atomic per PUSH_GRAB units, fetched one round ahead): with a static split the
-    // slowest warp of a dense iteration ran 1.4x longer than the mean (skewed batch sizes).
+    // (1) short rows: up to 32 vertices per warp, lanes sweep the concatenated edge list.  When the
+    // frontier is small the batch shrinks so that every warp of the grid gets some rows (a warp works
+    // through its batch serially, one dependent atomic round trip per 32 edges).
     const i64 bw = min((i64)32, max((i64)1, ((i64)ns + nwarps - 1) / nwarps));
-    const u32 nb = (u32)((ns + bw - 1) / bw);
-    const u32 units = nb + nch;
-    u32* work = &ctl->work[par];
-    u32 nxt = 0;
-    if (lane == 0) nxt = atomicAdd(work, (u32)PUSH_GRAB);
-    for (;;) {
-        const u32 first = __shfl_sync(0xffffffffu, nxt, 0);
-        if (first >= units) break;
-        if (lane == 0) nxt = atomicAdd(work, (u32)PUSH_GRAB);  // prefetch the next grab; consumed next round
-        const u32 last = min(units, first + PUSH_GRAB);
-        for (u32 unit = first; unit < last; unit++) {
-            if (unit < nb) {
-                // (1) short rows
-                i64 item = (i64)unit * bw + lane;
-                u64 pk = 0, q = 0;
-                if (lane < bw && item < ns) { pk = A.s_pack[item]; q = A.s_q[item]; }
-                u32 d = vtx_deg(pk);
-                u32 incl = d;
+    for (i64 wbase = gwarp * bw; wbase < ns; wbase += nwarps * bw) {
+        i64 item = wbase + lane;
+        u64 pk = 0, q = 0;
+        if (lane < bw && item < ns) { pk = A.s_pack[item]; q = A.s_q[item]; }
+        u32 d = vtx_deg(pk);
+        u32 incl = d;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                u32 excl = incl - d;
-                u32 total = __shfl_sync(0xffffffffu, incl, 31);
-                w_excl[lane] = excl;
-                w_beg[lane] = vtx_begin(pk) - excl;  // edge address of concatenated position e is w_beg[owner] + e
-                w_q[lane] = q;
-                __syncwarp();
-                for (u32 eb = 0; eb < total; eb += 128) {  // four independent edges per lane in flight
-                    u32 u[4];
-                    u64 qq[4];
-                    bool cr[4];
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        u32 excl = incl - d;
+        u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        w_excl[lane] = excl;
+        w_beg[lane] = vtx_begin(pk) - excl;  // edge address of concatenated position e is w_beg[owner] + e
+        w_q[lane] = q;
+        __syncwarp();
+        for (u32 eb = 0; eb < total; eb += 128) {  // four independent edges per lane in flight
+            u32 u[4];
+            u64 qq[4];
+            bool cr[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        u32 e = eb + 32 * k + lane;
-                        u[k] = 0xffffffffu;
-                        qq[k] = 0;
-                        if (e < total) {
-                            int o = 0;
+            for (int k = 0; k < 4; k++) {
+                u32 e = eb + 32 * k + lane;
+                u[k] = 0xffffffffu;
+                qq[k] = 0;
+                if (e < total) {
+                    int o = 0;
 #pragma unroll
-                            for (int s = 16; s > 0; s >>= 1) { int p = o + s; if ((u32)w_excl[p] <= e) o = p; }
-                            u[k] = (u32)__ldg(&A.col_idx[w_beg[o] + e]);
-                            qq[k] = w_q[o];
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], qq[k]) : false;
-                    if (LIST) warp_append4_u32(next, next_cnt, cr, u);
-                }
-                __syncwarp();
-            } else {
-                // (2) long rows: one PUSH_CHUNK-edge chunk, coalesced neighbour loads
-                uint2 desc = A.chunks[unit - nb];
-                u64 pk = A.l_pack[desc.x];
-                u64 q = A.l_q[desc.x];
-                u32 d = vtx_deg(pk);
-                u32 off = desc.y * PUSH_CHUNK;
-                u32 len = min((u32)PUSH_CHUNK, d - off);
-                const i32* row = A.col_idx + vtx_begin(pk) + off;
-                for (u32 eb = 0; eb < len; eb += 128) {
-                    u32 u[4];
-                    bool cr[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) { u32 e = eb + 32 * k + lane; u[k] = e < len ? (u32)__ldg(&row[e]) : 0xffffffffu; }
-#pragma unroll
-                    for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], q) : false;
-                    if (LIST) warp_append4_u32(next, next_cnt, cr, u);
+                    for (int s = 16; s > 0; s >>= 1) { int p = o + s; if ((u32)w_excl[p] <= e) o = p; }
+                    u[k] = (u32)__ldg(&A.col_idx[w_beg[o] + e]);
+                    qq[k] = w_q[o];
                 }
             }
+#pragma unroll
+            for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], qq[k]) : false;
+            if (LIST) warp_append4_u32(next, next_cnt, cr, u);
+        }
+        __syncwarp();
+    }
+
+    // (2) long rows: one warp per PUSH_CHUNK-edge chunk, four independent edges per lane in flight
+    for (i64 c = gwarp; c < nch; c += nwarps) {
+        uint2 desc = A.chunks[c];
+        u64 pk = A.l_pack[desc.x];
+        u64 q = A.l_q[desc.x];
+        u32 d = vtx_deg(pk);
+        u32 off = desc.y * PUSH_CHUNK;
+        u32 len = min((u32)PUSH_CHUNK, d - off);
+        const i32* row = A.col_idx + vtx_begin(pk) + off;
+        for (u32 eb = 0; eb < len; eb += 128) {
+            u32 u[4];
+            bool cr[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { u32 e = eb + 32 * k + lane; u[k] = e < len ? (u32)__ldg(&row[e]) : 0xffffffffu; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], q) : false;
+            if (LIST) warp_append4_u32(next, next_cnt, cr, u);
         }
     }
 
-#ifdef PUSH_PROFILE_WARPS
-    if (lane == 0) {  // diagnostic build only: per-warp busy time of this phase (sum and max over warps)
-        u64 dt = globaltimer_ns() - wt0;
-        atomicAdd((ull*)&ctl->prof_sum, (ull)dt);
-        atomicMax((ull*)&ctl->prof_max, (ull)dt);
-    }
-#endif
     // (3) dangling mass -> source (J/Forward_Push.java:101-113) and the iteration's bookkeeping
     if (gtid == 0) {
         u64 dsum = *(volatile u64*)&ctl->dang[par];
@@ -520,7 +496,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
         for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
         if (gtid == 0) {
             ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
-            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0; ctl->work[0] = ctl->work[1] = 0;
+            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
             ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
             ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0; ctl->dbg_count = 0;
@@ -531,7 +507,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
         ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0;
         if (!A.init) {  // top-k round: host supplied the round's rmax; counters of both parities must be clean
             ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
-            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0; ctl->work[0] = ctl->work[1] = 0;
+            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
         }
     }
@@ -580,10 +556,6 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
                     u64* d = A.dbg + (size_t)k * DBG_FIELDS;
                     d[0] = t0; d[1] = t1; d[2] = globaltimer_ns(); d[3] = fcnt; d[4] = ctl->edges;
                     d[5] = (have_list ? 0 : 1) | (next_scan ? 2 : 0);
-#ifdef PUSH_PROFILE_WARPS
-                    d[5] |= (ctl->prof_sum / (gsize >> 5)) << 8 | (ctl->prof_max << 36);
-                    ctl->prof_sum = 0; ctl->prof_max = 0;
-#endif
                     ctl->dbg_count = k + 1;
                 }
             }
@@ -625,7 +597,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_init(PushArgs A) {
     for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
     if (gtid == 0) {
         ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
-        ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0; ctl->work[0] = ctl->work[1] = 0;
+        ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
         ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
         ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
         ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0;

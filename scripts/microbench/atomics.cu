@@ -10,6 +10,12 @@ __global__ void k_init(uint32_t* idx, size_t m, uint32_t mask, uint64_t seed) {
         idx[i] = (uint32_t)z & mask;
     }
 }
+__global__ void k_hot(uint32_t* idx, size_t m, int h) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t z = (i + 12345) * 0xD6E8FEB86659FD93ull; z ^= z >> 32; z *= 0xD6E8FEB86659FD93ull; z ^= z >> 32;
+        if ((z & ((1ull << h) - 1)) == 0) idx[i] = 7;
+    }
+}
 template <int MODE>
 __global__ void __launch_bounds__(256) k_op(const uint32_t* __restrict__ idx, size_t m, ull* data, ull* sink) {
     ull acc = 0;
@@ -35,7 +41,7 @@ int main() {
     cudaMemset(data, 0, (size_t)1 << 30);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     const char* names[4] = {"RED.64", "ATOM.64+ret", "LDG.64 gather", "RED.32"};
-    for (int lg = 20; lg <= 27; lg += (lg < 24 ? 2 : 1)) {  // 2^lg elements of 8 B
+    for (int lg = 20; lg <= 20; lg += 1) {  // 2^lg elements of 8 B
         k_init<<<1184, 256>>>(idx, m, (1u << lg) - 1, 77);
         for (int mode = 0; mode < 4; mode++) {
             for (int blocks : {148 * 4, 148 * 8}) {
@@ -53,7 +59,22 @@ int main() {
             }
         }
     }
-    // hot-spot: 1/8 of the ops hit one of 64 addresses (hub-like), rest random over 8 MB
+    // hot spots: a fraction 1/2^h of the ops goes to ONE address (a hub), the rest is random over 8 MB
+    for (int h : {4, 6, 8, 10, 12}) {
+        k_init<<<1184, 256>>>(idx, m, (1u << 20) - 1, 99);
+        k_hot<<<1184, 256>>>(idx, m, h);
+        for (int mode : {0, 2}) {
+            float best = 1e9;
+            for (int rep = 0; rep < 3; rep++) {
+                cudaEventRecord(a);
+                if (mode == 0) k_op<0><<<148 * 4, 256>>>(idx, m, data, sink);
+                if (mode == 2) k_op<2><<<148 * 4, 256>>>(idx, m, data, sink);
+                cudaEventRecord(b); cudaEventSynchronize(b);
+                float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms;
+            }
+            printf("hot 1/%d to one address, 8 MB footprint  %-14s : %7.3f ms  %6.1f Gop/s   (%.2f ns per hot op)\n", 1 << h, names[mode], best, m / best / 1e6, best * 1e6 / (m >> h));
+        }
+    }
     printf("cuda status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
