@@ -41,7 +41,7 @@ int main() {
     cudaMemset(data, 0, (size_t)1 << 30);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     const char* names[4] = {"RED.64", "ATOM.64+ret", "LDG.64 gather", "RED.32"};
-    for (int lg = 20; lg <= 20; lg += 1) {  // 2^lg elements of 8 B
+    for (int lg = 20; lg <= 27; lg += (lg < 24 ? 2 : 1)) {  // 2^lg elements of 8 B
         k_init<<<1184, 256>>>(idx, m, (1u << lg) - 1, 77);
         for (int mode = 0; mode < 4; mode++) {
             for (int blocks : {148 * 4, 148 * 8}) {
