@@ -98,8 +98,10 @@ int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_rounds);
 /* Frontier-mode switch of the push kernels: an iteration whose frontier has at least this many out-edges
  * scatters with plain reductions and the next frontier is found by a dense sweep; smaller frontiers use
  * returning atomics and exact threshold-crossing detection.  Results are bit-identical either way.
- * < 0 restores the default (n); 0 = always sweep; INT64_MAX = never sweep. */
-int32_t ppr_set_tuning(ppr_ctx* ctx, int64_t scan_threshold_edges);
+ * < 0 restores the default (n); 0 = always sweep; INT64_MAX = never sweep.
+ * hot_min_indeg (>= 0; < 0 keeps the current value, default 64): minimum in-degree for a vertex to get one of
+ * the 4096 hub slots whose incoming adds are staged in shared memory; applies to graphs created afterwards. */
+int32_t ppr_set_tuning(ppr_ctx* ctx, int64_t scan_threshold_edges, int32_t hot_min_indeg);
 
 /* Measurement helpers (bench.py): CUDA events on the context's compute stream, the stream every kernel
  * of this library is launched on (after joining the download stream), and an L2 flush (a write of a

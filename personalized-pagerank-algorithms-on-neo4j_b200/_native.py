@@ -88,7 +88,7 @@ def load():
         "ppr_last_error": (C.c_char_p, [vp]),
         "ppr_device_info": (i32, [vp, C.POINTER(i32), C.POINTER(i64), C.c_char_p, i32]),
         "ppr_set_balance": (i32, [vp, f64, i32]),
-        "ppr_set_tuning": (i32, [vp, i64]),
+        "ppr_set_tuning": (i32, [vp, i64, i32]),
         "ppr_timer_record": (i32, [vp, i32]),
         "ppr_timer_elapsed_ms": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
         "ppr_flush_l2": (i32, [vp]),
@@ -167,8 +167,8 @@ class Context:
         self.check(self.L.ppr_device_info(self.h, C.byref(sm), C.byref(mem), name, 256))
         return {"sm_count": sm.value, "total_mem": mem.value, "name": name.value.decode()}
 
-    def set_tuning(self, scan_threshold_edges=-1):
-        self.check(self.L.ppr_set_tuning(self.h, scan_threshold_edges))
+    def set_tuning(self, scan_threshold_edges=-1, hot_min_indeg=-1):
+        self.check(self.L.ppr_set_tuning(self.h, scan_threshold_edges, hot_min_indeg))
 
     def timer_record(self, slot):
         self.check(self.L.ppr_timer_record(self.h, slot))

@@ -36,6 +36,9 @@ typedef unsigned long long ull;
 
 #define DBG_ITERS 4096
 #define DBG_FIELDS 6   // t_start, t_after_A, t_after_B (globaltimer ns), frontier size, cumulative edges, mode
+#define HOT_SLOTS 4096      // hub vertices whose incoming adds are staged in shared memory (32 KB per CTA)
+#define HOT_BIT 0x80000000u
+#define HOT_MASK 0x00000fffu
 #define PUSH_THREADS 256
 #define WALK_THREADS 256
 
@@ -135,6 +138,7 @@ struct ppr_ctx {
     double walk_cost;
     int max_rounds;
     i64 scan_threshold;    // < 0: default (n)
+    i32 hot_min_indeg;     // a vertex needs at least this in-degree to get a hub slot (graphs created afterwards)
 };
 
 struct DevGraph {
@@ -145,6 +149,9 @@ struct DevGraph {
     u64* in_vtx;    // [n] packed over the CSC
     i32* row_idx;   // [m]
     u64* invdeg;    // [n] (2^64-1)/out_deg, 0 for dangling
+    u32* push_idx;  // [m] col_idx with hub targets encoded as HOT_BIT | slot
+    u32* hot_id;    // [n_hot] slot -> vertex
+    u32 n_hot;
 };
 
 struct Workspace {

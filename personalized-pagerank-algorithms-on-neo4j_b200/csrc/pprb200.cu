@@ -66,6 +66,7 @@ extern "C" int32_t ppr_init(int32_t device, ppr_ctx** out) {
     ctx->walk_cost = 6.0;   // measured on B200: one walk costs about as much as six relaxed edges
     ctx->max_rounds = 64;
     ctx->scan_threshold = -1;
+    ctx->hot_min_indeg = 64;
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
         delete ctx;
@@ -115,9 +116,10 @@ extern "C" int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_r
     return PPR_OK;
 }
 
-extern "C" int32_t ppr_set_tuning(ppr_ctx* ctx, int64_t scan_threshold_edges) {
+extern "C" int32_t ppr_set_tuning(ppr_ctx* ctx, int64_t scan_threshold_edges, int32_t hot_min_indeg) {
     if (!ctx) return PPR_E_INVALID;
     ctx->scan_threshold = scan_threshold_edges;
+    if (hot_min_indeg >= 0) ctx->hot_min_indeg = hot_min_indeg;
     return PPR_OK;
 }
 
@@ -271,7 +273,7 @@ extern "C" int32_t ppr_graph_destroy(ppr_graph* g) {
     if (x && x->ws1_ready) ws_free(g->ws[1]);
     if (x && x->bws_ready) bws_free(x->bws);
     cudaFree(g->d.out_vtx); cudaFree(g->d.col_idx); cudaFree(g->d.out_deg);
-    cudaFree(g->d.in_vtx); cudaFree(g->d.row_idx); cudaFree(g->d.invdeg);
+    cudaFree(g->d.in_vtx); cudaFree(g->d.row_idx); cudaFree(g->d.invdeg); cudaFree(g->d.push_idx); cudaFree(g->d.hot_id);
     for (size_t i = 0; i < g_extras.size(); i++) if (g_extras[i].first == g) { delete g_extras[i].second; g_extras.erase(g_extras.begin() + i); break; }
     delete g;
     return PPR_OK;
@@ -311,6 +313,22 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
             for (i64 e = row_ptr[v]; e < row_ptr[v + 1]; e++) ri[(size_t)pos[col_idx[e]]++] = (i32)v;
     }
 
+    // hub set: the (up to) HOT_SLOTS vertices of highest in-degree, at least hot_min_indeg in-edges each;
+    // push_idx = col_idx with those targets replaced by HOT_BIT | slot (read by the push kernels only)
+    std::vector<u32> hot_id;
+    std::vector<u32> push_idx;
+    try {
+        std::vector<std::pair<i64, i32>> cand;
+        const i64 min_in = std::max<i64>(1, ctx->hot_min_indeg);
+        for (i64 v = 0; v < n; v++) { i64 d = cp[v + 1] - cp[v]; if (d >= min_in) cand.push_back(std::make_pair(-d, (i32)v)); }
+        size_t keep = std::min<size_t>(cand.size(), HOT_SLOTS);
+        std::partial_sort(cand.begin(), cand.begin() + keep, cand.end());
+        std::vector<i32> slot_of((size_t)n, -1);
+        for (size_t s = 0; s < keep; s++) { hot_id.push_back((u32)cand[s].second); slot_of[(size_t)cand[s].second] = (i32)s; }
+        push_idx.resize((size_t)m);
+        for (i64 e = 0; e < m; e++) { i32 sl = slot_of[(size_t)col_idx[e]]; push_idx[(size_t)e] = sl >= 0 ? (HOT_BIT | (u32)sl) : (u32)col_idx[e]; }
+    } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed"); }
+
     cudaSetDevice(ctx->device);
     ppr_graph* g = new (std::nothrow) ppr_graph();
     GraphExtra* x = new (std::nothrow) GraphExtra();
@@ -327,6 +345,8 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     G_TRY(dalloc(&g->d.out_vtx, (size_t)n)); G_TRY(dalloc(&g->d.out_deg, (size_t)n)); G_TRY(dalloc(&g->d.invdeg, (size_t)n));
     G_TRY(dalloc(&g->d.in_vtx, (size_t)n)); G_TRY(dalloc(&g->d.col_idx, (size_t)m)); G_TRY(dalloc(&g->d.row_idx, (size_t)m));
     G_TRY(dalloc(&d_ptr, (size_t)n + 1));
+    G_TRY(dalloc(&g->d.push_idx, (size_t)m)); G_TRY(dalloc(&g->d.hot_id, (size_t)HOT_SLOTS));
+    g->d.n_hot = (u32)hot_id.size();
     int blocks = ctx->sm_count * 8;
     G_TRY(cudaMemcpyAsync(d_ptr, row_ptr, ((size_t)n + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
     k_build_vtx<<<blocks, 256, 0, ctx->stream>>>(d_ptr, g->d.out_vtx, g->d.out_deg, g->d.invdeg, n);
@@ -338,7 +358,9 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     if (m > 0) {
         G_TRY(cudaMemcpyAsync(g->d.col_idx, col_idx, (size_t)m * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
         G_TRY(cudaMemcpyAsync(g->d.row_idx, ri.data(), (size_t)m * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
+        G_TRY(cudaMemcpyAsync(g->d.push_idx, push_idx.data(), (size_t)m * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (!hot_id.empty()) G_TRY(cudaMemcpyAsync(g->d.hot_id, hot_id.data(), hot_id.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     G_TRY(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_ptr); d_ptr = nullptr;
 #undef G_TRY
@@ -378,6 +400,7 @@ extern "C" int32_t ppr_graph_export_csc(ppr_graph* g, int64_t* col_ptr, int32_t*
 static void fill_push_args(PushArgs& A, ppr_graph* g, Workspace& w) {
     memset(&A, 0, sizeof A);
     A.n = g->d.n; A.out_vtx = g->d.out_vtx; A.col_idx = g->d.col_idx; A.out_deg = g->d.out_deg;
+    A.push_idx = g->d.push_idx; A.hot_id = g->d.hot_id; A.n_hot = g->d.n_hot;
     A.r = w.r; A.reserve = w.reserve; A.est = w.est; A.front[0] = w.front[0]; A.front[1] = w.front[1];
     A.s_pack = w.s_pack; A.s_q = w.s_q; A.l_pack = w.l_pack; A.l_q = w.l_q; A.chunks = w.chunks;
     A.ws_v = w.ws_v; A.ws_begin = w.ws_begin; A.ws_inc = w.ws_inc; A.ws_rem = w.ws_rem;

@@ -36,6 +36,9 @@ struct PushArgs {
     const u64* out_vtx;
     const i32* col_idx;
     const u32* out_deg;
+    const u32* push_idx;   // col_idx with hub targets replaced by HOT_BIT | slot (see hot_id)
+    const u32* hot_id;     // slot -> vertex id of the n_hot highest in-degree vertices
+    u32 n_hot;
     // state
     u64* r;
     u64* reserve;
@@ -236,20 +239,26 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
 // --------------------------------------------------------------------------------- phase B
 // One relaxed edge.  LIST: returning atomic + crossing test; otherwise a fire-and-forget reduction.
 template <bool LIST>
-__device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32 u, u64 q) {
+__device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32& u, u64 q, u64* sm_hot) {
+    // `u` comes from push_idx: hub targets are encoded as HOT_BIT | slot.
     if (LIST) {
+        if (u & HOT_BIT) u = __ldg(&A.hot_id[u & HOT_MASK]);
         u64 old = atomicAdd((ull*)&A.r[u], (ull)q);
         u64 th = thr_fwd(rmax_fx, __ldg(&A.out_deg[u]));
         return old < th && old + q >= th;
     } else {
-        atomicAdd((ull*)&A.r[u], (ull)q);  // result unused: compiles to RED.E.ADD.64
+        // dense frontiers: adds to hub vertices are accumulated per CTA in shared memory and flushed once
+        // per phase -- same-address RED.64 serialises at ~0.7 ns in L2, and a hub receives up to
+        // max-in-degree adds per iteration (scripts/microbench: 1/256 of the adds on one address costs 30 %)
+        if (u & HOT_BIT) atomicAdd((ull*)&sm_hot[u & HOT_MASK], (ull)q);
+        else atomicAdd((ull*)&A.r[u], (ull)q);  // result unused: compiles to RED.E.ADD.64
         return false;
     }
 }
 
 template <bool LIST>
 __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u64* sm_excl /*[warps][32]*/,
-                             u64* sm_beg, u64* sm_q) {
+                             u64* sm_beg, u64* sm_q, u64* sm_hot /*[HOT_SLOTS], all zero on entry and exit; unused when LIST*/) {
     PushCtl* ctl = A.ctl;
     const u32 ns = *(volatile u32*)&ctl->ns[par];
     const u32 nch = *(volatile u32*)&ctl->nchunks[par];
@@ -293,12 +302,12 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
                     int o = 0;
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) { int p = o + s; if ((u32)w_excl[p] <= e) o = p; }
-                    u[k] = (u32)__ldg(&A.col_idx[w_beg[o] + e]);
+                    u[k] = __ldg(&A.push_idx[w_beg[o] + e]);
                     qq[k] = w_q[o];
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], qq[k]) : false;
+            for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], qq[k], sm_hot) : false;
             if (LIST) warp_append4_u32(next, next_cnt, cr, u);
         }
         __syncwarp();
@@ -312,18 +321,26 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
         u32 d = vtx_deg(pk);
         u32 off = desc.y * PUSH_CHUNK;
         u32 len = min((u32)PUSH_CHUNK, d - off);
-        const i32* row = A.col_idx + vtx_begin(pk) + off;
+        const u32* row = A.push_idx + vtx_begin(pk) + off;
         for (u32 eb = 0; eb < len; eb += 128) {
             u32 u[4];
             bool cr[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) { u32 e = eb + 32 * k + lane; u[k] = e < len ? (u32)__ldg(&row[e]) : 0xffffffffu; }
+            for (int k = 0; k < 4; k++) { u32 e = eb + 32 * k + lane; u[k] = e < len ? __ldg(&row[e]) : 0xffffffffu; }
 #pragma unroll
-            for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], q) : false;
+            for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], q, sm_hot) : false;
             if (LIST) warp_append4_u32(next, next_cnt, cr, u);
         }
     }
 
+    if (!LIST && A.n_hot) {  // flush the CTA's hub accumulators (uniform: every thread of the CTA gets here)
+        __syncthreads();
+        for (u32 sl = threadIdx.x; sl < A.n_hot; sl += blockDim.x) {
+            u64 x = sm_hot[sl];
+            if (x) { atomicAdd((ull*)&A.r[__ldg(&A.hot_id[sl])], (ull)x); sm_hot[sl] = 0; }
+        }
+        __syncthreads();
+    }
     // (3) dangling mass -> source (J/Forward_Push.java:101-113) and the iteration's bookkeeping
     if (gtid == 0) {
         u64 dsum = *(volatile u64*)&ctl->dang[par];
@@ -488,9 +505,12 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
     __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
     __shared__ __align__(8) u32 sm_cnt[16];
+    __shared__ u64 sm_hot[HOT_SLOTS];
     PushCtl* ctl = A.ctl;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 gsize = (i64)gridDim.x * blockDim.x;
+    for (u32 sl = threadIdx.x; sl < HOT_SLOTS; sl += blockDim.x) sm_hot[sl] = 0;
+    __syncthreads();
 
     if (A.init) {
         for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
@@ -547,8 +567,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
             if (fcnt == 0) break;
             const bool next_scan = (i64)fedges >= A.scan_threshold;
             if (gtid == 0) t1 = globaltimer_ns();
-            if (next_scan) push_phase_b<false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
-            else push_phase_b<true>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
+            if (next_scan) push_phase_b<false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
+            else push_phase_b<true>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
             grid.sync();
             if (gtid == 0) {
                 u32 k = ctl->dbg_count;
@@ -624,5 +644,5 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_b(PushArgs A, int par) {
     __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
-    push_phase_b<true>(A, par, A.ctl->rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q);
+    push_phase_b<true>(A, par, A.ctl->rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, nullptr);
 }

@@ -221,6 +221,29 @@ def test_frontier_modes_give_identical_bits(ctx, G, OG, R12, O):
         ctx.set_tuning(-1)
 
 
+def test_hub_slots_give_identical_bits(pkg, ctx, got, rmat12, O):
+    # every vertex with an in-edge gets a shared-memory hub slot (hot_min_indeg = 1) and every iteration runs in
+    # SCAN mode (threshold 0): the staged adds + per-CTA flush must reproduce the oracle's bits
+    try:
+        ctx.set_tuning(0, 1)
+        for rp, ci in (got[:2], rmat12):
+            g = pkg.Graph(ctx, rp, ci)
+            og = O.OGraph(rp, ci)
+            deg = np.diff(og.rp)
+            for s in [int(x) for x in np.flatnonzero(deg > 0)[[0, 5, 11]]]:
+                check_fora(g, og, O, s, EPS)
+                g.forward_push(s, ALPHA, 1e-8, want_residue=False)
+                raw_res, raw_r = g.last_raw()
+                ores, orr, _ = O.b_forward_push(og, s, ALPHA, 1e-8)
+                assert np.array_equal(raw_res, ores) and np.array_equal(raw_r, orr)
+            ctx.set_tuning(1 << 62, -1)   # same graph (hub-encoded edges), LIST mode: decode path
+            check_fora(g, og, O, int(np.flatnonzero(deg > 0)[3]), EPS)
+            ctx.set_tuning(0, -1)
+            g.close()
+    finally:
+        ctx.set_tuning(-1, 64)
+
+
 def test_fora_guarantee(G, OG, R12, O):
     # FORA's guarantee (Dissertation p.14): |est - pi| <= eps * pi for every pi > delta = 1/n, w.p. 1 - 1/n.
     # Tolerance: exactly eps = 0.5 relative; the exact answer is the power iteration run to 1e-17.
