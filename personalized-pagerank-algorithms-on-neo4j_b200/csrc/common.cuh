@@ -92,9 +92,10 @@ __device__ __forceinline__ u32 lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemas
 struct PushCtl {
     // frontier bookkeeping (index = iteration parity)
     u32 cnt[2];        // frontier sizes
-    u32 ns[2];         // staged small items
-    u32 nl[2];         // staged large items
-    u32 nchunks[2];    // chunk descriptors
+    u64 stage[2];      // forward push: staged work of the iteration, (chunk descriptors << 32) | short rows
+    u32 ns[2];         // reverse push: staged short rows
+    u32 nl[2];         // reverse push: staged long rows
+    u32 nchunks[2];    // reverse push: chunk descriptors
     u64 dang[2];       // dangling mass headed for the source
     u32 fcnt[2];       // vertices pushed by the iteration (both frontier modes)
     u64 fedges[2];     // edges relaxed by the iteration

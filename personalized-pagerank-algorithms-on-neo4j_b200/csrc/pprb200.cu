@@ -193,7 +193,7 @@ static int32_t ws_alloc(ppr_ctx* ctx, Workspace& w, i64 n, i64 chunk_cap) {
     size_t N = (size_t)n;
     CUDA_TRY(dalloc(&w.r, N)); CUDA_TRY(dalloc(&w.reserve, N)); CUDA_TRY(dalloc(&w.est, N));
     CUDA_TRY(dalloc(&w.front[0], N)); CUDA_TRY(dalloc(&w.front[1], N));
-    CUDA_TRY(dalloc(&w.s_pack, N)); CUDA_TRY(dalloc(&w.s_q, N)); CUDA_TRY(dalloc(&w.l_pack, N)); CUDA_TRY(dalloc(&w.l_q, N));
+    CUDA_TRY(dalloc(&w.s_pack, N)); CUDA_TRY(dalloc(&w.s_q, N)); CUDA_TRY(dalloc(&w.l_pack, std::max(N, (size_t)chunk_cap))); CUDA_TRY(dalloc(&w.l_q, std::max(N, (size_t)chunk_cap)));
     CUDA_TRY(dalloc(&w.chunks, (size_t)chunk_cap));
     CUDA_TRY(dalloc(&w.ws_v, N)); CUDA_TRY(dalloc(&w.ws_begin, N + 64)); CUDA_TRY(dalloc(&w.ws_inc, N)); CUDA_TRY(dalloc(&w.ws_rem, N));
     int occ = 0;

@@ -128,91 +128,84 @@ __device__ void push_scan(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64
 // --------------------------------------------------------------------------------- phase A
 // Per-vertex capture shared by both frontier modes.  SCAN = true sweeps all vertices (coalesced reads of
 // r[] and the vertex table) and keeps those at or above threshold; SCAN = false walks the frontier list.
+// Work is warp-granular: a warp takes 128 consecutive items (4 per lane, loads issued together), counts
+// its short rows and long-row chunks with ballots, reserves staging slots for the whole tile with ONE
+// packed 64-bit atomic (chunks << 32 | short rows) and writes.  No CTA barrier inside the loop: an earlier
+// version reserved per CTA tile behind __syncthreads and spent ~11 us per tile on the atomic round trip.
 template <bool SCAN>
 __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u32* sm_cnt /*16 words, 8-byte aligned*/) {
     PushCtl* ctl = A.ctl;
     const i64 cnt = SCAN ? A.n : (i64)*(volatile u32*)&ctl->cnt[par];
     if (gtid == 0) {  // recycle the other parity's counters (last read before the preceding barrier)
-        ctl->cnt[par ^ 1] = 0; ctl->ns[par ^ 1] = 0; ctl->nl[par ^ 1] = 0; ctl->nchunks[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
+        ctl->cnt[par ^ 1] = 0; ctl->stage[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
         ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0;
     }
-    u64 edges_local = 0, resv_local = 0, dang_local = 0;
-    u32 pushed_local = 0;
+    u64 edges_local = 0, resv_local = 0, dang_local = 0, pushed_local = 0;
     const u32* F = A.front[par];
-    // One tile = PA_ITEMS * blockDim consecutive items per CTA.  Staging slots are claimed with
-    // shared-memory atomics inside the tile and ONE global atomic per counter per tile: a global counter
-    // bumped once per warp serialises at ~1 op/clk in its L2 slice and used to dominate this phase.
+    const u32 lane = lane_id();
+    const i64 gwarp = gtid >> 5, nwarps = gsize >> 5;
     constexpr int PA_ITEMS = 4;
-    const i64 tile_span = (i64)blockDim.x * PA_ITEMS;
-    for (i64 tile = (i64)blockIdx.x * tile_span; tile < cnt; tile += (i64)gridDim.x * tile_span) {
-        if (threadIdx.x < 3) sm_cnt[threadIdx.x] = 0;
-        __syncthreads();
-        u64 pk[PA_ITEMS], q[PA_ITEMS];
-        u32 loc[PA_ITEMS], loc_c[PA_ITEMS];
-        u32 cls[PA_ITEMS];  // 0 none, 1 small, 2 large
+    for (i64 tile = gwarp * (32 * PA_ITEMS); tile < cnt; tile += nwarps * (32 * PA_ITEMS)) {
+        u64 pk[PA_ITEMS], q[PA_ITEMS], x[PA_ITEMS];
+        u32 v[PA_ITEMS], cls[PA_ITEMS];  // cls: 0 none, 1 short row, 2 long row
 #pragma unroll
         for (int k = 0; k < PA_ITEMS; k++) {
-            i64 i = tile + (i64)k * blockDim.x + threadIdx.x;
-            pk[k] = 0; q[k] = 0; cls[k] = 0; loc[k] = 0; loc_c[k] = 0;
-            if (i < cnt) {
-                u32 v = SCAN ? (u32)i : F[i];
-                u64 x = A.r[v];
-                bool take = true;
-                if (SCAN) {
-                    take = false;
-                    if (x) { pk[k] = A.out_vtx[v]; take = x >= thr_fwd(rmax_fx, vtx_deg(pk[k])); }
-                } else {
-                    pk[k] = A.out_vtx[v];
+            i64 i = tile + (i64)k * 32 + lane;
+            v[k] = i < cnt ? (SCAN ? (u32)i : F[i]) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) x[k] = v[k] != 0xffffffffu ? A.r[v[k]] : 0;
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) pk[k] = (v[k] != 0xffffffffu && (!SCAN || x[k])) ? A.out_vtx[v[k]] : 0;
+        u32 my_nch = 0;
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) {
+            q[k] = 0; cls[k] = 0;
+            bool take = v[k] != 0xffffffffu && (!SCAN || (x[k] && x[k] >= thr_fwd(rmax_fx, vtx_deg(pk[k]))));
+            if (take) {
+                u32 d = vtx_deg(pk[k]);
+                u64 a = mulhi64(x[k], A.alpha_q64);
+                u64 y = x[k] - a;
+                u64 left;
+                if (d == 0) { left = 0; dang_local += y; }
+                else { q[k] = y / (u64)d; left = y - q[k] * (u64)d; }
+                A.r[v[k]] = left;
+                A.reserve[v[k]] += a;
+                resv_local += a;
+                edges_local += d;
+                pushed_local += 1;
+                cls[k] = d == 0 ? 0u : (d <= PUSH_SMALL_MAX ? 1u : 2u);
+                if (cls[k] == 2) my_nch += (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
+            }
+        }
+        u32 ms[PA_ITEMS], small_total = 0;
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) { ms[k] = __ballot_sync(0xffffffffu, cls[k] == 1); small_total += __popc(ms[k]); }
+        u32 chunk_incl = 0, chunk_total = 0;
+        if (__any_sync(0xffffffffu, my_nch != 0)) {
+            chunk_incl = my_nch;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, chunk_incl, o); if (lane >= o) chunk_incl += t; }
+            chunk_total = __shfl_sync(0xffffffffu, chunk_incl, 31);
+        }
+        if (small_total | chunk_total) {
+            u64 base = 0;
+            if (lane == 0) base = atomicAdd((ull*)&ctl->stage[par], ((ull)chunk_total << 32) | (ull)small_total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            u32 off = (u32)base;
+            u32 cb = (u32)(base >> 32) + chunk_incl - my_nch;
+#pragma unroll
+            for (int k = 0; k < PA_ITEMS; k++) {
+                if (cls[k] == 1) { u32 slot = off + __popc(ms[k] & lanemask_lt()); A.s_pack[slot] = pk[k]; A.s_q[slot] = q[k]; }
+                off += __popc(ms[k]);
+                if (cls[k] == 2) {  // a long row is identified by its first chunk slot
+                    u32 nch = (vtx_deg(pk[k]) + PUSH_CHUNK - 1) / PUSH_CHUNK;
+                    A.l_pack[cb] = pk[k]; A.l_q[cb] = q[k];
+                    for (u32 c = 0; c < nch; c++) A.chunks[cb + c] = make_uint2(cb, c);
+                    cb += nch;
                 }
-                if (take) {
-                    u32 d = vtx_deg(pk[k]);
-                    u64 a = mulhi64(x, A.alpha_q64);
-                    u64 y = x - a;
-                    u64 left;
-                    if (d == 0) { q[k] = y; left = 0; dang_local += y; }
-                    else { q[k] = y / (u64)d; left = y - q[k] * (u64)d; }
-                    A.r[v] = left;
-                    A.reserve[v] += a;
-                    resv_local += a;
-                    edges_local += d;
-                    pushed_local += 1;
-                    cls[k] = d == 0 ? 0u : (d <= PUSH_SMALL_MAX ? 1u : 2u);
-                }
             }
         }
-#pragma unroll
-        for (int k = 0; k < PA_ITEMS; k++) {
-            u32 mask = __ballot_sync(0xffffffffu, cls[k] == 1);
-            if (mask) {
-                u32 leader = __ffs(mask) - 1, b = 0;
-                if (lane_id() == leader) b = atomicAdd(&sm_cnt[0], (u32)__popc(mask));
-                b = __shfl_sync(0xffffffffu, b, leader);
-                if (cls[k] == 1) loc[k] = b + __popc(mask & lanemask_lt());
-            }
-            if (cls[k] == 2) {
-                u32 nch = (vtx_deg(pk[k]) + PUSH_CHUNK - 1) / PUSH_CHUNK;
-                loc[k] = atomicAdd(&sm_cnt[1], 1u);
-                loc_c[k] = atomicAdd(&sm_cnt[2], nch);
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < 3 && sm_cnt[threadIdx.x]) {
-            u32* gc = threadIdx.x == 0 ? &ctl->ns[par] : threadIdx.x == 1 ? &ctl->nl[par] : &ctl->nchunks[par];
-            sm_cnt[4 + threadIdx.x] = atomicAdd(gc, sm_cnt[threadIdx.x]);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < PA_ITEMS; k++) {
-            if (cls[k] == 1) { u32 slot = sm_cnt[4] + loc[k]; A.s_pack[slot] = pk[k]; A.s_q[slot] = q[k]; }
-            if (cls[k] == 2) {
-                u32 slot = sm_cnt[5] + loc[k];
-                A.l_pack[slot] = pk[k]; A.l_q[slot] = q[k];
-                u32 cb = sm_cnt[6] + loc_c[k];
-                u32 nch = (vtx_deg(pk[k]) + PUSH_CHUNK - 1) / PUSH_CHUNK;
-                for (u32 c = 0; c < nch; c++) A.chunks[cb + c] = make_uint2(slot, c);
-            }
-        }
-        __syncthreads();
     }
     // CTA-level totals first (shared-memory atomics), then one global atomic per counter per CTA
     u64* sm_acc = reinterpret_cast<u64*>(sm_cnt + 8);
@@ -222,9 +215,9 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     edges_local = warp_sum_u64(edges_local);
     resv_local = warp_sum_u64(resv_local);
     dang_local = warp_sum_u64(dang_local);
-    u64 pushed64 = warp_sum_u64((u64)pushed_local);
-    if (lane_id() == 0) {
-        if (pushed64) atomicAdd((ull*)&sm_acc[0], (ull)pushed64);
+    pushed_local = warp_sum_u64(pushed_local);
+    if (lane == 0) {
+        if (pushed_local) atomicAdd((ull*)&sm_acc[0], (ull)pushed_local);
         if (edges_local) atomicAdd((ull*)&sm_acc[1], (ull)edges_local);
         if (resv_local) atomicAdd((ull*)&sm_acc[2], (ull)resv_local);
         if (dang_local) atomicAdd((ull*)&sm_acc[3], (ull)dang_local);
@@ -247,7 +240,7 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
 __device__ void push_phase_a_dense(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u32* sm_cnt) {
     PushCtl* ctl = A.ctl;
     if (gtid == 0) {
-        ctl->cnt[par ^ 1] = 0; ctl->ns[par ^ 1] = 0; ctl->nl[par ^ 1] = 0; ctl->nchunks[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
+        ctl->cnt[par ^ 1] = 0; ctl->stage[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
         ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0;
     }
     u64 edges_local = 0, resv_local = 0, dang_local = 0, pushed_local = 0;
@@ -322,8 +315,9 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     PushCtl* ctl = A.ctl;
     // item source: compacted staging written by the list-mode phase A, or (DENSE) the vertex range itself
     // with qv[] and the graph's static chunk table
-    const i64 ns = DENSE ? A.n : (i64)*(volatile u32*)&ctl->ns[par];
-    const u32 nch = DENSE ? A.n_big_chunks : *(volatile u32*)&ctl->nchunks[par];
+    const u64 staged = *(volatile u64*)&ctl->stage[par];
+    const i64 ns = DENSE ? A.n : (i64)(u32)staged;
+    const u32 nch = DENSE ? A.n_big_chunks : (u32)(staged >> 32);
     const i64 gwarp = gtid >> 5, nwarps = gsize >> 5;
     const u32 lane = lane_id();
     const int wib = threadIdx.x >> 5;
@@ -592,8 +586,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
     if (A.init) {
         for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
         if (gtid == 0) {
-            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
-            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
+            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
             ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
             ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0; ctl->dbg_count = 0;
@@ -603,8 +596,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
     if (gtid == 0) {
         ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0;
         if (!A.init) {  // top-k round: host supplied the round's rmax; counters of both parities must be clean
-            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
-            ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
+            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
         }
     }
@@ -636,7 +628,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
                 if (*(volatile u32*)&ctl->cnt[par] == 0) break;
                 push_phase_a<false>(A, par, rmax_fx, gtid, gsize, sm_cnt);
             } else {
-                push_phase_a_dense(A, par, rmax_fx, gtid, gsize, sm_cnt);
+                push_phase_a<true>(A, par, rmax_fx, gtid, gsize, sm_cnt);
             }
             grid.sync();
             const u32 fcnt = *(volatile u32*)&ctl->fcnt[par];
@@ -644,13 +636,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
             if (fcnt == 0) break;
             const bool next_scan = (i64)fedges >= A.scan_threshold;
             if (gtid == 0) t1 = globaltimer_ns();
-            if (have_list) {
-                if (next_scan) push_phase_b<false, false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
-                else push_phase_b<true, false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
-            } else {
-                if (next_scan) push_phase_b<false, true>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
-                else push_phase_b<true, true>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
-            }
+            if (next_scan) push_phase_b<false, false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
+            else push_phase_b<true, false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
             grid.sync();
             if (gtid == 0) {
                 u32 k = ctl->dbg_count;
@@ -698,8 +685,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_init(PushArgs A) {
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
     for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
     if (gtid == 0) {
-        ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
-        ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
+        ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
         ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
         ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
         ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0;
