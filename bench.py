@@ -34,7 +34,7 @@ PKG = "personalized-pagerank-algorithms-on-neo4j_b200"
 ALPHA, EPS = 0.15, 0.5
 # Push/walk balance (stand-in for the reference's wall-clock balancer, J/Fora_Whole_Graph.java:93-103, which
 # adapts to the machine it runs on): each arm uses the constant that matches its own measured costs.
-GPU_WALK_COST = 6.0    # B200: one walk ~ 6 relaxed edges
+GPU_WALK_COST = None   # library default: 6 while the graph fits in L2, 24 beyond (ppr_set_balance)
 CPU_WALK_COST = 32.0   # host core: one walk ~ 32 relaxed edges (the reference's 400 ns / walk)
 
 
@@ -179,7 +179,7 @@ def workload_config(args, q):
     return {"workload": "R-MAT scale-%d (n=%d, m=%d, a/b/c/d=0.57/0.19/0.19/0.05, relabelled, seed 42) FORA single-source PPR "
                         "(BASELINE.json configs[1] shape)" % (args.scale, n, n * args.edge_factor),
             "alpha": ALPHA, "eps": args.eps, "delta": "1/n", "p_f": "1/n", "queries_per_step": q,
-            "sources": "uniform over vertices with out-degree > 0, seed 1234",
+            "sources": "uniform over vertices with out-degree > 0, seed 1234", "cpu_walk_cost": CPU_WALK_COST,
             "l2": "L2 flushed (256 MiB write) before every step; working set at scale 20 is ~100 MB vs 126 MB L2"}
 
 
@@ -289,7 +289,7 @@ def main():
         "metric": "FORA SSPPR queries/s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (2^-62 fixed point; f64 only at the boundary)", "data": "synthetic",
-        "config": dict(workload_config(args, q), walk_cost=walk_cost, parallelism="%d independent query streams (one per GPU)" % world),
+        "config": dict(workload_config(args, q), walk_cost=walk_cost if walk_cost is not None else "auto (6 in L2, 24 beyond)", parallelism="%d independent query streams (one per GPU)" % world),
         "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": 4 * q, "d2h_bytes_per_step": 8 * g.n * q,
                 "api": "ppr_fora_batch (Fora_Whole_Graph.computeWholeGraphPPR per source), dense f64 result to pinned host memory"},
         "gpu_launches": int(acc["launches"]),

@@ -91,14 +91,15 @@ int32_t ppr_device_info(ppr_ctx* ctx, int32_t* sm_count, int64_t* total_mem, cha
 
 /* Tunables that replace the wall-clock push/walk balancer of J/Fora_Whole_Graph.java:35,93-103:
  * the push keeps halving rmax while (vertices pushed + edges relaxed) < walk_cost * r_sum * omega and
- * rounds < max_rounds.  Defaults: walk_cost = 6 (a walk costs about six relaxed edges on a B200; the
- * reference's 400 ns/walk against its Java push is about 32), max_rounds = 64. */
+ * rounds < max_rounds.  walk_cost < 0 (default) = automatic: 6 while the graph fits in the 126 MB L2, 24
+ * beyond (measured B200 costs; the reference's 400 ns/walk against its Java push is about 32).
+ * max_rounds default 64. */
 int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_rounds);
 
 /* Frontier-mode switch of the push kernels: an iteration whose frontier has at least this many out-edges
  * scatters with plain reductions and the next frontier is found by a dense sweep; smaller frontiers use
  * returning atomics and exact threshold-crossing detection.  Results are bit-identical either way.
- * < 0 restores the default (n); 0 = always sweep; INT64_MAX = never sweep.
+ * < 0 restores the default (n/4); 0 = always sweep; INT64_MAX = never sweep.
  * hot_min_indeg (>= 0; < 0 keeps the current value, default 64): minimum in-degree for a vertex to get one of
  * the 4096 hub slots whose incoming adds are staged in shared memory; applies to graphs created afterwards. */
 int32_t ppr_set_tuning(ppr_ctx* ctx, int64_t scan_threshold_edges, int32_t hot_min_indeg);

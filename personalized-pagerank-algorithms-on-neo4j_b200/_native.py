@@ -159,7 +159,7 @@ class Context:
         if rc != PPR_OK:
             raise PPRError(rc, (self.L.ppr_last_error(self.h) or b"").decode())
 
-    def set_balance(self, walk_cost=6.0, max_rounds=64):
+    def set_balance(self, walk_cost=-1.0, max_rounds=64):
         self.check(self.L.ppr_set_balance(self.h, walk_cost, max_rounds))
 
     def device_info(self):

@@ -63,7 +63,7 @@ extern "C" int32_t ppr_init(int32_t device, ppr_ctx** out) {
     ppr_ctx* ctx = new (std::nothrow) ppr_ctx();
     if (!ctx) return ctx_fail(nullptr, PPR_E_NOMEM, "ppr_init: host allocation failed");
     ctx->device = device;
-    ctx->walk_cost = 6.0;   // measured on B200: one walk costs about as much as six relaxed edges
+    ctx->walk_cost = -1.0;  // auto: 6 when the graph lives in L2, 24 otherwise (measured on B200)
     ctx->max_rounds = 64;
     ctx->scan_threshold = -1;
     ctx->hot_min_indeg = 64;
@@ -110,7 +110,7 @@ extern "C" int32_t ppr_device_info(ppr_ctx* ctx, int32_t* sm_count, int64_t* tot
 
 extern "C" int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_rounds) {
     if (!ctx) return PPR_E_INVALID;
-    if (!(walk_cost >= 0) || max_rounds < 1) return ctx_fail(ctx, PPR_E_INVALID, "ppr_set_balance: walk_cost >= 0, max_rounds >= 1");
+    if (max_rounds < 1) return ctx_fail(ctx, PPR_E_INVALID, "ppr_set_balance: max_rounds >= 1");
     ctx->walk_cost = walk_cost;
     ctx->max_rounds = max_rounds;
     return PPR_OK;
@@ -419,7 +419,7 @@ static void fill_push_args(PushArgs& A, ppr_graph* g, Workspace& w) {
     A.ws_v = w.ws_v; A.ws_begin = w.ws_begin; A.ws_inc = w.ws_inc; A.ws_rem = w.ws_rem;
     A.blk_a = w.blk_a; A.blk_b = w.blk_b; A.ctl = w.ctl; A.dbg = w.dbg;
     A.prep_adds_push_part = 1;
-    A.scan_threshold = g->ctx->scan_threshold < 0 ? g->d.n : g->ctx->scan_threshold;
+    A.scan_threshold = g->ctx->scan_threshold < 0 ? std::max<i64>(1, g->d.n / 4) : g->ctx->scan_threshold;
 }
 
 static cudaError_t launch_push(ppr_ctx* ctx, Workspace& w, PushArgs& A) {
@@ -469,6 +469,15 @@ static int32_t read_ctl(ppr_graph* g, Workspace& w) {
     CUDA_TRY(cudaMemcpyAsync(w.ctl_host, w.ctl, sizeof(PushCtl), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return PPR_OK;
+}
+
+// Push/walk balance constant.  A walk costs ~6 relaxed edges while col_idx and the vertex table fit in the
+// 126 MB L2 (scale 20: 0.10 ns per walk vs 0.013 ns per edge) and ~15-25 once walks miss to HBM (scale 22:
+// 0.14 ns vs 0.0095 ns); measured sweep in profiles/.  ppr_set_balance(walk_cost >= 0) overrides.
+static double effective_walk_cost(const ppr_graph* g) {
+    if (g->ctx->walk_cost >= 0) return g->ctx->walk_cost;
+    double footprint = 4.0 * (double)g->d.m + 8.0 * (double)g->d.n;
+    return footprint > 96.0 * 1024 * 1024 ? 24.0 : 6.0;
 }
 
 struct ForaParams { double delta, pfail, L, rmax, omega; };
@@ -526,7 +535,7 @@ static int32_t fora_launch(ppr_graph* g, Workspace& w, i32 src, double alpha, do
     ForaParams p = fora_params(g->d.n, g->d.m, alpha, eps, conf);
     PushArgs A;
     fill_push_args(A, g, w);
-    A.src = src; A.alpha_q64 = h_alpha_q64(alpha); A.alpha = alpha; A.omega = p.omega; A.walk_cost = ctx->walk_cost;
+    A.src = src; A.alpha_q64 = h_alpha_q64(alpha); A.alpha = alpha; A.omega = p.omega; A.walk_cost = effective_walk_cost(g);
     A.rmax0 = p.rmax; A.max_rounds = ctx->max_rounds; A.mode = PMODE_FORA; A.init = 1;
     A.zero_reserve_after_push = shard != 0; A.prep_adds_push_part = shard == 0;
     if (omega_out) *omega_out = p.omega;

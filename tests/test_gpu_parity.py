@@ -200,7 +200,7 @@ def test_fora_balance_knobs(pkg, ctx, G, OG, O):
         oraw, ost = O.b_fora(OG, 63, ALPHA, EPS, SEED, walk_cost=4.0, max_rounds=3)
         assert np.array_equal(G.last_raw(False)[0], oraw) and st["rounds"] == ost["rounds"] <= 3
     finally:
-        ctx.set_balance(6.0, 64)
+        ctx.set_balance(-1.0, 64)
 
 
 def test_frontier_modes_give_identical_bits(ctx, G, OG, R12, O):
