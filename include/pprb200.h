@@ -104,6 +104,10 @@ int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_rounds);
  * the 4096 hub slots whose incoming adds are staged in shared memory; applies to graphs created afterwards. */
 int32_t ppr_set_tuning(ppr_ctx* ctx, int64_t scan_threshold_edges, int32_t hot_min_indeg);
 
+/* All-pair backward search: targets advanced together per kernel launch (0 = automatic: sized so that the
+ * batch's residue matrix stays near the L2 capacity). */
+int32_t ppr_set_bwd_batch(ppr_ctx* ctx, int32_t targets_per_batch);
+
 /* Measurement helpers (bench.py): CUDA events on the context's compute stream, the stream every kernel
  * of this library is launched on (after joining the download stream), and an L2 flush (a write of a
  * 256 MiB scratch buffer, larger than the 126 MB L2).  slot is 0..3. */

@@ -52,6 +52,23 @@ __device__ __forceinline__ void warp_append_u64(u64* list, u32* counter, i64 cap
     }
 }
 
+// four predicated items per lane, one counter round trip per warp
+__device__ __forceinline__ void warp_append4_u64(u64* list, u32* counter, i64 cap, u32* err, const bool (&pred)[4], const u64 (&value)[4]) {
+    u32 m[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { m[k] = __ballot_sync(0xffffffffu, pred[k]); tot += __popc(m[k]); }
+    if (tot) {
+        u32 base = 0;
+        if (lane_id() == 0) base = atomicAdd(counter, tot);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (pred[k]) { u32 slot = base + __popc(m[k] & lanemask_lt()); if ((i64)slot < cap) list[slot] = value[k]; else *err = 1; }
+            base += __popc(m[k]);
+        }
+    }
+}
+
 __device__ __forceinline__ bool relax_in_edge(const BwdArgs& A, u64* rt, u32 u, u64 y) {
     u64 inc = mulhi64(y, __ldg(&A.invdeg[u]));
     u64 old = atomicAdd((ull*)&rt[u], (ull)inc);
@@ -73,8 +90,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_bwd_batch(BwdArgs A) {
 
     // seed: state was zeroed by the host (memset); one item per target with in-edges
     if (gtid == 0) {
-        ctl->cnt[0] = ctl->cnt[1] = 0; ctl->ns[0] = ctl->ns[1] = 0; ctl->nl[0] = ctl->nl[1] = 0;
-        ctl->nchunks[0] = ctl->nchunks[1] = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->err = 0; ctl->err_a = 0;
+        ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0;
+        ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->err = 0; ctl->err_a = 0;
         ctl->pairs = 0; ctl->pairs_needed = 0;
     }
     grid.sync();
@@ -95,47 +112,67 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_bwd_batch(BwdArgs A) {
     for (;;) {
         const u32 cnt = *(volatile u32*)&ctl->cnt[par];
         if (cnt == 0 || *(volatile u32*)&ctl->err) break;
-        // ---------------- phase A
+        // ---------------- phase A: warp-granular tiles of 128 items, one packed staging atomic per tile
         if (gtid == 0) {
-            ctl->cnt[par ^ 1] = 0; ctl->ns[par ^ 1] = 0; ctl->nl[par ^ 1] = 0; ctl->nchunks[par ^ 1] = 0;
+            ctl->cnt[par ^ 1] = 0; ctl->stage[par ^ 1] = 0;
             ctl->pushes += cnt; ctl->iters += 1;
         }
         u64 edges_local = 0;
-        for (i64 base = 0; base < cnt; base += gsize) {
-            i64 i = base + gtid;
-            bool is_small = false, is_large = false;
-            u64 pk = 0, y = 0; u32 slot_t = 0;
-            if (i < cnt) {
-                u64 item = A.front[par][i];
-                slot_t = (u32)(item >> 32);
-                u32 v = (u32)item;
-                u64* rt = A.r + (i64)slot_t * n;
-                u64 x = rt[v];
-                rt[v] = 0;
-                u64 a = mulhi64(x, A.alpha_q64);
-                A.reserve[(i64)slot_t * n + v] += a;
-                y = x - a;
-                pk = A.in_vtx[v];
-                u32 d = vtx_deg(pk);
-                edges_local += d;
-                is_small = d > 0 && d <= PUSH_SMALL_MAX;
-                is_large = d > PUSH_SMALL_MAX;
+        for (i64 tile = gwarp * 128; tile < cnt; tile += nwarps * 128) {
+            u64 pk[4], y[4], item[4];
+            u32 cls[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { i64 i = tile + k * 32 + lane; item[k] = i < cnt ? A.front[par][i] : ~0ull; }
+            u32 my_nch = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                pk[k] = 0; y[k] = 0; cls[k] = 0;
+                if (item[k] != ~0ull) {
+                    u32 slot_t = (u32)(item[k] >> 32), v = (u32)item[k];
+                    u64* rt = A.r + (i64)slot_t * n;
+                    u64 x = rt[v];
+                    rt[v] = 0;
+                    u64 a = mulhi64(x, A.alpha_q64);
+                    A.reserve[(i64)slot_t * n + v] += a;
+                    y[k] = x - a;
+                    pk[k] = A.in_vtx[v];
+                    u32 d = vtx_deg(pk[k]);
+                    edges_local += d;
+                    cls[k] = d == 0 ? 0u : (d <= PUSH_SMALL_MAX ? 1u : 2u);
+                    if (cls[k] == 2) my_nch += (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
+                }
             }
-            u32 mask = __ballot_sync(0xffffffffu, is_small);
-            if (mask) {
-                u32 leader = __ffs(mask) - 1, b = 0;
-                if (lane == leader) b = atomicAdd(&ctl->ns[par], (u32)__popc(mask));
-                b = __shfl_sync(0xffffffffu, b, leader);
-                if (is_small) { u32 s = b + __popc(mask & lanemask_lt()); A.s_pack[s] = pk; A.s_y[s] = y; A.s_t[s] = slot_t; }
+            u32 ms[4], small_total = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { ms[k] = __ballot_sync(0xffffffffu, cls[k] == 1); small_total += __popc(ms[k]); }
+            u32 chunk_incl = 0, chunk_total = 0;
+            if (__any_sync(0xffffffffu, my_nch != 0)) {
+                chunk_incl = my_nch;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, chunk_incl, o); if (lane >= o) chunk_incl += t; }
+                chunk_total = __shfl_sync(0xffffffffu, chunk_incl, 31);
             }
-            if (is_large) {
-                u32 s = atomicAdd(&ctl->nl[par], 1u);
-                A.l_pack[s] = pk; A.l_y[s] = y; A.l_t[s] = slot_t;
-                u32 d = vtx_deg(pk);
-                u32 nch = (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
-                u32 cb = atomicAdd(&ctl->nchunks[par], nch);
-                if ((i64)cb + nch <= A.chunk_cap) { for (u32 c = 0; c < nch; c++) A.chunks[cb + c] = make_uint2(s, c); }
-                else ctl->err_a = 1;
+            if (small_total | chunk_total) {
+                u64 base = 0;
+                if (lane == 0) base = atomicAdd((ull*)&ctl->stage[par], ((ull)chunk_total << 32) | (ull)small_total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                u32 off = (u32)base;
+                u32 cb = (u32)(base >> 32) + chunk_incl - my_nch;
+                if ((i64)off + small_total > A.front_cap || (i64)(base >> 32) + chunk_total > A.chunk_cap) {
+                    if (lane == 0) ctl->err_a = 1;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (cls[k] == 1) { u32 s = off + __popc(ms[k] & lanemask_lt()); A.s_pack[s] = pk[k]; A.s_y[s] = y[k]; A.s_t[s] = (u32)(item[k] >> 32); }
+                        off += __popc(ms[k]);
+                        if (cls[k] == 2) {
+                            u32 nch = (vtx_deg(pk[k]) + PUSH_CHUNK - 1) / PUSH_CHUNK;
+                            A.l_pack[cb] = pk[k]; A.l_y[cb] = y[k]; A.l_t[cb] = (u32)(item[k] >> 32);
+                            for (u32 c = 0; c < nch; c++) A.chunks[cb + c] = make_uint2(cb, c);
+                            cb += nch;
+                        }
+                    }
+                }
             }
         }
         edges_local = warp_sum_u64(edges_local);
@@ -143,15 +180,16 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_bwd_batch(BwdArgs A) {
         grid.sync();
         if (*(volatile u32*)&ctl->err_a) break;
         // ---------------- phase B
-        const u32 ns = *(volatile u32*)&ctl->ns[par];
-        const u32 nch = *(volatile u32*)&ctl->nchunks[par];
+        const u64 staged = *(volatile u64*)&ctl->stage[par];
+        const u32 ns = (u32)staged, nch = (u32)(staged >> 32);
         u64* next = A.front[par ^ 1];
         u32* next_cnt = &ctl->cnt[par ^ 1];
         u64* w_excl = sm_excl + wib * 32; u64* w_beg = sm_beg + wib * 32; u64* w_y = sm_y + wib * 32; u32* w_t = sm_t + wib * 32;
-        for (i64 wbase = gwarp * 32; wbase < ns; wbase += nwarps * 32) {
+        const i64 bw = min((i64)32, max((i64)1, ((i64)ns + nwarps - 1) / nwarps));
+        for (i64 wbase = gwarp * bw; wbase < ns; wbase += nwarps * bw) {
             i64 item = wbase + lane;
             u64 pk = 0, y = 0; u32 st = 0;
-            if (item < ns) { pk = A.s_pack[item]; y = A.s_y[item]; st = A.s_t[item]; }
+            if (lane < bw && item < ns) { pk = A.s_pack[item]; y = A.s_y[item]; st = A.s_t[item]; }
             u32 d = vtx_deg(pk), incl = d;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -159,20 +197,28 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_bwd_batch(BwdArgs A) {
             u32 total = __shfl_sync(0xffffffffu, incl, 31);
             w_excl[lane] = excl; w_beg[lane] = vtx_begin(pk) - excl; w_y[lane] = y; w_t[lane] = st;
             __syncwarp();
-            for (u32 eb = 0; eb < total; eb += 32) {
-                u32 e = eb + lane;
-                bool cross = false;
-                u64 nitem = 0;
-                if (e < total) {
-                    int o = 0;
+            for (u32 eb = 0; eb < total; eb += 128) {
+                u32 u[4], tt[4];
+                u64 yy[4], nitem[4];
+                bool cr[4];
 #pragma unroll
-                    for (int s = 16; s > 0; s >>= 1) { int p = o + s; if ((u32)w_excl[p] <= e) o = p; }
-                    u32 u = (u32)__ldg(&A.row_idx[w_beg[o] + e]);
-                    u32 t = w_t[o];
-                    cross = relax_in_edge(A, A.r + (i64)t * n, u, w_y[o]);
-                    nitem = ((u64)t << 32) | u;
+                for (int k = 0; k < 4; k++) {
+                    u32 e = eb + 32 * k + lane;
+                    u[k] = 0xffffffffu; tt[k] = 0; yy[k] = 0;
+                    if (e < total) {
+                        int o = 0;
+#pragma unroll
+                        for (int s = 16; s > 0; s >>= 1) { int p = o + s; if ((u32)w_excl[p] <= e) o = p; }
+                        u[k] = (u32)__ldg(&A.row_idx[w_beg[o] + e]);
+                        tt[k] = w_t[o]; yy[k] = w_y[o];
+                    }
                 }
-                warp_append_u64(next, next_cnt, A.front_cap, &ctl->err, cross, nitem);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    cr[k] = u[k] != 0xffffffffu ? relax_in_edge(A, A.r + (i64)tt[k] * n, u[k], yy[k]) : false;
+                    nitem[k] = ((u64)tt[k] << 32) | u[k];
+                }
+                warp_append4_u64(next, next_cnt, A.front_cap, &ctl->err, cr, nitem);
             }
             __syncwarp();
         }
@@ -185,16 +231,18 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_bwd_batch(BwdArgs A) {
             u32 len = min((u32)PUSH_CHUNK, d - off);
             const i32* row = A.row_idx + vtx_begin(pk) + off;
             u64* rt = A.r + (i64)t * n;
-            for (u32 eb = 0; eb < len; eb += 32) {
-                u32 e = eb + lane;
-                bool cross = false;
-                u64 nitem = 0;
-                if (e < len) {
-                    u32 u = (u32)__ldg(&row[e]);
-                    cross = relax_in_edge(A, rt, u, y);
-                    nitem = ((u64)t << 32) | u;
+            for (u32 eb = 0; eb < len; eb += 128) {
+                u32 u[4];
+                u64 nitem[4];
+                bool cr[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { u32 e = eb + 32 * k + lane; u[k] = e < len ? (u32)__ldg(&row[e]) : 0xffffffffu; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    cr[k] = u[k] != 0xffffffffu ? relax_in_edge(A, rt, u[k], y) : false;
+                    nitem[k] = ((u64)t << 32) | u[k];
                 }
-                warp_append_u64(next, next_cnt, A.front_cap, &ctl->err, cross, nitem);
+                warp_append4_u64(next, next_cnt, A.front_cap, &ctl->err, cr, nitem);
             }
         }
         grid.sync();

@@ -139,6 +139,7 @@ struct ppr_ctx {
     double walk_cost;
     int max_rounds;
     i64 scan_threshold;    // < 0: default (n)
+    i32 bwd_batch;         // all-pair backward search: targets per batch (0 = automatic)
     i32 hot_min_indeg;     // a vertex needs at least this in-degree to get a hub slot (graphs created afterwards)
 };
 
