@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(WALK_THREADS, 4) k_walk(WalkArgs A) {
     bool active = false;
     WalkState w; w.start = w.cur = w.restart = w.step = 0; w.j = 0; w.first = false;
     u64 inc = 0, steps = 0, done = 0;
+    u64 src_acc = 0;  // contributions to the query source stay in a register: in Monte-Carlo 15 % of all walks stop on
+                      // it, and same-address REDs serialise at ~0.7 ns each in L2
 
     for (;;) {
         u32 needy = __ballot_sync(0xffffffffu, !active);
@@ -135,7 +137,8 @@ __global__ void __launch_bounds__(WALK_THREADS, 4) k_walk(WalkArgs A) {
         if (!__any_sync(0xffffffffu, active)) break;
         if (active) {
             if (walk_step(w, A.out_vtx, A.col_idx, A.k0, A.k1, A.tstop, steps)) {
-                atomicAdd((ull*)&A.target[w.cur], (ull)inc);
+                if (w.cur == (u32)A.src) src_acc += inc;
+                else atomicAdd((ull*)&A.target[w.cur], (ull)inc);
                 active = false;
                 done++;
             }
@@ -143,7 +146,9 @@ __global__ void __launch_bounds__(WALK_THREADS, 4) k_walk(WalkArgs A) {
     }
     steps = warp_sum_u64(steps);
     done = warp_sum_u64(done);
+    src_acc = warp_sum_u64(src_acc);
     if (lane == 0) {
+        if (src_acc) atomicAdd((ull*)&A.target[A.src], (ull)src_acc);
         atomicAdd((ull*)&ctl->steps, (ull)steps);
         atomicAdd((ull*)&ctl->walks_done, (ull)done);
     }
