@@ -62,31 +62,54 @@ def monte_carlo_sharded(graph, src, alpha, eps, seed, rank, world, out=None, gro
 
 def merge_pairs(parts, n):
     """Concatenate per-rank inverted indexes (src_ptr, tgt, val) whose target blocks ascend with rank."""
+    cnts = [np.diff(p[0]) for p in parts]
     ptr = np.zeros(n + 1, np.int64)
-    for p, _, _ in parts:
-        ptr[1:] += np.diff(p)
-    np.cumsum(ptr[1:], out=ptr[1:])
+    np.cumsum(sum(cnts), out=ptr[1:])
     total = int(ptr[-1])
-    tgt = np.zeros(total, parts[0][1].dtype if parts else np.int32)
-    val = np.zeros(total, parts[0][2].dtype if parts else np.float64)
-    pos = ptr[:-1].copy()
-    for p, t, v in parts:  # rank order = ascending targets, so rows stay sorted by target
-        cnt = np.diff(p)
-        if t.size == 0:
-            continue
-        rows = np.repeat(np.arange(n), cnt)
-        off = np.arange(t.size) - np.repeat(p[:-1], cnt)
-        dst = pos[rows] + off
-        tgt[dst] = t
-        val[dst] = v
-        pos += cnt
+    tgt = np.empty(total, parts[0][1].dtype if parts else np.int32)
+    val = np.empty(total, parts[0][2].dtype if parts else np.float64)
+    start = ptr[:-1].copy()                       # where the next part's slice of row v begins
+    for (p, t, v), cnt in zip(parts, cnts):       # rank order = ascending targets, so rows stay sorted by target
+        if t.size:
+            dst = np.repeat(start - p[:-1], cnt)  # row-wise shift from the part's position to the merged position
+            dst += np.arange(t.size, dtype=np.int64)
+            tgt[dst] = t
+            val[dst] = v
+        start += cnt
     return ptr, tgt, val
 
 
 def gather_pairs(local, n, group=None):
-    """All-gather the per-rank (src_ptr, tgt, val) results of a block-partitioned all-pair run."""
+    """All-gather the per-rank (src_ptr, tgt, val) results of a block-partitioned all-pair run.
+
+    With NCCL the three arrays travel as padded device tensors (one all_gather each, over NVLink); with gloo
+    (CPU tests) as pickled objects.
+    """
+    import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    parts = [None] * world
-    dist.all_gather_object(parts, local, group=group)
+    if dist.get_backend(group) != "nccl":
+        parts = [None] * world
+        dist.all_gather_object(parts, local, group=group)
+        return merge_pairs(parts, n)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ptr, tgt, val = local
+    cnt = torch.tensor([tgt.shape[0]], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    cnts = [int(c.item()) for c in cnts]
+    mx = max(max(cnts), 1)
+
+    def gather(arr, length, np_dtype, t_dtype):
+        buf = torch.zeros(length, dtype=t_dtype, device=dev)
+        if arr.shape[0]:
+            buf[:arr.shape[0]] = torch.from_numpy(np.ascontiguousarray(arr).view(np_dtype)).to(dev)
+        out = torch.empty(world * length, dtype=t_dtype, device=dev)
+        dist.all_gather_into_tensor(out, buf, group=group)
+        return out.cpu().numpy().reshape(world, length)
+
+    P = gather(ptr, n + 1, np.int64, torch.int64)
+    T = gather(tgt, mx, np.int32, torch.int32)
+    V = gather(val, mx, np.int64, torch.int64)
+    parts = [(P[r], T[r, :cnts[r]], V[r, :cnts[r]].view(val.dtype)) for r in range(world)]
     return merge_pairs(parts, n)
