@@ -122,6 +122,11 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_push_query launch, from `ncu --set full` captures of
+# scripts/one_query.py at library defaults (profiles/r01_ncu_full_summary.txt); bytes per launch, keyed by R-MAT scale
+NCU_PUSH_TRAFFIC = {20: 0.320043e9 + 39.152896e6, 22: 6.574943e9 + 1.402604e9}
+
+
 def cpu_port_query(O, og, src, eps, seed, walk_cost):
     t0 = time.perf_counter()
     _, st = O.a_fora(og, int(src), ALPHA, eps, seed, walk_cost=walk_cost)
@@ -295,7 +300,10 @@ def main():
         "gpu_launches": int(acc["launches"]),
         "clocks": m["clocks"],
         "roofline": {"bound": "hbm", "kernel": "k_push_query", "achieved": push_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": push_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": push_gbs / peak, "traffic": NCU_PUSH_TRAFFIC.get(args.scale) if args.walk_cost is None else None,
+                     "traffic_note": "DRAM bytes per launch from the ncu --set full capture in profiles/ (same scale, library defaults); "
+                                     "algorithmic bytes per launch = %.3g" % (push_bytes / max(nq_rank, 1)),
+                     "peak_source": peak_src,
                      "algorithmic_bytes": "48*V_p + 24*E_p", "V_p": acc["pushes"], "E_p": acc["edges"],
                      "launches": nq_rank, "avg_launch_ms": acc["ms_push"] / max(nq_rank, 1),
                      "share_of_step": acc["ms_push"] / m["ms"]},
