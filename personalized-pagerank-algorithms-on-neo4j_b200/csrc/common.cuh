@@ -154,8 +154,6 @@ struct DevGraph {
     u32* push_idx;  // [m] col_idx with hub targets encoded as HOT_BIT | slot
     u32* hot_id;    // [n_hot] slot -> vertex
     u32 n_hot;
-    uint2* big_chunks;  // [n_big_chunks] static (vertex, chunk index) of rows longer than PUSH_SMALL_MAX
-    u32 n_big_chunks;
 };
 
 struct Workspace {

@@ -280,7 +280,7 @@ extern "C" int32_t ppr_graph_destroy(ppr_graph* g) {
     if (x && x->ws1_ready) ws_free(g->ws[1]);
     if (x && x->bws_ready) bws_free(x->bws);
     cudaFree(g->d.out_vtx); cudaFree(g->d.col_idx); cudaFree(g->d.out_deg);
-    cudaFree(g->d.in_vtx); cudaFree(g->d.row_idx); cudaFree(g->d.invdeg); cudaFree(g->d.push_idx); cudaFree(g->d.hot_id); cudaFree(g->d.big_chunks);
+    cudaFree(g->d.in_vtx); cudaFree(g->d.row_idx); cudaFree(g->d.invdeg); cudaFree(g->d.push_idx); cudaFree(g->d.hot_id);
     for (size_t i = 0; i < g_extras.size(); i++) if (g_extras[i].first == g) { delete g_extras[i].second; g_extras.erase(g_extras.begin() + i); break; }
     delete g;
     return PPR_OK;
@@ -336,15 +336,6 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
         for (i64 e = 0; e < m; e++) { i32 sl = slot_of[(size_t)col_idx[e]]; push_idx[(size_t)e] = sl >= 0 ? (HOT_BIT | (u32)sl) : (u32)col_idx[e]; }
     } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed"); }
 
-    std::vector<uint2> big_chunks;
-    try {
-        big_chunks.reserve((size_t)chunk_cap);
-        for (i64 v = 0; v < n; v++) {
-            i64 d = row_ptr[v + 1] - row_ptr[v];
-            if (d > PUSH_SMALL_MAX) for (i64 c = 0; c < (d + PUSH_CHUNK - 1) / PUSH_CHUNK; c++) big_chunks.push_back(make_uint2((u32)v, (u32)c));
-        }
-    } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed"); }
-
     cudaSetDevice(ctx->device);
     ppr_graph* g = new (std::nothrow) ppr_graph();
     GraphExtra* x = new (std::nothrow) GraphExtra();
@@ -363,9 +354,6 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     G_TRY(dalloc(&d_ptr, (size_t)n + 1));
     G_TRY(dalloc(&g->d.push_idx, (size_t)m)); G_TRY(dalloc(&g->d.hot_id, (size_t)HOT_SLOTS));
     g->d.n_hot = (u32)hot_id.size();
-    G_TRY(dalloc(&g->d.big_chunks, big_chunks.size()));
-    g->d.n_big_chunks = (u32)big_chunks.size();
-    if (!big_chunks.empty()) G_TRY(cudaMemcpyAsync(g->d.big_chunks, big_chunks.data(), big_chunks.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
     int blocks = ctx->sm_count * 8;
     G_TRY(cudaMemcpyAsync(d_ptr, row_ptr, ((size_t)n + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
     k_build_vtx<<<blocks, 256, 0, ctx->stream>>>(d_ptr, g->d.out_vtx, g->d.out_deg, g->d.invdeg, n);
@@ -420,7 +408,6 @@ static void fill_push_args(PushArgs& A, ppr_graph* g, Workspace& w) {
     memset(&A, 0, sizeof A);
     A.n = g->d.n; A.out_vtx = g->d.out_vtx; A.col_idx = g->d.col_idx; A.out_deg = g->d.out_deg;
     A.push_idx = g->d.push_idx; A.hot_id = g->d.hot_id; A.n_hot = g->d.n_hot;
-    A.big_chunks = g->d.big_chunks; A.n_big_chunks = g->d.n_big_chunks;
     A.r = w.r; A.reserve = w.reserve; A.est = w.est; A.front[0] = w.front[0]; A.front[1] = w.front[1];
     A.s_pack = w.s_pack; A.s_q = w.s_q; A.l_pack = w.l_pack; A.l_q = w.l_q; A.chunks = w.chunks;
     A.ws_v = w.ws_v; A.ws_begin = w.ws_begin; A.ws_inc = w.ws_inc; A.ws_rem = w.ws_rem;

@@ -39,8 +39,6 @@ struct PushArgs {
     const u32* push_idx;   // col_idx with hub targets replaced by HOT_BIT | slot (see hot_id)
     const u32* hot_id;     // slot -> vertex id of the n_hot highest in-degree vertices
     u32 n_hot;
-    const uint2* big_chunks;   // static (vertex, chunk index) descriptors of every row longer than PUSH_SMALL_MAX
-    u32 n_big_chunks;
     // state
     u64* r;
     u64* reserve;
@@ -170,7 +168,7 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
                 if (d == 0) { left = 0; dang_local += y; }
                 else { q[k] = y / (u64)d; left = y - q[k] * (u64)d; }
                 A.r[v[k]] = left;
-                A.reserve[v[k]] += a;
+                A.reserve[v[k]] += a;   // (a RED here was measured 2x slower than this load + store)
                 resv_local += a;
                 edges_local += d;
                 pushed_local += 1;
@@ -231,64 +229,6 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     }
 }
 
-// --------------------------------------------------------------------------------- phase A, dense staging
-// Round starts and iterations that follow a SCAN-mode phase B have no frontier list: sweep every vertex,
-// capture those at or above threshold and write the per-edge amount to the dense array qv[] (0 = not
-// pushed).  Pure streaming: coalesced reads of r[] / the vertex table, no staging lists, no atomics in
-// the loop.  Phase B then walks the vertex range itself (short rows) and the graph's static chunk
-// table (long rows), skipping zeros.
-__device__ void push_phase_a_dense(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u32* sm_cnt) {
-    PushCtl* ctl = A.ctl;
-    if (gtid == 0) {
-        ctl->cnt[par ^ 1] = 0; ctl->stage[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
-        ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0;
-    }
-    u64 edges_local = 0, resv_local = 0, dang_local = 0, pushed_local = 0;
-    u64* qv = A.s_q;
-    for (i64 v = gtid; v < A.n; v += gsize) {
-        u64 x = A.r[v];
-        u64 q = 0;
-        if (x) {
-            u64 pk = A.out_vtx[v];
-            u32 d = vtx_deg(pk);
-            if (x >= thr_fwd(rmax_fx, d)) {
-                u64 a = mulhi64(x, A.alpha_q64);
-                u64 y = x - a;
-                u64 left;
-                if (d == 0) { left = 0; dang_local += y; }
-                else { q = y / (u64)d; left = y - q * (u64)d; }
-                A.r[v] = left;
-                A.reserve[v] += a;
-                resv_local += a;
-                edges_local += d;
-                pushed_local += 1;
-            }
-        }
-        qv[v] = q;
-    }
-    u64* sm_acc = reinterpret_cast<u64*>(sm_cnt + 8);
-    __syncthreads();
-    if (threadIdx.x < 4) sm_acc[threadIdx.x] = 0;
-    __syncthreads();
-    edges_local = warp_sum_u64(edges_local);
-    resv_local = warp_sum_u64(resv_local);
-    dang_local = warp_sum_u64(dang_local);
-    pushed_local = warp_sum_u64(pushed_local);
-    if (lane_id() == 0) {
-        if (pushed_local) atomicAdd((ull*)&sm_acc[0], (ull)pushed_local);
-        if (edges_local) atomicAdd((ull*)&sm_acc[1], (ull)edges_local);
-        if (resv_local) atomicAdd((ull*)&sm_acc[2], (ull)resv_local);
-        if (dang_local) atomicAdd((ull*)&sm_acc[3], (ull)dang_local);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (sm_acc[0]) atomicAdd(&ctl->fcnt[par], (u32)sm_acc[0]);
-        if (sm_acc[1]) atomicAdd((ull*)&ctl->fedges[par], (ull)sm_acc[1]);
-        if (sm_acc[2]) atomicAdd((ull*)&ctl->reserve_total, (ull)sm_acc[2]);
-        if (sm_acc[3]) atomicAdd((ull*)&ctl->dang[par], (ull)sm_acc[3]);
-    }
-}
-
 // --------------------------------------------------------------------------------- phase B
 // One relaxed edge.  LIST: returning atomic + crossing test; otherwise a fire-and-forget reduction.
 template <bool LIST>
@@ -309,15 +249,13 @@ __device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32& 
     }
 }
 
-template <bool LIST, bool DENSE>
+template <bool LIST>
 __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u64* sm_excl /*[warps][32]*/,
                              u64* sm_beg, u64* sm_q, u64* sm_hot /*[HOT_SLOTS], all zero on entry and exit; unused when LIST*/) {
     PushCtl* ctl = A.ctl;
-    // item source: compacted staging written by the list-mode phase A, or (DENSE) the vertex range itself
-    // with qv[] and the graph's static chunk table
     const u64 staged = *(volatile u64*)&ctl->stage[par];
-    const i64 ns = DENSE ? A.n : (i64)(u32)staged;
-    const u32 nch = DENSE ? A.n_big_chunks : (u32)(staged >> 32);
+    const i64 ns = (i64)(u32)staged;
+    const u32 nch = (u32)(staged >> 32);
     const i64 gwarp = gtid >> 5, nwarps = gsize >> 5;
     const u32 lane = lane_id();
     const int wib = threadIdx.x >> 5;
@@ -330,17 +268,11 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     // (1) short rows: up to 32 vertices per warp, lanes sweep the concatenated edge list.  When the
     // frontier is small the batch shrinks so that every warp of the grid gets some rows (a warp works
     // through its batch serially, one dependent atomic round trip per 32 edges).
-    const i64 bw = DENSE ? (i64)32 : min((i64)32, max((i64)1, ((i64)ns + nwarps - 1) / nwarps));
+    const i64 bw = min((i64)32, max((i64)1, ((i64)ns + nwarps - 1) / nwarps));
     for (i64 wbase = gwarp * bw; wbase < ns; wbase += nwarps * bw) {
         i64 item = wbase + lane;
         u64 pk = 0, q = 0;
-        if (DENSE) {
-            if (item < ns) {
-                q = A.s_q[item];                       // qv[v]
-                if (q) { pk = A.out_vtx[item]; if (vtx_deg(pk) > PUSH_SMALL_MAX) pk = 0; }   // long rows: chunk table below
-            }
-            if (!__any_sync(0xffffffffu, pk != 0)) continue;
-        } else if (lane < bw && item < ns) { pk = A.s_pack[item]; q = A.s_q[item]; }
+        if (lane < bw && item < ns) { pk = A.s_pack[item]; q = A.s_q[item]; }
         u32 d = vtx_deg(pk);
         u32 incl = d;
 #pragma unroll
@@ -377,18 +309,9 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
 
     // (2) long rows: one warp per PUSH_CHUNK-edge chunk, four independent edges per lane in flight
     for (i64 c = gwarp; c < nch; c += nwarps) {
-        u64 pk, q;
-        uint2 desc;
-        if (DENSE) {
-            desc = A.big_chunks[c];                    // (vertex, chunk index)
-            q = A.s_q[desc.x];
-            if (q == 0) continue;
-            pk = A.out_vtx[desc.x];
-        } else {
-            desc = A.chunks[c];
-            pk = A.l_pack[desc.x];
-            q = A.l_q[desc.x];
-        }
+        uint2 desc = A.chunks[c];
+        u64 pk = A.l_pack[desc.x];
+        u64 q = A.l_q[desc.x];
         u32 d = vtx_deg(pk);
         u32 off = desc.y * PUSH_CHUNK;
         u32 len = min((u32)PUSH_CHUNK, d - off);
@@ -636,8 +559,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
             if (fcnt == 0) break;
             const bool next_scan = (i64)fedges >= A.scan_threshold;
             if (gtid == 0) t1 = globaltimer_ns();
-            if (next_scan) push_phase_b<false, false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
-            else push_phase_b<true, false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
+            if (next_scan) push_phase_b<false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
+            else push_phase_b<true>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
             grid.sync();
             if (gtid == 0) {
                 u32 k = ctl->dbg_count;
@@ -712,5 +635,5 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_b(PushArgs A, int par) {
     __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
-    push_phase_b<true, false>(A, par, A.ctl->rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, nullptr);
+    push_phase_b<true>(A, par, A.ctl->rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, nullptr);
 }

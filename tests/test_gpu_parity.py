@@ -388,3 +388,66 @@ def test_error_codes(pkg, G):
             call()
         assert e.value.code == E.PPR_E_INVALID
     G.fora(0, ALPHA, EPS, 1)                                   # the context stays usable after errors
+
+
+# ------------------------------------------------------------------ edge-case graphs
+def _edge_graphs(pkg):
+    G = pkg.graphio.csr_from_edges
+    star_src = [0] * 1000 + list(range(1, 1001))            # hub with 1000 out-edges (4 chunks) and 1000 in-edges
+    star_dst = list(range(1, 1001)) + [0] * 1000
+    return {
+        "self_loop": G(1, [0], [0]),
+        "two_cycle": G(2, [0, 1], [1, 0]),
+        "path_with_sink": G(5, [0, 1, 2, 3], [1, 2, 3, 4]),
+        "duplicates_and_loops": G(4, [0, 0, 0, 1, 1, 2, 2, 3], [1, 1, 0, 2, 2, 0, 3, 3]),
+        "star_1000": G(1001, star_src, star_dst),
+        "hub_to_sinks": G(700, [0] * 699, list(range(1, 700))),   # one long row, every target dangling
+    }
+
+
+def test_edge_case_graphs(pkg, ctx, O):
+    for name, (rp, ci) in _edge_graphs(pkg).items():
+        g = pkg.Graph(ctx, rp, ci)
+        og = O.OGraph(rp, ci)
+        try:
+            for s in sorted({0, og.n - 1, og.n // 2}):
+                for rmax in (1e-3, 1e-9):
+                    g.forward_push(s, ALPHA, rmax)
+                    res, r = g.last_raw()
+                    ores, orr, _ = O.b_forward_push(og, s, ALPHA, rmax)
+                    assert np.array_equal(res, ores) and np.array_equal(r, orr), (name, s, rmax)
+                    fr = g.push_trace(s, ALPHA, rmax)
+                    _, _, ost = O.b_forward_push(og, s, ALPHA, rmax, trace=True)
+                    assert len(fr) == len(ost["frontiers"]) and all(np.array_equal(a, b) for a, b in zip(fr, ost["frontiers"])), name
+                for flags in (0, 1):
+                    check_fora(g, og, O, s, EPS, flags)
+                g.monte_carlo(s, ALPHA, 1.0, SEED)
+                assert np.array_equal(g.last_raw(False)[0], O.b_monte_carlo(og, s, ALPHA, 1.0, SEED)[0]), name
+                g.backward_search(s, ALPHA, 1e-4)
+                bres, br = g.last_raw()
+                obres, obr, _ = O.b_backward_search(og, s, ALPHA, 1e-4)
+                assert np.array_equal(bres, obres) and np.array_equal(br, obr), name
+                k = min(3, og.n)
+                ids, vals, _ = g.fora_topk(s, ALPHA, EPS, k, SEED)
+                oest, _ = O.b_fora_topk(og, s, ALPHA, EPS, k, SEED)
+                assert np.array_equal(g.last_raw(False)[0], oest) and np.array_equal(ids, O.topk_select(oest, k)), name
+                pm = g.power_iteration(s, ALPHA, 100)
+                assert np.abs(pm - O.power_method(og, s, ALPHA, 100)).max() < 1e-13
+            ptr, tgt, val, _ = g.backward_all_pairs(ALPHA, 1e-4, raw=True)
+            optr, otgt, oval, _ = O.b_base_all_pairs(og, ALPHA, 1e-4)
+            assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval), name
+        finally:
+            g.close()
+
+
+def test_graph_without_edges(pkg, ctx):
+    g = pkg.Graph(ctx, np.zeros(4, np.int64), np.zeros(0, np.int32))
+    try:
+        reserve, residue, rsum, st = g.forward_push(1, ALPHA, 1e-6)       # dangling source: {s: 1}, rsum 0
+        assert reserve[1] == 1.0 and reserve.sum() == 1.0 and rsum == 0.0 and st["pushes"] == 0
+        ppr, _ = g.monte_carlo(2, ALPHA, 1.0, 1)
+        assert np.count_nonzero(ppr) == 1 and ppr[2] > 0.99
+        with pytest.raises(pkg.PPRError):                                 # FORA's rmax divides by m
+            g.fora(0, ALPHA, EPS, 1)
+    finally:
+        g.close()
