@@ -29,7 +29,7 @@
 //                every out-edge (v,u) adds q to r[u];
 //        d == 0: q = y goes to r[source];  r[v] = 0.
 //     Mass is conserved exactly: sum(reserve) + sum(r) == FX_ONE at all times.
-//   * Threshold: rmax_fx = max(1, (uint64)(rmax * 2^62));
+//   * Threshold: rmax_fx = max(2^64/alpha_q64 + 2, (uint64)(rmax * 2^62))  (floor: a push must move >= 1 unit to reserve);
 //        thr(u) = d(u)==0 ? 1 : saturating(rmax_fx * d(u)).     (J/Forward_Push.java:132: r/d >= rmax;
 //        d==0 gives +inf >= rmax, i.e. any positive residue on a dangling vertex is pushed)
 //   * Synchronous schedule: iteration k's frontier is {v : r[v] >= thr(v)}; all frontier vertices
@@ -469,11 +469,15 @@ inline u64 thr_fwd(u64 rmax_fx, i64 d) {
     unsigned __int128 p = (unsigned __int128)rmax_fx * (u64)d;
     return (p >> 64) ? ~0ull : (u64)p;
 }
-inline u64 rmax_to_fx(double rmax) {
+// Smallest usable threshold: below 1/alpha units mulhi64(x, alpha_q64) is 0, a push would move no mass into the
+// reserve and a cycle could circulate forever.  (2^-62 / alpha ~ 1e-18: far below any meaningful rmax.)
+inline u64 rmax_floor_fx(u64 alpha_q64) { return ~0ull / alpha_q64 + 2; }
+inline u64 rmax_to_fx(double rmax, u64 alpha_q64) {
+    const u64 lo = rmax_floor_fx(alpha_q64);
     double x = rmax * FX_SCALE;
-    if (!(x >= 1.0)) return 1;
+    if (!(x >= 1.0)) return lo;
     if (x >= 18446744073709551615.0) return ~0ull;
-    return (u64)x;
+    return std::max(lo, (u64)x);
 }
 
 struct Trace {  // frontier sequence of a synchronous push (ascending ids inside an iteration)
@@ -610,7 +614,7 @@ void b_fora(const Graph& g, i32 s, double alpha, double eps, u64 seed, double wa
         int rounds = 0;
         u64 rfx = 0;
         for (;;) {
-            rfx = rmax_to_fx(rmax);
+            rfx = rmax_to_fx(rmax, aq);
             b_push_round(g, s, aq, rfx, S, tr);
             u64 rsum_fx = FX_ONE - S.reserve_total;
             double rsum_w = (double)rsum_fx * FX_INV * (1.0 - alpha);
@@ -650,7 +654,7 @@ void b_fora_topk(const Graph& g, i32 s, double alpha, double eps_in, i64 k, u64 
             double rmax_local = epsilon * std::sqrt(delta_local / 3.0 / (double)g.m / L);
             double omega_local = (epsilon + 2.0) * L / epsilon / epsilon / delta_local;
             rmax_local *= std::sqrt((double)g.m * rmax_local) * 3.0;
-            u64 rfx = rmax_to_fx(rmax_local);
+            u64 rfx = rmax_to_fx(rmax_local, aq);
             b_push_round(g, s, aq, rfx, S, nullptr);
             st.rmax_fx_final = rfx;
             u64 rsum_fx = FX_ONE - S.reserve_total;
@@ -736,11 +740,12 @@ inline u64 thr_ge_fx(double threshold) {  // smallest FX value whose real value 
     if (x >= 18446744073709551615.0) return ~0ull;
     return (u64)x;
 }
-inline u64 rmax_abs_fx(double rmax) {  // largest FX value whose real value is <= rmax
-    if (!(rmax > 0)) return 0;
+inline u64 rmax_abs_fx(double rmax, u64 alpha_q64) {  // largest FX value whose real value is <= rmax (floored, see rmax_floor_fx)
+    const u64 lo = rmax_floor_fx(alpha_q64);
+    if (!(rmax > 0)) return lo;
     double x = std::floor(rmax * FX_SCALE);
     if (x >= 18446744073709551615.0) return ~0ull;
-    return (u64)x;
+    return std::max(lo, (u64)x);
 }
 
 }  // namespace
@@ -912,7 +917,7 @@ void orc_b_forward_push(i64 n, i64 m, const i64* rp, const i32* ci, i32 s, doubl
     BState S(n);
     Trace tr;
     if (g.deg(s) == 0) { S.reserve[s] = FX_ONE; }
-    else { S.r[s] = FX_ONE; b_push_round(g, s, alpha_q64_of(alpha), rmax_to_fx(rmax), S, &tr); }
+    else { S.r[s] = FX_ONE; b_push_round(g, s, alpha_q64_of(alpha), rmax_to_fx(rmax, alpha_q64_of(alpha)), S, &tr); }
     std::copy(S.reserve.begin(), S.reserve.end(), reserve);
     if (residue) std::copy(S.r.begin(), S.r.end(), residue);
     if (stats) { stats[0] = S.pushes; stats[1] = S.edges; stats[2] = S.iters; }
@@ -963,7 +968,7 @@ void orc_b_backward_search(i64 n, i64 m, const i64* rp, const i32* ci, i32 t, do
     for (i64 v = 0; v < n; v++) if (g.deg(v) > 0) invdeg[v] = ~0ull / (u64)g.deg(v);
     std::vector<u64> r(n);
     PushStats st = {0, 0}; i64 it = 0;
-    b_backward(g, invdeg, t, alpha_q64_of(alpha), rmax_abs_fx(rmax), reserve, r.data(), &st, &it);
+    b_backward(g, invdeg, t, alpha_q64_of(alpha), rmax_abs_fx(rmax, alpha_q64_of(alpha)), reserve, r.data(), &st, &it);
     if (residue) std::copy(r.begin(), r.end(), residue);
     if (stats) { stats[0] = st.pushes; stats[1] = st.edges; stats[2] = it; }
 }
@@ -975,7 +980,7 @@ i64 orc_b_base_all_pairs(i64 n, i64 m, const i64* rp, const i32* ci, double alph
     g.build_csc();
     std::vector<u64> invdeg(n, 0);
     for (i64 v = 0; v < n; v++) if (g.deg(v) > 0) invdeg[v] = ~0ull / (u64)g.deg(v);
-    u64 aq = alpha_q64_of(alpha), rfx = rmax_abs_fx(threshold), tfx = thr_ge_fx(threshold);
+    u64 aq = alpha_q64_of(alpha), rfx = rmax_abs_fx(threshold, aq), tfx = thr_ge_fx(threshold);
     std::vector<std::vector<std::pair<i32, u64>>> inv(n);
     std::vector<u64> reserve(n), r(n);
     PushStats st = {0, 0}; i64 it = 0;

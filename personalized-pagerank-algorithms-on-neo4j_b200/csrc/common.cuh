@@ -202,9 +202,3 @@ int32_t ctx_fail_cuda(ppr_ctx* ctx, cudaError_t e, const char* expr, const char*
 static inline u64 h_alpha_q64(double alpha) { return (u64)__builtin_ldexp(alpha, 64); }
 static inline u64 h_stop_threshold(double alpha) { return (u64)__builtin_ceil(__builtin_ldexp(alpha, 53)); }
 static inline u64 h_walk_key(u64 seed, u64 tag) { return seed + tag * 0x9E3779B97F4A7C15ull; }
-static inline u64 h_rmax_to_fx(double rmax) {
-    double x = rmax * FX_SCALE;
-    if (!(x >= 1.0)) return 1;
-    if (x >= 18446744073709551615.0) return ~0ull;
-    return (u64)x;
-}

@@ -941,6 +941,7 @@ static int32_t bwd_run_batch(ppr_graph* g, BwdWorkspace& b, i32 t0, i32 T, doubl
     double fl = threshold > 0 ? std::floor(threshold * FX_SCALE) : 0.0;
     double cl = threshold > 0 ? std::ceil(threshold * FX_SCALE) : 0.0;
     A.rmax_fx = fl >= 18446744073709551615.0 ? ~0ull : (u64)fl;
+    A.rmax_fx = std::max<u64>(A.rmax_fx, ~0ull / A.alpha_q64 + 2);   // floor: a push must move >= 1 unit into the reserve
     A.thr_fx = cl >= 18446744073709551615.0 ? ~0ull : (u64)cl;
     A.out_v = b.out_v; A.out_t = b.out_t; A.out_val = b.out_val; A.out_cap = b.out_cap;
     CUDA_TRY(cudaMemsetAsync(b.r, 0, (size_t)T * n * 8, ctx->stream));

@@ -100,11 +100,14 @@ __device__ __forceinline__ void warp_append4_u32(u32* list, u32* counter, const 
 
 __device__ __forceinline__ u64 globaltimer_ns() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-__device__ __forceinline__ u64 rmax_to_fx_dev(double rmax) {
+// floor: below 1/alpha units mulhi64(x, alpha_q64) is 0 and a push would move nothing into the reserve
+__device__ __forceinline__ u64 rmax_to_fx_dev(double rmax, u64 alpha_q64) {
+    const u64 lo = ~0ull / alpha_q64 + 2;
     double x = __dmul_rn(rmax, FX_SCALE);
-    if (!(x >= 1.0)) return 1ull;
+    if (!(x >= 1.0)) return lo;
     if (x >= 18446744073709551615.0) return ~0ull;
-    return (u64)x;  // truncation
+    u64 v = (u64)x;  // truncation
+    return v > lo ? v : lo;
 }
 
 // --------------------------------------------------------------------------------- frontier seeding by dense scan
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
         if (gtid == 0) {
             ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
             ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
-            ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
+            ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0, A.alpha_q64);
             ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0; ctl->dbg_count = 0;
         }
         grid.sync();
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
         ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0;
         if (!A.init) {  // top-k round: host supplied the round's rmax; counters of both parities must be clean
             ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
-            ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
+            ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0, A.alpha_q64);
         }
     }
     const bool dangling_src = A.out_deg[A.src] == 0;  // J/Forward_Push.java:72-76, J/Fora_Topk.java:128-132
@@ -585,7 +588,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
             bool cont = A.mode == PMODE_FORA && cost < __dmul_rn(__dmul_rn(A.walk_cost, rsum_w), A.omega) &&
                         rounds < (u64)A.max_rounds;
             ctl->rmax = rmax;
-            if (cont) ctl->rmax_fx = rmax_to_fx_dev(rmax);
+            if (cont) ctl->rmax_fx = rmax_to_fx_dev(rmax, A.alpha_q64);
             ctl->cont = cont ? 1u : 0u;
         }
         grid.sync();
@@ -610,7 +613,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_init(PushArgs A) {
     if (gtid == 0) {
         ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
         ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
-        ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0);
+        ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0, A.alpha_q64);
         ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0;
         ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0;
     }
