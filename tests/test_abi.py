@@ -69,3 +69,18 @@ def test_product_does_not_import_oracle(pkg):
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(root, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "ppr_oracle" not in txt, fn
+
+
+def test_cpp_host_driver_builds_and_fails_loudly(pkg, tmp_path):
+    """host/ppr_main.cpp: the reference's `PPR` driver (same options) compiled against the C ABI."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pkg.__file__), "PPR")
+    assert os.path.exists(exe)
+    out = subprocess.run([exe, "-help"], capture_output=True, text=True)
+    assert out.returncode == 0
+    for opt in ("-alpha", "-eps", "-query", "-k", "-node", "-label", "-rel", "-db", "-help"):
+        assert opt in out.stdout                                   # J/PPR.java:157-166
+    assert subprocess.run([exe, "-bogus"], capture_output=True).returncode == 2
+    if not os.path.exists("/dev/nvidia0"):
+        r = subprocess.run([exe, "-query", "1", "-db", os.path.join(ROOT, "tests", "golden", "got"), "-out", str(tmp_path)], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout

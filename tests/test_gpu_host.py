@@ -114,3 +114,24 @@ def test_full_size_properties(pkg, ctx):
         assert (ppr[np.setdiff1d(np.arange(len(ppr)), ids)] < vals[-1]).all()
     finally:
         g.close()
+
+
+def test_cpp_host_driver_on_got(pkg, tmp_path):
+    """The compiled C++ `PPR` driver runs the reference's harness protocol on GOT and writes its result-file format."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pkg.__file__), "PPR")
+    got = os.path.join(os.path.dirname(__file__), "golden", "got")
+    r = subprocess.run([exe, "-alpha", "0.15", "-eps", "0.5", "-query", "5", "-k", "10", "-db", got, "-out", str(tmp_path)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    text = open(tmp_path / "got_AlgoPerfResults.txt").read()
+    assert "Test 1. Whole-Graph test" in text and "1.1 FORA_WHOLE_GRAPH" in text and "2.1 FORA_TOPK" in text and "1.5 BASE_WHOLE_GRAPH" in text
+    sec = text.split("1.1 FORA_WHOLE_GRAPH\n")[1].split("\n\n")[0].splitlines()
+    assert [l.split(",")[0] for l in sec] == ["10.0", "5.0", "0.5", "0.1", "0.05"]        # J/Gen_Util.java:463
+    errs = [float(l.split(",")[2].replace("E", "e")) for l in sec]
+    assert errs[2] < 0.05 and errs[4] < errs[0]                      # eps = 0.5 row; error shrinks with eps
+    sec = text.split("2.1 FORA_TOPK\n")[1].split("\n\n")[0].splitlines()
+    prec = [float(l.split(",")[3].replace("E", "e")) for l in sec]
+    assert min(prec[2:]) > 0.8
+    sec = text.split("1.2 FWDPUSH\n")[1].split("\n\n")[0].splitlines()
+    assert float(sec[-1].split(",")[2].replace("E", "e")) < 1e-6       # rmax 1e-8
