@@ -75,7 +75,7 @@ __device__ __forceinline__ bool relax_in_edge(const BwdArgs& A, u64* rt, u32 u, 
     return old <= A.rmax_fx && old + inc > A.rmax_fx;
 }
 
-__global__ void __launch_bounds__(PUSH_THREADS, 4) k_bwd_batch(BwdArgs A) {
+__global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_bwd_batch(BwdArgs A) {
     cg::grid_group grid = cg::this_grid();
     __shared__ u64 sm_excl[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];

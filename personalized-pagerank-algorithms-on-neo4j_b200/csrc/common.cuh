@@ -39,7 +39,8 @@ typedef unsigned long long ull;
 #define HOT_SLOTS 4096      // hub vertices whose incoming adds are staged in shared memory (32 KB per CTA)
 #define HOT_BIT 0x80000000u
 #define HOT_MASK 0x00000fffu
-#define PUSH_THREADS 256
+#define PUSH_THREADS 512
+#define PUSH_CTAS_PER_SM (1024 / PUSH_THREADS)   // 32 resident warps per SM at 64 registers per thread
 #define WALK_THREADS 256
 
 #define CUDA_TRY(expr)                                                       \

@@ -496,7 +496,7 @@ __device__ void walk_prep(const PushArgs& A, cg::grid_group& grid, u64* sm) {
 }
 
 // --------------------------------------------------------------------------------- the persistent query kernel
-__global__ void __launch_bounds__(PUSH_THREADS, 4) k_push_query(PushArgs A) {
+__global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(PushArgs A) {
     cg::grid_group grid = cg::this_grid();
     __shared__ u64 sm_excl[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
