@@ -142,7 +142,7 @@ def run_reference(args, rank, world):
     O.lib()
     rp, ci, _ = make_graph(pkg, args.scale, args.edge_factor)
     og = O.OGraph(rp, ci)
-    threads = args.ref_threads or max(1, min(os.cpu_count() or 1, 16))
+    threads = args.ref_threads or max(1, min(os.cpu_count() or 1, 64))
     walk_cost = CPU_WALK_COST if args.walk_cost is None else args.walk_cost
     srcs = pick_sources(rp, (args.steps + args.warmup) * threads)
 
