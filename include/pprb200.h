@@ -104,6 +104,10 @@ int32_t ppr_set_balance(ppr_ctx* ctx, double walk_cost, int32_t max_rounds);
  * the 4096 hub slots whose incoming adds are staged in shared memory; applies to graphs created afterwards. */
 int32_t ppr_set_tuning(ppr_ctx* ctx, int64_t scan_threshold_edges, int32_t hot_min_indeg);
 
+/* ppr_fora_batch: 2 keeps two queries in flight on two streams (each cooperative kernel takes one CTA per SM), 1 runs
+ * them back to back, 0 (default) picks 2 while the graph fits in the L2.  Results are identical. */
+int32_t ppr_set_batch_streams(ppr_ctx* ctx, int32_t streams);
+
 /* All-pair backward search: targets advanced together per kernel launch (0 = automatic: sized so that the
  * batch's residue matrix stays near the L2 capacity). */
 int32_t ppr_set_bwd_batch(ppr_ctx* ctx, int32_t targets_per_batch);

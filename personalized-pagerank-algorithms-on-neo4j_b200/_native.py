@@ -21,7 +21,7 @@ FX_INV = 1.0 / float(1 << 62)
 
 # every symbol include/pprb200.h declares (checked by tests/test_abi.py against the header text)
 EXPORTS = [
-    "ppr_init", "ppr_shutdown", "ppr_set_tuning", "ppr_set_bwd_batch", "ppr_timer_record", "ppr_timer_elapsed_ms", "ppr_flush_l2", "ppr_device_sync", "ppr_last_error", "ppr_device_info", "ppr_set_balance", "ppr_host_alloc",
+    "ppr_init", "ppr_shutdown", "ppr_set_tuning", "ppr_set_bwd_batch", "ppr_set_batch_streams", "ppr_timer_record", "ppr_timer_elapsed_ms", "ppr_flush_l2", "ppr_device_sync", "ppr_last_error", "ppr_device_info", "ppr_set_balance", "ppr_host_alloc",
     "ppr_host_free", "ppr_graph_create", "ppr_graph_destroy", "ppr_graph_node_count", "ppr_graph_rel_count",
     "ppr_graph_export_csc", "ppr_forward_push", "ppr_monte_carlo", "ppr_fora", "ppr_fora_topk", "ppr_topk",
     "ppr_power_iteration", "ppr_fora_batch", "ppr_backward_search", "ppr_backward_all_pairs", "ppr_pairs_count",
@@ -90,6 +90,7 @@ def load():
         "ppr_set_balance": (i32, [vp, f64, i32]),
         "ppr_set_tuning": (i32, [vp, i64, i32]),
         "ppr_set_bwd_batch": (i32, [vp, i32]),
+        "ppr_set_batch_streams": (i32, [vp, i32]),
         "ppr_timer_record": (i32, [vp, i32]),
         "ppr_timer_elapsed_ms": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
         "ppr_flush_l2": (i32, [vp]),
@@ -170,6 +171,9 @@ class Context:
 
     def set_tuning(self, scan_threshold_edges=-1, hot_min_indeg=-1):
         self.check(self.L.ppr_set_tuning(self.h, scan_threshold_edges, hot_min_indeg))
+
+    def set_batch_streams(self, streams=0):
+        self.check(self.L.ppr_set_batch_streams(self.h, streams))
 
     def set_bwd_batch(self, targets_per_batch=0):
         self.check(self.L.ppr_set_bwd_batch(self.h, targets_per_batch))

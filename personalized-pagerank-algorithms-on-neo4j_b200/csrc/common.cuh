@@ -135,11 +135,13 @@ struct ppr_ctx {
     std::string name;
     std::string err;
     cudaStream_t stream;   // compute
+    cudaStream_t stream2;  // second compute stream of the batch pipeline
     cudaStream_t copy;     // result download (batch pipeline)
     cudaEvent_t ev[8];
     double walk_cost;
     int max_rounds;
     i64 scan_threshold;    // < 0: default (n)
+    i32 batch_streams;     // ppr_fora_batch: 1 = queries back to back, 2 = two queries in flight
     i32 bwd_batch;         // all-pair backward search: targets per batch (0 = automatic)
     i32 hot_min_indeg;     // a vertex needs at least this in-degree to get a hub slot (graphs created afterwards)
 };
