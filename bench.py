@@ -247,7 +247,22 @@ def measure_ours(pkg, ctx, g, rp, args, srcs, steps, warmup, q, rank, world, dis
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
     chk = float(out[q - 1].sum())
-    return {"ms": ms, "ms_e2e": ms_e2e, "acc": acc, "clocks": clocks, "check_sum": chk}
+
+    # device-resident, pipelined (same batch call, results left on the device): what the overlap of two queries buys
+    def pipe_step(i):
+        ctx.flush_l2()
+        g.fora_batch(srcs[i * q:(i + 1) * q], ALPHA, args.eps, 1000 + i * q, want_stats=False, resident=True)
+
+    for i in range(warmup):
+        pipe_step(i)
+    barrier()
+    ctx.timer_record(0)
+    for i in range(warmup, warmup + steps):
+        pipe_step(i)
+    ctx.timer_record(1)
+    ms_pipe = max_over_ranks(ctx.timer_elapsed_ms(0, 1))
+    barrier()
+    return {"ms": ms, "ms_e2e": ms_e2e, "ms_pipe": ms_pipe, "acc": acc, "clocks": clocks, "check_sum": chk}
 
 
 def main():
@@ -296,7 +311,11 @@ def main():
         "vs_baseline": None, "dtype": "u64 (2^-62 fixed point; f64 only at the boundary)", "data": "synthetic",
         "config": dict(workload_config(args, q), walk_cost=walk_cost if walk_cost is not None else "auto (6 in L2, 24 beyond)", parallelism="%d independent query streams (one per GPU)" % world),
         "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": 4 * q, "d2h_bytes_per_step": 8 * g.n * q,
-                "api": "ppr_fora_batch (Fora_Whole_Graph.computeWholeGraphPPR per source), dense f64 result to pinned host memory"},
+                "api": "ppr_fora_batch (Fora_Whole_Graph.computeWholeGraphPPR per source), dense f64 result to pinned host memory; "
+                       "the batch call keeps two queries in flight while the graph fits in L2, which is why e2e can exceed `value` "
+                       "(measured one query at a time so that per-kernel CUDA-event times are unambiguous)"},
+        "resident_pipelined": {"value": nq_rank * world / (m["ms_pipe"] / 1e3), "unit": "queries/s",
+                               "api": "ppr_fora_batch with results left on the device"},
         "gpu_launches": int(acc["launches"]),
         "clocks": m["clocks"],
         "roofline": {"bound": "hbm", "kernel": "k_push_query", "achieved": push_gbs, "peak": peak, "unit": "GB/s",

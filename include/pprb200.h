@@ -174,7 +174,8 @@ int32_t ppr_topk(ppr_ctx* ctx, const double* vec, int64_t n, int32_t k, int32_t*
 int32_t ppr_power_iteration(ppr_graph* g, int32_t src, double alpha, int32_t iters, double* out);
 
 /* Throughput path: nq FORA queries back to back, results written to ppr_out[q*n .. (q+1)*n) while
- * the next query computes.  Query q uses seed + q.  stats_out (nullable) is an array of nq entries. */
+ * the next query computes.  Query q uses seed + q.  stats_out (nullable) is an array of nq entries.
+ * ppr_out == NULL leaves the results on the device (throughput measurements; ppr_last_raw reads the last one). */
 int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq, double alpha, double eps, uint64_t seed,
                        int32_t flags, const ppr_conf* conf, double* ppr_out, ppr_stats* stats_out);
 

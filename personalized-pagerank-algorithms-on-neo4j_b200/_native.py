@@ -284,10 +284,11 @@ class Graph:
         self.ctx.check(self.L.ppr_monte_carlo_shard(self.h, src, alpha, eps, seed, _conf(conf), shard, nshards, C.byref(st)))
         return st.as_dict()
 
-    def fora_batch(self, srcs, alpha, eps, seed, flags=0, out=None, want_stats=True, conf=None):
+    def fora_batch(self, srcs, alpha, eps, seed, flags=0, out=None, want_stats=True, conf=None, resident=False):
         srcs = np.ascontiguousarray(srcs, np.int32)
         nq = srcs.shape[0]
-        out = np.zeros((nq, self.n)) if out is None else out
+        if not resident:
+            out = np.zeros((nq, self.n)) if out is None else out
         st = (Stats * max(nq, 1))()
         self.ctx.check(self.L.ppr_fora_batch(self.h, _ptr(srcs), nq, alpha, eps, seed, flags, _conf(conf), _ptr(out), st if want_stats else None))
         return out, [st[i].as_dict() for i in range(nq)] if want_stats else None

@@ -603,7 +603,8 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
                                   int32_t flags, const ppr_conf* conf, double* ppr_out, ppr_stats* stats_out) {
     if (!g) return PPR_E_INVALID;
     ppr_ctx* ctx = g->ctx;
-    if (!srcs || !ppr_out || nq < 0) return ctx_fail(ctx, PPR_E_INVALID, "ppr_fora_batch: NULL argument");
+    if (!srcs || nq < 0) return ctx_fail(ctx, PPR_E_INVALID, "ppr_fora_batch: NULL argument");
+    const bool resident = ppr_out == nullptr;  // results stay on the device (only the last query of each workspace survives)
     for (int q = 0; q < nq; q++) { int32_t rc = check_fora(g, srcs[q], alpha, eps, 0, 1, "ppr_fora_batch"); if (rc) return rc; }
     cudaSetDevice(ctx->device);
     GraphExtra* x = extra_of(g);
@@ -650,13 +651,13 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
         if (used[q & 1]) cudaStreamWaitEvent(st, copied[q & 1], 0);  // out_f64 of this workspace is free again
         rc = fora_launch(g, w, srcs[q], alpha, eps, seed + (u64)q, flags, conf, 0, 1, e[0], e[1], e[2], &omegas[q], st, dual ? ctx->sm_count : 0);
         if (rc) break;
-        k_export_f64<<<ctx->sm_count * 8, 256, 0, st>>>(w.reserve, w.out_f64, n, 0.0);
+        if (!resident) k_export_f64<<<ctx->sm_count * 8, 256, 0, st>>>(w.reserve, w.out_f64, n, 0.0);
         cudaMemcpyAsync(&snaps[q], w.ctl, sizeof(PushCtl), cudaMemcpyDeviceToHost, st);
         cudaEventRecord(e[3], st);
         used[q & 1] = true;
-        if (q > 0) { cudaError_t ce = issue_copy(q - 1); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, "batch download", __FILE__, __LINE__); }
+        if (q > 0 && !resident) { cudaError_t ce = issue_copy(q - 1); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, "batch download", __FILE__, __LINE__); }
     }
-    if (rc == PPR_OK && nq > 0) { cudaError_t ce = issue_copy(nq - 1); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, "batch download", __FILE__, __LINE__); }
+    if (rc == PPR_OK && nq > 0 && !resident) { cudaError_t ce = issue_copy(nq - 1); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, "batch download", __FILE__, __LINE__); }
     cudaError_t s1 = cudaStreamSynchronize(ctx->stream), s2 = cudaStreamSynchronize(ctx->copy);
     { cudaError_t s3 = cudaStreamSynchronize(ctx->stream2); if (s1 == cudaSuccess) s1 = s3; }
     if (rc == PPR_OK && (s1 != cudaSuccess || s2 != cudaSuccess)) rc = ctx_fail_cuda(ctx, s1 != cudaSuccess ? s1 : s2, "batch sync", __FILE__, __LINE__);
@@ -668,7 +669,7 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
             cudaEventElapsedTime(&st->ms_push, e[0], e[1]);
             cudaEventElapsedTime(&st->ms_walk, e[1], e[2]);
             cudaEventElapsedTime(&st->ms_total, e[0], e[3]);
-            st->launches = 3;
+            st->launches = resident ? 2 : 3;
         }
         if (nq > 0) { g->last_ws = (nq - 1) & 1; g->last_kind = 1; x->last_divisor = 0.0; }
     }
