@@ -256,6 +256,7 @@ template <bool LIST>
 __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u64* sm_excl /*[warps][32]*/,
                              u64* sm_beg, u64* sm_q, u64* sm_hot /*[HOT_SLOTS], all zero on entry and exit; unused when LIST*/) {
     PushCtl* ctl = A.ctl;
+    const u64 pol_stream = l2_policy_evict_first();  // the edge array is streamed once per iteration: do not let it evict r[] / degrees
     const u64 staged = *(volatile u64*)&ctl->stage[par];
     const i64 ns = (i64)(u32)staged;
     const u32 nch = (u32)(staged >> 32);
@@ -299,7 +300,7 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
                     int o = 0;
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) { int p = o + s; if ((u32)w_excl[p] <= e) o = p; }
-                    u[k] = __ldg(&A.push_idx[w_beg[o] + e]);
+                    u[k] = ld_hint_u32(&A.push_idx[w_beg[o] + e], pol_stream);
                     qq[k] = w_q[o];
                 }
             }
@@ -323,7 +324,7 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
             u32 u[4];
             bool cr[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) { u32 e = eb + 32 * k + lane; u[k] = e < len ? __ldg(&row[e]) : 0xffffffffu; }
+            for (int k = 0; k < 4; k++) { u32 e = eb + 32 * k + lane; u[k] = e < len ? ld_hint_u32(&row[e], pol_stream) : 0xffffffffu; }
 #pragma unroll
             for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], q, sm_hot) : false;
             if (LIST) warp_append4_u32(next, next_cnt, cr, u);
