@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(WALK_THREADS, 4) k_walk(WalkArgs A) {
 
     for (;;) {
         u32 needy = __ballot_sync(0xffffffffu, !active);
-        if (needy && wnext < wh) {
+        // refill in batches: the bookkeeping below costs about as many instructions as a walk step, so wait until
+        // WALK_REFILL_MIN lanes are idle (or the warp has nothing left to do)
+        if (wnext < wh && (__popc(needy) >= WALK_REFILL_MIN || needy == 0xffffffffu)) {
             mywin[lane] = A.ws_begin[scur + lane];
             if (lane < 2) mywin[32 + lane] = A.ws_begin[scur + 32 + lane];
             __syncwarp();
