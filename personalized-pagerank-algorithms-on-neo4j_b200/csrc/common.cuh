@@ -36,8 +36,6 @@ typedef unsigned long long ull;
 
 #define DBG_ITERS 4096
 #define DBG_FIELDS 6   // t_start, t_after_A, t_after_B (globaltimer ns), frontier size, cumulative edges, mode
-#define STAGE_LISTS 8       // short-row staging segments of the forward push (power of two)
-#define STAGE_STRIDE 64     // u32 stride between their counters
 #define HOT_SLOTS 4096      // hub vertices whose incoming adds are staged in shared memory (32 KB per CTA)
 #define HOT_BIT 0x80000000u
 #define HOT_MASK 0x00000fffu
@@ -109,9 +107,7 @@ __device__ __forceinline__ u32 lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemas
 struct PushCtl {
     // frontier bookkeeping (index = iteration parity)
     u32 cnt[2];        // frontier sizes
-    u64 stage[2];      // reverse push: staged work of the iteration, (chunk descriptors << 32) | short rows
-    u32 stage_c[2];    // forward push: chunk descriptors staged by the iteration
-    u32 stage_s[2][STAGE_LISTS * STAGE_STRIDE];  // forward push: short rows staged per segment (counters 256 B apart)
+    u64 stage[2];      // forward push: staged work of the iteration, (chunk descriptors << 32) | short rows
     u32 ns[2];         // reverse push: staged short rows
     u32 nl[2];         // reverse push: staged long rows
     u32 nchunks[2];    // reverse push: chunk descriptors

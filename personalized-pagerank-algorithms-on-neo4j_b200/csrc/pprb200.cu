@@ -211,8 +211,7 @@ static int32_t ws_alloc(ppr_ctx* ctx, Workspace& w, i64 n, i64 chunk_cap) {
     size_t N = (size_t)n;
     CUDA_TRY(dalloc(&w.r, N)); CUDA_TRY(dalloc(&w.reserve, N)); CUDA_TRY(dalloc(&w.est, N));
     CUDA_TRY(dalloc(&w.front[0], N)); CUDA_TRY(dalloc(&w.front[1], N));
-    const size_t SN = (size_t)STAGE_LISTS * ((size_t)n / STAGE_LISTS + 256);   // STAGE_LISTS segments of n/8 + 256 slots
-    CUDA_TRY(dalloc(&w.s_pack, SN)); CUDA_TRY(dalloc(&w.s_q, SN)); CUDA_TRY(dalloc(&w.l_pack, std::max(N, (size_t)chunk_cap))); CUDA_TRY(dalloc(&w.l_q, std::max(N, (size_t)chunk_cap)));
+    CUDA_TRY(dalloc(&w.s_pack, N)); CUDA_TRY(dalloc(&w.s_q, N)); CUDA_TRY(dalloc(&w.l_pack, std::max(N, (size_t)chunk_cap))); CUDA_TRY(dalloc(&w.l_q, std::max(N, (size_t)chunk_cap)));
     CUDA_TRY(dalloc(&w.chunks, (size_t)chunk_cap));
     CUDA_TRY(dalloc(&w.ws_v, N)); CUDA_TRY(dalloc(&w.ws_begin, N + 64)); CUDA_TRY(dalloc(&w.ws_inc, N)); CUDA_TRY(dalloc(&w.ws_rem, N));
     int occ = 0;
@@ -425,7 +424,6 @@ static void fill_push_args(PushArgs& A, ppr_graph* g, Workspace& w) {
     A.ws_v = w.ws_v; A.ws_begin = w.ws_begin; A.ws_inc = w.ws_inc; A.ws_rem = w.ws_rem;
     A.blk_a = w.blk_a; A.blk_b = w.blk_b; A.ctl = w.ctl; A.dbg = w.dbg;
     A.prep_adds_push_part = 1;
-    A.stage_seg = g->d.n / STAGE_LISTS + 256;
     A.scan_threshold = g->ctx->scan_threshold < 0 ? std::max<i64>(1, g->d.n / 4) : g->ctx->scan_threshold;
 }
 

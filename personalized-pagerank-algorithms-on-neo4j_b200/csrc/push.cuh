@@ -62,7 +62,6 @@ struct PushArgs {
     int init;           // 1: reset state and seed r[src] = 1
     int zero_reserve_after_push;  // shard != 0 of a multi-GPU FORA: drop the push reserve before the walk prep
     int prep_adds_push_part;      // shard == 0
-    i64 stage_seg;                // capacity of one short-row staging segment (s_pack / s_q hold STAGE_LISTS of them)
     i64 scan_threshold;           // frontier edges >= this: next frontier is found by a dense sweep (SCAN mode)
 };
 
@@ -139,10 +138,9 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     PushCtl* ctl = A.ctl;
     const i64 cnt = SCAN ? A.n : (i64)*(volatile u32*)&ctl->cnt[par];
     if (gtid == 0) {  // recycle the other parity's counters (last read before the preceding barrier)
-        ctl->cnt[par ^ 1] = 0; ctl->stage_c[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
+        ctl->cnt[par ^ 1] = 0; ctl->stage[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
         ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0;
     }
-    if (gtid < STAGE_LISTS) ctl->stage_s[par ^ 1][gtid * STAGE_STRIDE] = 0;
     u64 edges_local = 0, resv_local = 0, dang_local = 0, pushed_local = 0;
     const u32* F = A.front[par];
     const u32 lane = lane_id();
@@ -192,18 +190,11 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
             chunk_total = __shfl_sync(0xffffffffu, chunk_incl, 31);
         }
         if (small_total | chunk_total) {
-            // Short rows go to one of STAGE_LISTS segments picked by the tile index (each with its own counter on its
-            // own 256-byte line): one shared counter took n/128 same-address atomics per sweep, ~0.7 ns each.
-            const u32 lid = (u32)(tile >> 7) & (STAGE_LISTS - 1);
-            u32 b_s = 0, b_c = 0;
-            if (lane == 0) {
-                if (small_total) b_s = atomicAdd(&ctl->stage_s[par][lid * STAGE_STRIDE], small_total);
-                if (chunk_total) b_c = atomicAdd(&ctl->stage_c[par], chunk_total);
-            }
-            b_s = __shfl_sync(0xffffffffu, b_s, 0);
-            b_c = __shfl_sync(0xffffffffu, b_c, 0);
-            u32 off = lid * (u32)A.stage_seg + b_s;
-            u32 cb = b_c + chunk_incl - my_nch;
+            u64 base = 0;
+            if (lane == 0) base = atomicAdd((ull*)&ctl->stage[par], ((ull)chunk_total << 32) | (ull)small_total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            u32 off = (u32)base;
+            u32 cb = (u32)(base >> 32) + chunk_incl - my_nch;
 #pragma unroll
             for (int k = 0; k < PA_ITEMS; k++) {
                 if (cls[k] == 1) { u32 slot = off + __popc(ms[k] & lanemask_lt()); A.s_pack[slot] = pk[k]; A.s_q[slot] = q[k]; }
@@ -263,18 +254,12 @@ __device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32& 
 
 template <bool LIST>
 __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u64* sm_excl /*[warps][32]*/,
-                             u64* sm_beg, u64* sm_q, u64* sm_hot /*[HOT_SLOTS], all zero on entry and exit; unused when LIST*/,
-                             u32* sm_units /*[2 * STAGE_LISTS + 1]*/) {
+                             u64* sm_beg, u64* sm_q, u64* sm_hot /*[HOT_SLOTS], all zero on entry and exit; unused when LIST*/) {
     PushCtl* ctl = A.ctl;
     const u64 pol_stream = l2_policy_evict_first();  // the edge array is streamed once per iteration: do not let it evict r[] / degrees
-    const u32 nch = *(volatile u32*)&ctl->stage_c[par];
-    // per-segment counts and unit offsets live in shared memory (sm_units: [0..7] counts, [8..16] first unit)
-    __syncthreads();
-    if (threadIdx.x < STAGE_LISTS) sm_units[threadIdx.x] = *(volatile u32*)&ctl->stage_s[par][threadIdx.x * STAGE_STRIDE];
-    __syncthreads();
-    i64 ns = 0;
-#pragma unroll
-    for (int l = 0; l < STAGE_LISTS; l++) ns += sm_units[l];
+    const u64 staged = *(volatile u64*)&ctl->stage[par];
+    const i64 ns = (i64)(u32)staged;
+    const u32 nch = (u32)(staged >> 32);
     const i64 gwarp = gtid >> 5, nwarps = gsize >> 5;
     const u32 lane = lane_id();
     const int wib = threadIdx.x >> 5;
@@ -286,24 +271,12 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
 
     // (1) short rows: up to 32 vertices per warp, lanes sweep the concatenated edge list.  When the
     // frontier is small the batch shrinks so that every warp of the grid gets some rows (a warp works
-    // through its batch serially, one dependent atomic round trip per 32 edges).  Units are numbered
-    // through the STAGE_LISTS segments one after the other.
+    // through its batch serially, one dependent atomic round trip per 32 edges).
     const i64 bw = min((i64)32, max((i64)1, ((i64)ns + nwarps - 1) / nwarps));
-    if (threadIdx.x == 0) {
-        u32 acc = 0;
-        for (int l = 0; l < STAGE_LISTS; l++) { sm_units[STAGE_LISTS + l] = acc; acc += (u32)((sm_units[l] + bw - 1) / bw); }
-        sm_units[2 * STAGE_LISTS] = acc;
-    }
-    __syncthreads();
-    const u32 total_units = sm_units[2 * STAGE_LISTS];
-    for (i64 unit = gwarp; unit < total_units; unit += nwarps) {
-        int l = 0;
-#pragma unroll
-        for (int k = 1; k < STAGE_LISTS; k++) l += (u32)unit >= sm_units[STAGE_LISTS + k];
-        const u32 lbase = sm_units[STAGE_LISTS + l], lcnt = sm_units[l];
-        i64 local = ((i64)unit - lbase) * bw + lane;
+    for (i64 wbase = gwarp * bw; wbase < ns; wbase += nwarps * bw) {
+        i64 item = wbase + lane;
         u64 pk = 0, q = 0;
-        if (lane < bw && local < lcnt) { i64 item = (i64)l * A.stage_seg + local; pk = A.s_pack[item]; q = A.s_q[item]; }
+        if (lane < bw && item < ns) { pk = A.s_pack[item]; q = A.s_q[item]; }
         u32 d = vtx_deg(pk);
         u32 incl = d;
 #pragma unroll
@@ -531,7 +504,6 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(P
     __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
     __shared__ __align__(8) u32 sm_cnt[16];
     __shared__ u64 sm_hot[HOT_SLOTS];
-    __shared__ u32 sm_units[2 * STAGE_LISTS + 2];
     PushCtl* ctl = A.ctl;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 gsize = (i64)gridDim.x * blockDim.x;
@@ -541,8 +513,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(P
     if (A.init) {
         for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
         if (gtid == 0) {
-            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage_c[0] = ctl->stage_c[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
-            for (int l = 0; l < STAGE_LISTS; l++) ctl->stage_s[0][l * STAGE_STRIDE] = ctl->stage_s[1][l * STAGE_STRIDE] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
+            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
             ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0, A.alpha_q64);
             ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0; ctl->dbg_count = 0;
@@ -552,8 +523,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(P
     if (gtid == 0) {
         ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0;
         if (!A.init) {  // top-k round: host supplied the round's rmax; counters of both parities must be clean
-            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage_c[0] = ctl->stage_c[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
-            for (int l = 0; l < STAGE_LISTS; l++) ctl->stage_s[0][l * STAGE_STRIDE] = ctl->stage_s[1][l * STAGE_STRIDE] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
+            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0, A.alpha_q64);
         }
     }
@@ -593,8 +563,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(P
             if (fcnt == 0) break;
             const bool next_scan = (i64)fedges >= A.scan_threshold;
             if (gtid == 0) t1 = globaltimer_ns();
-            if (next_scan) push_phase_b<false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot, sm_units);
-            else push_phase_b<true>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot, sm_units);
+            if (next_scan) push_phase_b<false>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
+            else push_phase_b<true>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
             grid.sync();
             if (gtid == 0) {
                 u32 k = ctl->dbg_count;
@@ -642,8 +612,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_init(PushArgs A) {
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
     for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
     if (gtid == 0) {
-        ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage_c[0] = ctl->stage_c[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
-            for (int l = 0; l < STAGE_LISTS; l++) ctl->stage_s[0][l * STAGE_STRIDE] = ctl->stage_s[1][l * STAGE_STRIDE] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
+        ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
         ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
         ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0, A.alpha_q64);
         ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0;
@@ -669,7 +638,6 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_b(PushArgs A, int par) {
     __shared__ u64 sm_excl[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
-    __shared__ u32 sm_units[2 * STAGE_LISTS + 2];
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
-    push_phase_b<true>(A, par, A.ctl->rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, nullptr, sm_units);
+    push_phase_b<true>(A, par, A.ctl->rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, nullptr);
 }
