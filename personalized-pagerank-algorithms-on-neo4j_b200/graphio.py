@@ -59,6 +59,38 @@ def load_neo4j_csv(nodes_csv, rels_csv):
     return row_ptr, col_idx, names
 
 
+NODE_RECORD, REL_RECORD = 15, 34   # Neo4j 3.x "standard" record format
+
+
+def load_neo4j_store(db_dir):
+    """Read the topology straight from a Neo4j 3.x store directory (row N3 of SURVEY 8f) -- no JVM needed.
+
+    `neostore.nodestore.db`: 15-byte records, bit 0 of byte 0 = in use; the node id is the record index.
+    `neostore.relationshipstore.db`: 34-byte records, byte 0 = in-use bit + bits 32-34 of the first node,
+    bytes 1-4 / 5-8 = low 32 bits of first / second node (big endian), bytes 9-12 = type int whose bits
+    28-30 carry bits 32-34 of the second node.  Relationship id = record index, so edges come out in the
+    order `GraphLoader` scans them (verified on target/got.db: equal to the import CSV).
+    Returns (row_ptr, col_idx, original_ids): mapped id i <-> Neo4j id original_ids[i] (ascending), the
+    IdMap of `Graph.toMappedNodeId` / `toOriginalNodeId`.
+    """
+    nodes = np.fromfile(os.path.join(db_dir, "neostore.nodestore.db"), dtype=np.uint8)
+    nodes = nodes[: (nodes.size // NODE_RECORD) * NODE_RECORD].reshape(-1, NODE_RECORD)
+    original_ids = np.flatnonzero(nodes[:, 0] & 1).astype(np.int64)
+    rels = np.fromfile(os.path.join(db_dir, "neostore.relationshipstore.db"), dtype=np.uint8)
+    rels = rels[: (rels.size // REL_RECORD) * REL_RECORD].reshape(-1, REL_RECORD)
+    rels = rels[(rels[:, 0] & 1) == 1]
+    be32 = lambda b: (b[:, 0].astype(np.int64) << 24) | (b[:, 1].astype(np.int64) << 16) | (b[:, 2].astype(np.int64) << 8) | b[:, 3].astype(np.int64)
+    first = be32(rels[:, 1:5]) | (((rels[:, 0].astype(np.int64) & 0x0E) >> 1) << 32)
+    type_int = be32(rels[:, 9:13])
+    second = be32(rels[:, 5:9]) | ((type_int & 0x70000000) << 4)
+    mapped = np.full(int(original_ids.max()) + 1 if original_ids.size else 0, -1, np.int64)
+    mapped[original_ids] = np.arange(original_ids.size)
+    if rels.shape[0] and (first.max() >= mapped.size or second.max() >= mapped.size or (mapped[first] < 0).any() or (mapped[second] < 0).any()):
+        raise ValueError("relationship store references a node that is not in use")
+    row_ptr, col_idx = csr_from_edges(original_ids.size, mapped[first], mapped[second])
+    return row_ptr, col_idx, original_ids
+
+
 def got_paths(root=None):
     root = root or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "got")
     return os.path.join(root, "GOT_Nodes.csv"), os.path.join(root, "GOT_Rels.csv")

@@ -4,8 +4,8 @@ Mirrors /root/reference/src/main/java/joezie/fora_neo4j/PPR.java (options, defau
 Gen_Util.java (query sampling, timing loops, error metrics, parameter grids, result-file format), so
 `python -m <package>.harness -alpha 0.15 -eps 0.5 -query 50 -k 10 -db tests/golden/got` produces the same
 `<db>_AlgoPerfResults.txt` rows as `java PPR ...`.  The Neo4j competitor (NEO4J_METHOD) is out of
-scope and is skipped.  `-db` names a directory holding `*_Nodes.csv` / `*_Rels.csv`
-(the Neo4j import CSVs): a Neo4j store cannot be opened without a JVM.
+scope and is skipped.  `-db` names either a Neo4j 3.x store directory (its node and relationship stores are read natively,
+`graphio.load_neo4j_store`) or a directory holding the Neo4j import CSVs (`*_Nodes.csv` / `*_Rels.csv`).
 """
 import argparse
 import glob
@@ -228,9 +228,13 @@ class PPR(Gen_Util):
         t0 = time.perf_counter_ns()
         nodes = sorted(glob.glob(os.path.join(self.db_path, "*Nodes.csv")))
         rels = sorted(glob.glob(os.path.join(self.db_path, "*Rels.csv")))
-        if not nodes or not rels:
-            raise FileNotFoundError("no *_Nodes.csv / *_Rels.csv under %s (a Neo4j store needs a JVM to open)" % self.db_path)
-        row_ptr, col_idx, self.names = graphio.load_neo4j_csv(nodes[0], rels[0])
+        if os.path.exists(os.path.join(self.db_path, "neostore.nodestore.db")):   # a Neo4j 3.x store directory (target/got.db)
+            row_ptr, col_idx, self.original_ids = graphio.load_neo4j_store(self.db_path)
+            self.names = [str(i) for i in self.original_ids]
+        elif nodes and rels:
+            row_ptr, col_idx, self.names = graphio.load_neo4j_csv(nodes[0], rels[0])
+        else:
+            raise FileNotFoundError("neither a Neo4j store nor *_Nodes.csv / *_Rels.csv under %s" % self.db_path)
         self.adjM = N.Graph(self.ctx, row_ptr, col_idx)
         print("\nFinish graph loading in %d(ms)" % ((time.perf_counter_ns() - t0) // 1000000))
 

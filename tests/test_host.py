@@ -109,3 +109,11 @@ def test_gloo_world2_sharding():
     for p in ps:
         p.join(60)
     assert sorted(res) == [(0, True, True), (1, True, True)]
+
+
+def test_neo4j_store_reader_matches_csv(pkg):
+    """N3: the topology read natively from the Neo4j 3.x store files equals the import CSVs."""
+    store = os.path.join(ROOT, "tests", "golden", "got.db")
+    rp, ci, ids = pkg.graphio.load_neo4j_store(store)
+    rp2, ci2, names = pkg.graphio.load_got()
+    assert np.array_equal(ids, np.arange(107)) and np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
