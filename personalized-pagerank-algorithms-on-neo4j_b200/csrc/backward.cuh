@@ -30,7 +30,8 @@ struct BwdArgs {
     u64* s_pack; u64* s_y; u32* s_t;
     u64* l_pack; u64* l_y; u32* l_t;
     uint2* chunks; i64 chunk_cap;
-    u64* blk_a;
+    u32* wcnt;     // per-warp counts of the output compaction
+    u64* dbg;      // per-iteration timeline (same layout as the forward push)
     PushCtl* ctl;
     i32 t0;        // first target of the batch
     i32 T;         // targets in the batch
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_bwd_batch(Bw
     if (gtid == 0) {
         ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0;
         ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->err = 0; ctl->err_a = 0;
-        ctl->pairs = 0; ctl->pairs_needed = 0;
+        ctl->pairs = 0; ctl->pairs_needed = 0; ctl->dbg_count = 0;
     }
     grid.sync();
     for (i64 base = 0; base < A.T; base += gsize) {
@@ -113,29 +114,32 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_bwd_batch(Bw
         const u32 cnt = *(volatile u32*)&ctl->cnt[par];
         if (cnt == 0 || *(volatile u32*)&ctl->err) break;
         // ---------------- phase A: warp-granular tiles of 128 items, one packed staging atomic per tile
+        u64 tt0 = 0, tt1 = 0;
+        if (gtid == 0) tt0 = globaltimer_ns();
         if (gtid == 0) {
             ctl->cnt[par ^ 1] = 0; ctl->stage[par ^ 1] = 0;
             ctl->pushes += cnt; ctl->iters += 1;
         }
         u64 edges_local = 0;
         for (i64 tile = gwarp * 128; tile < cnt; tile += nwarps * 128) {
-            u64 pk[4], y[4], item[4];
+            u64 pk[4], y[4], item[4], x[4];
             u32 cls[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) { i64 i = tile + k * 32 + lane; item[k] = i < cnt ? A.front[par][i] : ~0ull; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[k] = item[k] != ~0ull ? A.r[(i64)(u32)(item[k] >> 32) * n + (u32)item[k]] : 0;   // loads first,
+#pragma unroll
+            for (int k = 0; k < 4; k++) pk[k] = item[k] != ~0ull ? __ldg(&A.in_vtx[(u32)item[k]]) : 0;                      // stores afterwards
             u32 my_nch = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                pk[k] = 0; y[k] = 0; cls[k] = 0;
+                y[k] = 0; cls[k] = 0;
                 if (item[k] != ~0ull) {
-                    u32 slot_t = (u32)(item[k] >> 32), v = (u32)item[k];
-                    u64* rt = A.r + (i64)slot_t * n;
-                    u64 x = rt[v];
-                    rt[v] = 0;
-                    u64 a = mulhi64(x, A.alpha_q64);
-                    A.reserve[(i64)slot_t * n + v] += a;
-                    y[k] = x - a;
-                    pk[k] = A.in_vtx[v];
+                    const i64 idx = (i64)(u32)(item[k] >> 32) * n + (u32)item[k];
+                    A.r[idx] = 0;
+                    u64 a = mulhi64(x[k], A.alpha_q64);
+                    A.reserve[idx] += a;
+                    y[k] = x[k] - a;
                     u32 d = vtx_deg(pk[k]);
                     edges_local += d;
                     cls[k] = d == 0 ? 0u : (d <= PUSH_SMALL_MAX ? 1u : 2u);
@@ -179,6 +183,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_bwd_batch(Bw
         if (lane == 0 && edges_local) atomicAdd((ull*)&ctl->edges, (ull)edges_local);
         grid.sync();
         if (*(volatile u32*)&ctl->err_a) break;
+        if (gtid == 0) tt1 = globaltimer_ns();
         // ---------------- phase B
         const u64 staged = *(volatile u64*)&ctl->stage[par];
         const u32 ns = (u32)staged, nch = (u32)(staged >> 32);
@@ -246,35 +251,41 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_bwd_batch(Bw
             }
         }
         grid.sync();
+        if (gtid == 0) {
+            u32 k = ctl->dbg_count;
+            if (k < DBG_ITERS) { u64* d = A.dbg + (size_t)k * DBG_FIELDS; d[0] = tt0; d[1] = tt1; d[2] = globaltimer_ns(); d[3] = cnt; d[4] = ctl->edges; d[5] = 0; ctl->dbg_count = k + 1; }
+        }
         par ^= 1;
     }
     if (*(volatile u32*)&ctl->err || *(volatile u32*)&ctl->err_a) return;
 
     // ---------------- ordered compaction of {reserve >= thr_fx} over the [T][n] matrix
+    // Warp-granular: every warp owns a contiguous slice, counts its qualifying entries (pass 1), gets its
+    // offset from the per-warp counts, and writes with ballots (pass 2).  No CTA barrier inside the loops
+    // (a block-scan version spent ~7 ms per 1024-target batch in __syncthreads).
     const i64 total = (i64)A.T * n;
-    const i64 per = (total + gridDim.x - 1) / gridDim.x;
-    const i64 lo = min(total, (i64)blockIdx.x * per), hi = min(total, lo + per);
-    u64 c = 0;
-    for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) { u64 x = A.reserve[i]; c += (x != 0 && x >= A.thr_fx); }
-    c = block_sum_u64(c, sm_excl);
-    if (threadIdx.x == 0) A.blk_a[blockIdx.x] = c;
+    const i64 per = (((total + nwarps - 1) / nwarps) + 31) & ~(i64)31;   // slice length, multiple of 32
+    const i64 lo = min(total, gwarp * per), hi = min(total, lo + per);
+    u32 c = 0;
+    for (i64 i = lo + lane; i < hi; i += 32) { u64 x = A.reserve[i]; c += (x != 0 && x >= A.thr_fx); }
+    c = (u32)warp_sum_u64(c);
+    if (lane == 0) A.wcnt[gwarp] = c;
     grid.sync();
     u64 off = 0;
-    for (u32 b = threadIdx.x; b < blockIdx.x; b += blockDim.x) off += A.blk_a[b];
-    off = block_sum_u64(off, sm_excl);
-    for (i64 tile = lo; tile < hi; tile += blockDim.x) {
-        i64 i = tile + threadIdx.x;
+    for (i64 w = lane; w < gwarp; w += 32) off += A.wcnt[w];
+    off = warp_sum_u64(off);
+    for (i64 base = lo; base < hi; base += 32) {
+        i64 i = base + lane;
         u64 x = i < hi ? A.reserve[i] : 0;
-        u64 has = (x != 0 && x >= A.thr_fx) ? 1 : 0;
-        u64 e1, e2, t1, t2;
-        block_excl_scan2(has, 0, sm_excl, e1, e2, t1, t2);
+        bool has = x != 0 && x >= A.thr_fx;
+        u32 mask = __ballot_sync(0xffffffffu, has);
         if (has) {
-            u64 slot = off + e1;
+            u64 slot = off + __popc(mask & lanemask_lt());
             if ((i64)slot < A.out_cap) { A.out_v[slot] = (u32)(i % n); A.out_t[slot] = (u32)(A.t0 + i / n); A.out_val[slot] = x; }
         }
-        off += t1;
+        off += __popc(mask);
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    if (gwarp == nwarps - 1 && lane == 0) {
         ctl->pairs_needed = off;
         ctl->pairs = min(off, (u64)A.out_cap);
     }

@@ -224,7 +224,7 @@ static int32_t ws_alloc(ppr_ctx* ctx, Workspace& w, i64 n, i64 chunk_cap) {
     if (occ < 1) return ctx_fail(ctx, PPR_E_CUDA, "cooperative kernels do not fit on an SM");
     w.coop_blocks = ctx->sm_count * std::min(occ, 4);
     CUDA_TRY(dalloc(&w.blk_a, (size_t)w.coop_blocks)); CUDA_TRY(dalloc(&w.blk_b, (size_t)w.coop_blocks));
-    CUDA_TRY(dalloc(&w.blk_c, (size_t)w.coop_blocks));
+    CUDA_TRY(dalloc(&w.blk_c, (size_t)w.coop_blocks * (PUSH_THREADS / 32)));   // also the per-warp counts of the reverse push
     CUDA_TRY(dalloc(&w.out_f64, N));
     CUDA_TRY(dalloc(&w.hist, (size_t)9 * 256));
     w.sel_cap = std::min<i64>(n, (i64)1 << 22);
@@ -960,7 +960,7 @@ static int32_t bwd_run_batch(ppr_graph* g, BwdWorkspace& b, i32 t0, i32 T, doubl
     A.n = n; A.in_vtx = g->d.in_vtx; A.row_idx = g->d.row_idx; A.invdeg = g->d.invdeg;
     A.r = b.r; A.reserve = b.reserve; A.front[0] = b.front[0]; A.front[1] = b.front[1]; A.front_cap = b.front_cap;
     A.s_pack = b.s_pack; A.s_y = b.s_y; A.s_t = b.s_t; A.l_pack = b.l_pack; A.l_y = b.l_y; A.l_t = b.l_t;
-    A.chunks = b.chunks; A.chunk_cap = b.chunk_cap; A.blk_a = w.blk_a; A.ctl = w.ctl; A.t0 = t0; A.T = T;
+    A.chunks = b.chunks; A.chunk_cap = b.chunk_cap; A.wcnt = reinterpret_cast<u32*>(w.blk_c); A.dbg = w.dbg; A.ctl = w.ctl; A.t0 = t0; A.T = T;
     A.alpha_q64 = h_alpha_q64(alpha);
     // J/Backward_Search.java:89 (r > rmax) and J/Base_Whole_Graph.java:83 (pi >= threshold), in fixed point
     double fl = threshold > 0 ? std::floor(threshold * FX_SCALE) : 0.0;
@@ -1047,7 +1047,6 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     BwdWorkspace& b = extra_of(g)->bws;
     T = std::min<i64>(T, b.T);
     std::vector<u32> hv, ht; std::vector<u64> hval;
-    std::vector<u32> bv, bt; std::vector<u64> bval;
     i64 pushes = 0, edges = 0, iters = 0;
     int launches = 0;
     CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1064,14 +1063,16 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
         }
         pushes += (i64)h.pushes; edges += (i64)h.edges; iters += (i64)h.iters;
         size_t cnt = (size_t)h.pairs;
-        if (cnt) {
-            try { bv.resize(cnt); bt.resize(cnt); bval.resize(cnt); } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
-            CUDA_TRY(cudaMemcpyAsync(bv.data(), b.out_v, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaMemcpyAsync(bt.data(), b.out_t, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaMemcpyAsync(bval.data(), b.out_val, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (cnt) {   // download straight into the tail of the host arrays
+            size_t old = hv.size();
+            try {
+                if (hv.capacity() < old + cnt) { size_t cap = std::max(old + cnt, old * 2); hv.reserve(cap); ht.reserve(cap); hval.reserve(cap); }
+                hv.resize(old + cnt); ht.resize(old + cnt); hval.resize(old + cnt);
+            } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
+            CUDA_TRY(cudaMemcpyAsync(hv.data() + old, b.out_v, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(ht.data() + old, b.out_t, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(hval.data() + old, b.out_val, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            try { hv.insert(hv.end(), bv.begin(), bv.end()); ht.insert(ht.end(), bt.begin(), bt.end()); hval.insert(hval.end(), bval.begin(), bval.end()); }
-            catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
         }
         t0 += Tb;
     }
