@@ -9,9 +9,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "backward.cuh"
@@ -950,6 +952,19 @@ extern "C" int32_t ppr_power_iteration(ppr_graph* g, int32_t src, double alpha, 
     return PPR_OK;
 }
 
+// host-side stage timer for tuning (PPR_DEBUG_TIMING=1 prints to stderr)
+#include <chrono>
+struct StageTimer {
+    bool on; std::chrono::steady_clock::time_point t;
+    StageTimer() : on(getenv("PPR_DEBUG_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pprb200] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 // ============================================================================================= backward search
 static int32_t bwd_run_batch(ppr_graph* g, BwdWorkspace& b, i32 t0, i32 T, double alpha, double threshold, PushCtl* hctl) {
     ppr_ctx* ctx = g->ctx;
@@ -1032,8 +1047,10 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     cudaSetDevice(ctx->device);
     g->trace_active = false;
     // batch size: dense per-target state is 16 n bytes; stay within a quarter of the free memory and 8 GB
+    StageTimer tm;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    tm.mark("cudaMemGetInfo");
     size_t budget = std::min<size_t>(free_b / 4, (size_t)8 << 30);
     i64 T = (i64)std::max<size_t>(1, budget / ((size_t)16 * (size_t)n));
     T = std::min<i64>(T, 4096);
@@ -1044,6 +1061,7 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     else T = std::min<i64>(T, std::max<i64>(32, ((i64)768 << 20) / (8 * n)));
     T = std::min<i64>(T, std::max<i64>(1, t_hi - t_lo));
     int32_t rc = bwd_ensure(g, (i32)T); if (rc) return rc;
+    tm.mark("workspace");
     BwdWorkspace& b = extra_of(g)->bws;
     T = std::min<i64>(T, b.T);
     std::vector<u32> hv, ht; std::vector<u64> hval;
@@ -1056,6 +1074,7 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
         PushCtl h;
         rc = bwd_run_batch(g, b, (i32)t0, (i32)Tb, alpha, threshold, &h); if (rc) return rc;
         launches++;
+        tm.mark("batch kernel + sync");
         if (h.err || h.err_a || h.pairs_needed > (u64)b.out_cap) {  // frontier or output overflow: rerun with fewer targets
             if (Tb == 1) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_backward_all_pairs: a single target overflows the batch buffers");
             curT = std::max<i64>(1, Tb / 2);
@@ -1073,22 +1092,48 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
             CUDA_TRY(cudaMemcpyAsync(ht.data() + old, b.out_t, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaMemcpyAsync(hval.data() + old, b.out_val, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            tm.mark("download");
         }
         t0 += Tb;
     }
     CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    tm.mark("final sync");
     // inverted index grouped by source v (J/Base_Whole_Graph.java:83-87): stable counting sort keeps targets ascending
     ppr_pairs* P = new (std::nothrow) ppr_pairs();
     if (!P) return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed");
     P->n = n;
     try {
+        // stable counting sort by source, parallel over contiguous chunks of the (target-ordered) pair list:
+        // per-chunk histograms -> per-(source, chunk) start offsets -> independent scatters
+        const size_t np = hv.size();
+        unsigned hw = std::thread::hardware_concurrency();
+        int nt = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
+        while (nt > 1 && ((size_t)n * nt > ((size_t)64 << 20) || np < ((size_t)1 << 18))) nt /= 2;
+        std::vector<u32> hist((size_t)n * nt, 0);
+        auto chunk = [&](int c, size_t& lo, size_t& hi) { lo = np * (size_t)c / nt; hi = np * (size_t)(c + 1) / nt; };
+        auto run = [&](auto fn) {
+            std::vector<std::thread> th;
+            for (int c = 1; c < nt; c++) th.emplace_back(fn, c);
+            fn(0);
+            for (auto& t : th) t.join();
+        };
+        run([&](int c) { size_t lo, hi; chunk(c, lo, hi); u32* h = hist.data() + (size_t)c * n; for (size_t i = lo; i < hi; i++) h[hv[i]]++; });
         P->src_ptr.assign((size_t)n + 1, 0);
-        for (size_t i = 0; i < hv.size(); i++) P->src_ptr[(size_t)hv[i] + 1]++;
-        for (i64 v = 0; v < n; v++) P->src_ptr[(size_t)v + 1] += P->src_ptr[(size_t)v];
-        P->tgt.resize(hv.size()); P->val.resize(hv.size());
-        std::vector<i64> pos(P->src_ptr.begin(), P->src_ptr.end() - 1);
-        for (size_t i = 0; i < hv.size(); i++) { i64 p = pos[hv[i]]++; P->tgt[(size_t)p] = (i32)ht[i]; P->val[(size_t)p] = hval[i]; }
+        {
+            i64 acc = 0;
+            for (i64 v = 0; v < n; v++) {
+                P->src_ptr[(size_t)v] = acc;
+                for (int c = 0; c < nt; c++) { u32 cnt = hist[(size_t)c * n + v]; hist[(size_t)c * n + v] = (u32)(acc - P->src_ptr[(size_t)v]); acc += cnt; }
+            }
+            P->src_ptr[(size_t)n] = acc;
+        }
+        P->tgt.resize(np); P->val.resize(np);
+        run([&](int c) {
+            size_t lo, hi; chunk(c, lo, hi);
+            u32* h = hist.data() + (size_t)c * n;   // now: offset of this chunk's next entry inside row v
+            for (size_t i = lo; i < hi; i++) { u32 v = hv[i]; size_t p = (size_t)P->src_ptr[v] + h[v]++; P->tgt[p] = (i32)ht[i]; P->val[p] = hval[i]; }
+        });
         if (k >= 0) {  // J/Base_Whole_Graph.java:133-148: keep >= k-th largest, sort descending (stable)
             std::vector<i64> nptr((size_t)n + 1, 0);
             std::vector<i32> ntgt; std::vector<u64> nval;
@@ -1110,6 +1155,7 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
             P->src_ptr.swap(nptr); P->tgt.swap(ntgt); P->val.swap(nval);
         }
     } catch (...) { delete P; return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
+    tm.mark("group by source");
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->pushes = pushes; stats->edges = edges; stats->iters = iters;
