@@ -32,6 +32,8 @@ typedef unsigned long long ull;
 
 // Forward-push work classes
 #define PUSH_SMALL_MAX 64   // degree <= this: warp-cooperative gather over 32 vertices
+#define PUSH_MINI_MAX PUSH_THREADS  // frontiers up to this size are iterated by one CTA without grid barriers
+#define PUSH_MINI_EDGES 4096        // ... owning at most this many edges
 #define PUSH_CHUNK 256      // larger rows are cut into chunks of this many edges, one warp per chunk
 
 #define DBG_ITERS 4096
@@ -114,6 +116,7 @@ struct PushCtl {
     u64 dang[2];       // dangling mass headed for the source
     u32 fcnt[2];       // vertices pushed by the iteration (both frontier modes)
     u64 fedges[2];     // edges relaxed by the iteration
+    u64 nedge[2];      // out-degree sum of the frontier list being built (LIST appends; degrees clamped to 2^20)
     // work counters
     u64 reserve_total; // sum of everything moved into reserve by pushes
     u64 pushes, edges, iters, rounds;
@@ -134,7 +137,7 @@ struct PushCtl {
     u32 err;           // device-side error flags
     u32 src_dangling;  // 1 = the query source has no out-edges (result is {src: 1})
     u32 err_a;         // error raised during a phase A (kept apart from err so each flag is only read behind a barrier)
-    u32 pad2;
+    u32 mini_par;      // forward push: frontier parity after a run of single-CTA iterations
     u32 dbg_count;     // timeline entries written
     u32 pad3;
     u64 pairs;         // all-pair backward search: (v, t) pairs written by the batch

@@ -422,7 +422,7 @@ static void fill_push_args(PushArgs& A, ppr_graph* g, Workspace& w) {
     A.n = g->d.n; A.out_vtx = g->d.out_vtx; A.col_idx = g->d.col_idx; A.out_deg = g->d.out_deg;
     A.push_idx = g->d.push_idx; A.hot_id = g->d.hot_id; A.n_hot = g->d.n_hot;
     A.r = w.r; A.reserve = w.reserve; A.est = w.est; A.front[0] = w.front[0]; A.front[1] = w.front[1];
-    A.s_pack = w.s_pack; A.s_q = w.s_q; A.l_pack = w.l_pack; A.l_q = w.l_q; A.chunks = w.chunks;
+    A.s_pack = w.s_pack; A.s_q = w.s_q; A.l_pack = w.l_pack; A.l_q = w.l_q; A.chunks = w.chunks; A.mini = getenv("PPR_NO_MINI") ? 0 : 1;
     A.ws_v = w.ws_v; A.ws_begin = w.ws_begin; A.ws_inc = w.ws_inc; A.ws_rem = w.ws_rem;
     A.blk_a = w.blk_a; A.blk_b = w.blk_b; A.ctl = w.ctl; A.dbg = w.dbg;
     A.prep_adds_push_part = 1;

@@ -63,6 +63,7 @@ struct PushArgs {
     int zero_reserve_after_push;  // shard != 0 of a multi-GPU FORA: drop the push reserve before the walk prep
     int prep_adds_push_part;      // shard == 0
     i64 scan_threshold;           // frontier edges >= this: next frontier is found by a dense sweep (SCAN mode)
+    int mini;                     // 1: frontiers of <= PUSH_MINI_MAX vertices are iterated by one CTA (push_mini)
 };
 
 #define PMODE_PUSH 0
@@ -81,18 +82,29 @@ __device__ __forceinline__ void warp_append_u32(u32* list, u32* counter, bool pr
     }
 }
 
-// Four predicated values per lane, one counter round trip for the whole warp.
-__device__ __forceinline__ void warp_append4_u32(u32* list, u32* counter, const bool (&pred)[4], const u32 (&value)[4]) {
+// Four predicated values per lane, one counter round trip for the whole warp.  The out-degrees of the appended
+// vertices (each clamped to 2^20, enough to compare against PUSH_MINI_EDGES) are summed into *edge_counter.
+template <typename EdgeCounter>
+__device__ __forceinline__ void warp_append4_u32(u32* list, u32* counter, EdgeCounter* edge_counter, const bool (&pred)[4],
+                                                 const u32 (&value)[4], const u32 (&deg)[4], u32* mirror, u32 mirror_cap) {
     u32 m[4], tot = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) { m[k] = __ballot_sync(0xffffffffu, pred[k]); tot += __popc(m[k]); }
     if (tot) {
+        u32 dsum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (pred[k]) dsum += min(deg[k], 1u << 20);
+        dsum = __reduce_add_sync(0xffffffffu, dsum);
         u32 base = 0;
-        if (lane_id() == 0) base = atomicAdd(counter, tot);
+        if (lane_id() == 0) { base = atomicAdd(counter, tot); atomicAdd(edge_counter, (EdgeCounter)dsum); }
         base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (pred[k]) list[base + __popc(m[k] & lanemask_lt())] = value[k];
+            if (pred[k]) {
+                u32 idx = base + __popc(m[k] & lanemask_lt());
+                list[idx] = value[k];
+                if (mirror && idx < mirror_cap) mirror[idx] = value[k];
+            }
             base += __popc(m[k]);
         }
     }
@@ -139,7 +151,7 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     const i64 cnt = SCAN ? A.n : (i64)*(volatile u32*)&ctl->cnt[par];
     if (gtid == 0) {  // recycle the other parity's counters (last read before the preceding barrier)
         ctl->cnt[par ^ 1] = 0; ctl->stage[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
-        ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0;
+        ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0; ctl->nedge[par ^ 1] = 0;
     }
     u64 edges_local = 0, resv_local = 0, dang_local = 0, pushed_local = 0;
     const u32* F = A.front[par];
@@ -235,12 +247,13 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
 // --------------------------------------------------------------------------------- phase B
 // One relaxed edge.  LIST: returning atomic + crossing test; otherwise a fire-and-forget reduction.
 template <bool LIST>
-__device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32& u, u64 q, u64* sm_hot) {
+__device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32& u, u64 q, u64* sm_hot, u32& deg) {
     // `u` comes from push_idx: hub targets are encoded as HOT_BIT | slot.
     if (LIST) {
         if (u & HOT_BIT) u = __ldg(&A.hot_id[u & HOT_MASK]);
         u64 old = atomicAdd((ull*)&A.r[u], (ull)q);
-        u64 th = thr_fwd(rmax_fx, __ldg(&A.out_deg[u]));
+        deg = __ldg(&A.out_deg[u]);
+        u64 th = thr_fwd(rmax_fx, deg);
         return old < th && old + q >= th;
     } else {
         // dense frontiers: adds to hub vertices are accumulated per CTA in shared memory and flushed once
@@ -288,7 +301,7 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
         w_q[lane] = q;
         __syncwarp();
         for (u32 eb = 0; eb < total; eb += 128) {  // four independent edges per lane in flight
-            u32 u[4];
+            u32 u[4], dg[4];
             u64 qq[4];
             bool cr[4];
 #pragma unroll
@@ -305,8 +318,8 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], qq[k], sm_hot) : false;
-            if (LIST) warp_append4_u32(next, next_cnt, cr, u);
+            for (int k = 0; k < 4; k++) { dg[k] = 0; cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], qq[k], sm_hot, dg[k]) : false; }
+            if (LIST) warp_append4_u32(next, next_cnt, (ull*)&ctl->nedge[par ^ 1], cr, u, dg, (u32*)nullptr, 0u);
         }
         __syncwarp();
     }
@@ -321,13 +334,13 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
         u32 len = min((u32)PUSH_CHUNK, d - off);
         const u32* row = A.push_idx + vtx_begin(pk) + off;
         for (u32 eb = 0; eb < len; eb += 128) {
-            u32 u[4];
+            u32 u[4], dg[4];
             bool cr[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) { u32 e = eb + 32 * k + lane; u[k] = e < len ? ld_hint_u32(&row[e], pol_stream) : 0xffffffffu; }
 #pragma unroll
-            for (int k = 0; k < 4; k++) cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], q, sm_hot) : false;
-            if (LIST) warp_append4_u32(next, next_cnt, cr, u);
+            for (int k = 0; k < 4; k++) { dg[k] = 0; cr[k] = u[k] != 0xffffffffu ? relax_edge<LIST>(A, rmax_fx, u[k], q, sm_hot, dg[k]) : false; }
+            if (LIST) warp_append4_u32(next, next_cnt, (ull*)&ctl->nedge[par ^ 1], cr, u, dg, (u32*)nullptr, 0u);
         }
     }
 
@@ -345,7 +358,7 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
         if (dsum) {
             u64 old = atomicAdd((ull*)&A.r[A.src], (ull)dsum);
             u64 th = thr_fwd(rmax_fx, A.out_deg[A.src]);
-            if (LIST && old < th && old + dsum >= th) { u32 idx = atomicAdd(next_cnt, 1u); next[idx] = (u32)A.src; }
+            if (LIST && old < th && old + dsum >= th) { u32 idx = atomicAdd(next_cnt, 1u); next[idx] = (u32)A.src; atomicAdd((ull*)&ctl->nedge[par ^ 1], (ull)A.out_deg[A.src]); }
         }
         ctl->iters += 1;
         ctl->pushes += *(volatile u32*)&ctl->fcnt[par];
@@ -393,6 +406,112 @@ __device__ __forceinline__ void block_excl_scan2(u64 a, u64 b, u64* sm /*>= 64 e
     ea = wa + ia - a;
     eb = wb + ib - b;
     __syncthreads();
+}
+
+// --------------------------------------------------------------------------------- single-CTA iterations
+// The head and the tail of every round are frontiers of a few (hundred) vertices, and a grid-wide iteration costs
+// ~22 us however little it does (two grid barriers and a dozen dependent L2 round trips on the counters).  While the
+// frontier holds at most PUSH_MINI_MAX vertices, CTA 0 runs the same synchronous iterations alone: one frontier
+// vertex per thread, frontier / staging / counters in shared memory, __syncthreads instead of grid barriers
+// (3-8 us per iteration).  The other CTAs wait at the next grid barrier.  Same schedule, same bits.  Entry needs the
+// frontier's edge count too (ctl->nedge, accumulated by the LIST appends): 30 vertices can own 50 K edges.
+// Ordering inside the CTA rests on __syncthreads alone (store -> barrier -> atomic on one address from one SM).  Do NOT add
+// __threadfence() here: with a fence anywhere in the kernel ptxas stops turning result-less atomics into REDG (it emits
+// ATOMG with an RZ destination instead) and the dense phase B drops from ~200 to ~140 G edges/s.
+__device__ __noinline__ void push_mini(const PushArgs& A, int par, u64 rmax_fx, u64* m_excl, u64* m_beg, u64* m_q, u64* scratch /*64*/,
+                          u32* mf /*PUSH_MINI_MAX*/, u32* m_ctr /*2*/) {
+    PushCtl* ctl = A.ctl;
+    const u32 tid = threadIdx.x;
+    u32 mc = __ldcg(&ctl->cnt[par]);
+    if (tid < mc) mf[tid] = __ldcg(&A.front[par][tid]);
+    u32 ne = 0;
+    u64* acc = scratch + 48;  // [iters, pushes, edges, reserve] of this run, kept by thread 0 (the scans use scratch[0..47])
+    if (tid == 0) { acc[0] = 0; acc[1] = 0; acc[2] = ctl->edges; acc[3] = 0; }
+    __syncthreads();
+    for (;;) {
+        u64 t0 = 0, t1 = 0;
+        if (tid == 0) t0 = globaltimer_ns();
+        // phase A: one frontier vertex per thread
+        u64 a = 0, dangy = 0, pk = 0, q = 0;
+        u32 d = 0;
+        if (tid < mc) {
+            const u32 v = mf[tid];
+            const u64 x = __ldcg(&A.r[v]);  // r[] is updated by L2 atomics between iterations: never through L1
+            pk = A.out_vtx[v];
+            d = vtx_deg(pk);
+            a = mulhi64(x, A.alpha_q64);
+            const u64 y = x - a;
+            u64 left;
+            if (d == 0) { left = 0; dangy = y; }
+            else { q = y / (u64)d; left = y - q * (u64)d; }
+            A.r[v] = left;
+            A.reserve[v] += a;
+        }
+        u64 e_d, e_a, t_d, t_a;
+        block_excl_scan2((u64)d, a, scratch, e_d, e_a, t_d, t_a);
+        const u64 dang_total = block_sum_u64(dangy, scratch);
+        m_excl[tid] = tid < mc ? e_d : ~0ull;
+        m_beg[tid] = vtx_begin(pk) - e_d;  // edge address of concatenated position e is m_beg[owner] + e
+        m_q[tid] = q;
+        if (tid == 0) { m_ctr[0] = 0; m_ctr[1] = 0; t1 = globaltimer_ns(); }
+        __syncthreads();
+        // phase B: threads sweep the concatenated edge list, four independent edges per thread in flight
+        u32* next = A.front[par ^ 1];
+        for (u64 eb = 0; eb < t_d; eb += 4 * PUSH_THREADS) {
+            u32 u[4], dg[4];
+            u64 qq[4];
+            bool cr[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const u64 e = eb + (u64)k * PUSH_THREADS + tid;
+                u[k] = 0xffffffffu;
+                qq[k] = 0;
+                if (e < t_d) {
+                    int o = 0;
+#pragma unroll
+                    for (int s = PUSH_MINI_MAX / 2; s > 0; s >>= 1) { int p = o + s; if (m_excl[p] <= e) o = p; }
+                    u[k] = __ldg(&A.push_idx[m_beg[o] + e]);
+                    qq[k] = m_q[o];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { dg[k] = 0; cr[k] = u[k] != 0xffffffffu ? relax_edge<true>(A, rmax_fx, u[k], qq[k], nullptr, dg[k]) : false; }
+            warp_append4_u32(next, &m_ctr[0], &m_ctr[1], cr, u, dg, mf, (u32)PUSH_MINI_MAX);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (dang_total) {  // dangling mass -> source (J/Forward_Push.java:101-113)
+                u64 old = atomicAdd((ull*)&A.r[A.src], (ull)dang_total);
+                u64 th = thr_fwd(rmax_fx, A.out_deg[A.src]);
+                if (old < th && old + dang_total >= th) {
+                    u32 idx = m_ctr[0]++;
+                    next[idx] = (u32)A.src;
+                    if (idx < PUSH_MINI_MAX) mf[idx] = (u32)A.src;
+                    m_ctr[1] += min(A.out_deg[A.src], 1u << 20);
+                }
+            }
+            acc[0] += 1; acc[1] += mc; acc[2] += t_d; acc[3] += t_a;
+            u32 k = ctl->dbg_count;
+            if (k < DBG_ITERS) {
+                u64* dd = A.dbg + (size_t)k * DBG_FIELDS;
+                dd[0] = t0; dd[1] = t1; dd[2] = globaltimer_ns(); dd[3] = mc; dd[4] = acc[2]; dd[5] = 4;
+                ctl->dbg_count = k + 1;
+            }
+        }
+        __syncthreads();
+        par ^= 1;
+        mc = m_ctr[0];
+        ne = m_ctr[1];
+        __syncthreads();
+        if (mc == 0 || mc > PUSH_MINI_MAX || ne > PUSH_MINI_EDGES) break;
+    }
+    if (tid == 0) {  // hand the state back to the grid-wide loop: list in front[par], its size in cnt[par], all else clean
+        ctl->cnt[par] = mc; ctl->cnt[par ^ 1] = 0;
+        ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0;
+        ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0; ctl->nedge[par] = ne; ctl->nedge[par ^ 1] = 0;
+        ctl->iters += acc[0]; ctl->pushes += acc[1]; ctl->edges = acc[2]; ctl->reserve_total += acc[3];
+        ctl->mini_par = (u32)par;
+    }
 }
 
 // --------------------------------------------------------------------------------- walk preparation (inside the cooperative kernel)
@@ -497,13 +616,16 @@ __device__ void walk_prep(const PushArgs& A, cg::grid_group& grid, u64* sm) {
 }
 
 // --------------------------------------------------------------------------------- the persistent query kernel
-__global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(PushArgs A) {
+__global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(const __grid_constant__ PushArgs A) {
     cg::grid_group grid = cg::this_grid();
     __shared__ u64 sm_excl[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
     __shared__ __align__(8) u32 sm_cnt[16];
     __shared__ u64 sm_hot[HOT_SLOTS];
+    __shared__ u64 sm_scan[64];
+    __shared__ u32 sm_mf[PUSH_MINI_MAX];
+    __shared__ u32 sm_mctr[2];
     PushCtl* ctl = A.ctl;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 gsize = (i64)gridDim.x * blockDim.x;
@@ -513,7 +635,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(P
     if (A.init) {
         for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
         if (gtid == 0) {
-            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
+            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0; ctl->nedge[0] = ctl->nedge[1] = 0;
             ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0, A.alpha_q64);
             ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0; ctl->dbg_count = 0;
@@ -523,7 +645,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(P
     if (gtid == 0) {
         ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0;
         if (!A.init) {  // top-k round: host supplied the round's rmax; counters of both parities must be clean
-            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
+            ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0; ctl->nedge[0] = ctl->nedge[1] = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0, A.alpha_q64);
         }
     }
@@ -541,18 +663,31 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(P
         }
         return;
     }
-    if (A.init && gtid == 0) A.r[A.src] = FX_ONE;
+    if (A.init && gtid == 0) {
+        A.r[A.src] = FX_ONE;
+        // the first frontier is known: {src} if it is above threshold -- no dense sweep needed to find it
+        if (FX_ONE >= thr_fwd(ctl->rmax_fx, A.out_deg[A.src])) { A.front[0][0] = (u32)A.src; ctl->cnt[0] = 1; ctl->nedge[0] = A.out_deg[A.src]; }
+    }
     grid.sync();
 
     int par = 0;
+    bool first_round = true;
     for (;;) {  // rounds (FORA: rmax halves between rounds)
         const u64 rmax_fx = *(volatile u64*)&ctl->rmax_fx;
-        bool have_list = false;  // a round starts with a dense sweep: rmax just changed
+        bool have_list = first_round && A.init;  // later rounds start with a dense sweep: rmax just changed
+        first_round = false;
         for (;;) {
             u64 t0 = 0, t1 = 0;
             if (gtid == 0) t0 = globaltimer_ns();
             if (have_list) {
-                if (*(volatile u32*)&ctl->cnt[par] == 0) break;
+                const u32 c = *(volatile u32*)&ctl->cnt[par];
+                if (c == 0) break;
+                if (A.mini && c <= PUSH_MINI_MAX && *(volatile u64*)&ctl->nedge[par] <= PUSH_MINI_EDGES) {
+                    if (blockIdx.x == 0) push_mini(A, par, rmax_fx, sm_excl, sm_beg, sm_q, sm_scan, sm_mf, sm_mctr);
+                    grid.sync();
+                    par = (int)*(volatile u32*)&ctl->mini_par;
+                    continue;
+                }
                 push_phase_a<false>(A, par, rmax_fx, gtid, gsize, sm_cnt);
             } else {
                 push_phase_a<true>(A, par, rmax_fx, gtid, gsize, sm_cnt);
@@ -612,7 +747,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_init(PushArgs A) {
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
     for (i64 v = gtid; v < A.n; v += gsize) { A.r[v] = 0; A.reserve[v] = 0; }
     if (gtid == 0) {
-        ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0;
+        ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0; ctl->nedge[0] = ctl->nedge[1] = 0;
         ctl->reserve_total = 0; ctl->pushes = 0; ctl->edges = 0; ctl->iters = 0; ctl->rounds = 0;
         ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0, A.alpha_q64);
         ctl->steps = 0; ctl->walks_done = 0; ctl->err = 0; ctl->src_dangling = 0; ctl->cont = 0;

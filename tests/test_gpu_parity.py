@@ -221,6 +221,25 @@ def test_frontier_modes_give_identical_bits(ctx, G, OG, R12, O):
         ctx.set_tuning(-1)
 
 
+def test_single_cta_iterations_give_identical_bits(G, OG, R12, R16, O, monkeypatch):
+    # small frontiers are iterated by one CTA (push_mini); PPR_NO_MINI=1 keeps every iteration grid-wide.
+    # Both must give the oracle's bits (the rest of this file runs with the default, i.e. mini enabled).
+    for no_mini in ("1", None):
+        if no_mini:
+            monkeypatch.setenv("PPR_NO_MINI", no_mini)
+        else:
+            monkeypatch.delenv("PPR_NO_MINI", raising=False)
+        for g, og, srcs in ((G, OG, (0, 63, 100)), (R12[0], R12[1], sources(R12[1], 2)), (R16[0], R16[1], sources(R16[1], 1))):
+            for s in srcs:
+                check_fora(g, og, O, s, EPS)
+                g.forward_push(s, ALPHA, 1e-7, want_residue=False)
+                raw_res, raw_r = g.last_raw()
+                ores, orr, ost = O.b_forward_push(og, s, ALPHA, 1e-7)
+                assert np.array_equal(raw_res, ores) and np.array_equal(raw_r, orr), (no_mini, s)
+        ids, _, _ = G.fora_topk(63, ALPHA, EPS, K, SEED)
+        assert np.array_equal(G.last_raw(False)[0], O.b_fora_topk(OG, 63, ALPHA, EPS, K, SEED)[0])
+
+
 def test_hub_slots_give_identical_bits(pkg, ctx, got, rmat12, O):
     # every vertex with an in-edge gets a shared-memory hub slot (hot_min_indeg = 1) and every iteration runs in
     # SCAN mode (threshold 0): the staged adds + per-CTA flush must reproduce the oracle's bits
