@@ -44,6 +44,10 @@ typedef unsigned long long ull;
 #define PUSH_THREADS 512
 #define PUSH_CTAS_PER_SM (1024 / PUSH_THREADS)   // 32 resident warps per SM at 64 registers per thread
 #define WALK_THREADS 256
+#ifndef WALK_PER_LANE
+#define WALK_PER_LANE 2      // walks in flight per lane
+#endif
+#define WALK_CTAS_PER_SM 4
 #ifndef WALK_REFILL_MIN
 #define WALK_REFILL_MIN 12
 #endif

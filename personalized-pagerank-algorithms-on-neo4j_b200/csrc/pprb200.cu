@@ -387,7 +387,7 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     rc = ws_alloc(ctx, g->ws[0], n, chunk_cap);
     if (rc != PPR_OK) { ppr_graph_destroy(g); return rc; }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<true>, WALK_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<true, WALK_PER_LANE>, WALK_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
     x->walk_blocks = ctx->sm_count * occ;
     *out = g;
     return PPR_OK;
@@ -445,8 +445,8 @@ static cudaError_t launch_walk(ppr_ctx* ctx, ppr_graph* g, Workspace& w, u64* ta
     W.tstop = h_stop_threshold(alpha);
     W.src = src; W.restart_at_source = restart_at_source; W.no_zero_hop = no_zero_hop;
     const bool big = 4.0 * (double)g->d.m + 8.0 * (double)g->d.n > 96.0 * 1024 * 1024;   // graph beyond the L2: use eviction hints
-    if (big) k_walk<true><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
-    else k_walk<false><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
+    if (big) k_walk<true, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
+    else k_walk<false, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
     return cudaGetLastError();
 }
 

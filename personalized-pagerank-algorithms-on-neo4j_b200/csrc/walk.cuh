@@ -74,8 +74,11 @@ __device__ __forceinline__ u64 mul_div_u64(u64 a, u64 b, u64 c) {  // floor(a*b/
 
 // HINT: L2 eviction-priority hints (vertex records evict-last, neighbour sectors evict-first).  Worth 6 % of the
 // walk time once the graph exceeds the L2 (scale 22+); costs 4 % in the issue-bound L2-resident case (scale 20).
-template <bool HINT>
-__global__ void __launch_bounds__(WALK_THREADS, 4) k_walk(WalkArgs A) {
+// NW: walks in flight per lane.  A move is two dependent random loads (vertex record, neighbour), so a lane with one
+// walk spends most of its time waiting; with NW walks the loads of each stage are issued together (predicated, no
+// branches in between) and the latency is paid once per stage for all of them.
+template <bool HINT, int NW>
+__global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_walk(WalkArgs A) {
     __shared__ u64 win[WALK_THREADS / 32][34];
     PushCtl* ctl = A.ctl;
     const u64 W = ctl->total_walks;
@@ -102,52 +105,102 @@ __global__ void __launch_bounds__(WALK_THREADS, 4) k_walk(WalkArgs A) {
     }
     const u64 pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     u64 wnext = wl;
-    bool active = false;
-    WalkState w; w.start = w.cur = w.restart = w.step = 0; w.j = 0; w.first = false;
-    u64 inc = 0, steps = 0, done = 0;
+    // per-slot walk state (arrays are fully unrolled into registers)
+    u32 w_start[NW], w_cur[NW], w_step[NW];
+    u64 w_j[NW], inc[NW];
+    bool active[NW], first[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) { w_start[k] = w_cur[k] = w_step[k] = 0; w_j[k] = 0; inc[k] = 0; active[k] = false; first[k] = false; }
+    u64 steps = 0, done = 0;
     u64 src_acc = 0;  // contributions to the query source stay in a register: in Monte-Carlo 15 % of all walks stop on
                       // it, and same-address REDs serialise at ~0.7 ns each in L2
 
     for (;;) {
-        u32 needy = __ballot_sync(0xffffffffu, !active);
+        u32 needy[NW], idle = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) { needy[k] = __ballot_sync(0xffffffffu, !active[k]); idle += __popc(needy[k]); }
         // refill in batches: the bookkeeping below costs about as many instructions as a walk step, so wait until
-        // WALK_REFILL_MIN lanes are idle (or the warp has nothing left to do)
-        if (wnext < wh && (__popc(needy) >= WALK_REFILL_MIN || needy == 0xffffffffu)) {
-            mywin[lane] = A.ws_begin[scur + lane];
-            if (lane < 2) mywin[32 + lane] = A.ws_begin[scur + 32 + lane];
-            __syncwarp();
-            u32 rank = __popc(needy & lanemask_lt());
-            u64 idx = wnext + rank;
-            if (!active && idx < wh) {
-                int o = 0;
+        // WALK_REFILL_MIN slots per walk-in-flight are idle (or the warp has nothing left to do)
+        if (wnext < wh && (idle >= NW * WALK_REFILL_MIN || idle == 32 * NW)) {
 #pragma unroll
-                for (int s = 16; s > 0; s >>= 1) { int p = o + s; if (mywin[p] <= idx) o = p; }
-                u32 si = scur + o;
-                w.start = A.ws_v[si];
-                w.j = idx - mywin[o];
-                inc = A.ws_inc[si] + (w.j == 0 ? A.ws_rem[si] : 0);
-                w.cur = w.start;
-                w.restart = A.restart_at_source ? (u32)A.src : w.start;
-                w.step = 0;
-                w.first = A.no_zero_hop != 0;
-                active = true;
-            }
-            u64 take = min((u64)__popc(needy), wh - wnext);
-            wnext += take;
-            if (wnext < wh) {  // slide the window: source containing wnext (offset may be 32)
-                int o = 0;
+            for (int k = 0; k < NW; k++) {
+                if (wnext >= wh || needy[k] == 0) continue;  // warp-uniform
+                mywin[lane] = A.ws_begin[scur + lane];
+                if (lane < 2) mywin[32 + lane] = A.ws_begin[scur + 32 + lane];
+                __syncwarp();
+                u32 rank = __popc(needy[k] & lanemask_lt());
+                u64 idx = wnext + rank;
+                if (!active[k] && idx < wh) {
+                    int o = 0;
 #pragma unroll
-                for (int s = 32; s > 0; s >>= 1) { int p = o + s; if (p <= 32 && mywin[p] <= wnext) o = p; }
-                scur += (u32)o;
+                    for (int s = 16; s > 0; s >>= 1) { int p = o + s; if (mywin[p] <= idx) o = p; }
+                    u32 si = scur + o;
+                    w_start[k] = A.ws_v[si];
+                    w_j[k] = idx - mywin[o];
+                    inc[k] = A.ws_inc[si] + (w_j[k] == 0 ? A.ws_rem[si] : 0);
+                    w_cur[k] = w_start[k];
+                    w_step[k] = 0;
+                    first[k] = A.no_zero_hop != 0;
+                    active[k] = true;
+                }
+                u64 take = min((u64)__popc(needy[k]), wh - wnext);
+                wnext += take;
+                if (wnext < wh) {  // slide the window: source containing wnext (offset may be 32)
+                    int o = 0;
+#pragma unroll
+                    for (int s = 32; s > 0; s >>= 1) { int p = o + s; if (p <= 32 && mywin[p] <= wnext) o = p; }
+                    scur += (u32)o;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
-        if (!__any_sync(0xffffffffu, active)) break;
-        if (active) {
-            if (walk_step<HINT>(w, A.out_vtx, A.col_idx, A.k0, A.k1, A.tstop, steps, pol_keep, pol_stream)) {
-                if (w.cur == (u32)A.src) src_acc += inc;
-                else atomicAdd((ull*)&A.target[w.cur], (ull)inc);
-                active = false;
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < NW; k++) any |= active[k];
+        if (!__any_sync(0xffffffffu, any)) break;
+
+        // stage 1: draws and stop tests (J/Monte_Carlo.java:75-90; :110-112 for the unconditional first move)
+        u64 rnd[NW];
+        bool go[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            go[k] = false;
+            rnd[k] = 0;
+            if (active[k]) {
+                Philox4 x = philox4x32_10(w_start[k], (u32)w_j[k], (u32)(w_j[k] >> 32), w_step[k], A.k0, A.k1);
+                w_step[k]++;
+                u64 u53 = ((u64)x.x0 << 21) | (u64)(x.x1 >> 11);
+                go[k] = first[k] || u53 >= A.tstop;
+                first[k] = false;
+                rnd[k] = ((u64)x.x2 << 32) | (u64)x.x3;
+            }
+        }
+        // stage 2: vertex records of all moving walks
+        u64 pk[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            pk[k] = 0;
+            if (go[k]) pk[k] = HINT ? ld_hint_u64(&A.out_vtx[w_cur[k]], pol_keep) : __ldg(&A.out_vtx[w_cur[k]]);
+        }
+        // stage 3: neighbours (a dangling vertex sends the walk to its restart vertex without a neighbour draw)
+        u32 nb[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const u32 d = vtx_deg(pk[k]);
+            nb[k] = A.restart_at_source ? (u32)A.src : w_start[k];
+            if (go[k] && d) {
+                const i32* p = &A.col_idx[vtx_begin(pk[k]) + mulhi64(rnd[k], (u64)d)];
+                nb[k] = HINT ? ld_hint_u32(p, pol_stream) : (u32)__ldg(p);
+            }
+        }
+        // stage 4: moves and terminals
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            if (go[k]) { w_cur[k] = nb[k]; steps++; }
+            else if (active[k]) {
+                if (w_cur[k] == (u32)A.src) src_acc += inc[k];
+                else atomicAdd((ull*)&A.target[w_cur[k]], (ull)inc[k]);
+                active[k] = false;
                 done++;
             }
         }
