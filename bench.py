@@ -124,7 +124,7 @@ def measured_peak():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_push_query launch, from `ncu --set full` captures of
 # scripts/one_query.py at library defaults (profiles/r01_ncu_full_summary.txt); bytes per launch, keyed by R-MAT scale
-NCU_PUSH_TRAFFIC = {20: 0.320043e9 + 39.152896e6, 22: 6.574943e9 + 1.402604e9}
+NCU_PUSH_TRAFFIC = {20: 0.334086e9 + 48.295680e6, 22: 6.547190e9 + 1.555525e9}
 
 
 def cpu_port_query(O, og, src, eps, seed, walk_cost):
