@@ -47,7 +47,9 @@ typedef unsigned long long ull;
 #ifndef WALK_PER_LANE
 #define WALK_PER_LANE 2      // walks in flight per lane
 #endif
+#ifndef WALK_CTAS_PER_SM
 #define WALK_CTAS_PER_SM 4
+#endif
 #ifndef WALK_REFILL_MIN
 #define WALK_REFILL_MIN 12
 #endif

@@ -106,10 +106,25 @@ def gather_pairs(local, n, group=None):
             buf[:arr.shape[0]] = torch.from_numpy(np.ascontiguousarray(arr).view(np_dtype)).to(dev)
         out = torch.empty(world * length, dtype=t_dtype, device=dev)
         dist.all_gather_into_tensor(out, buf, group=group)
-        return out.cpu().numpy().reshape(world, length)
+        return out.view(world, length)
 
     P = gather(ptr, n + 1, np.int64, torch.int64)
     T = gather(tgt, mx, np.int32, torch.int32)
     V = gather(val, mx, np.int64, torch.int64)
-    parts = [(P[r], T[r, :cnts[r]], V[r, :cnts[r]].view(val.dtype)) for r in range(world)]
-    return merge_pairs(parts, n)
+    # merge on the device (same arithmetic as merge_pairs): row v of the result is the concatenation, in rank order,
+    # of row v of every part -- rank order = ascending target blocks, so rows stay sorted by target
+    cnt = P[:, 1:] - P[:, :-1]                                   # [world, n]
+    mptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(cnt.sum(0), 0, out=mptr[1:])
+    before = torch.cumsum(cnt, 0) - cnt                          # pairs of row v held by lower ranks
+    total = int(mptr[-1].item())
+    mt = torch.empty(total, dtype=torch.int32, device=dev)
+    mv = torch.empty(total, dtype=torch.int64, device=dev)
+    for r in range(world):
+        if cnts[r]:
+            shift = mptr[:-1] + before[r] - P[r, :-1]            # part position -> merged position, per row
+            dst = torch.repeat_interleave(shift, cnt[r], output_size=cnts[r])
+            dst += torch.arange(cnts[r], dtype=torch.int64, device=dev)
+            mt[dst] = T[r, :cnts[r]]
+            mv[dst] = V[r, :cnts[r]]
+    return mptr.cpu().numpy(), mt.cpu().numpy(), mv.cpu().numpy().view(val.dtype)
