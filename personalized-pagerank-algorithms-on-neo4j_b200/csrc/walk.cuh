@@ -3,7 +3,7 @@
 // Replaces Monte_Carlo.random_walk / random_walk_no_zero_hop (J/Monte_Carlo.java:60-133) and the walk
 // loops of J/Monte_Carlo.java:149-154, J/Fora_Whole_Graph.java:133-139, J/Fora_Topk.java:161-167.
 //
-// One walk per lane.  Randomness is counter based (Philox4x32-10, key = seed, counter = (start vertex,
+// WALK_PER_LANE walks in flight per lane.  Randomness is counter based (Philox4x32-10, key = seed, counter = (start vertex,
 // walk index, step)), so the terminal of walk (v, j) is a pure function of its arguments: the CPU
 // replay in oracle/ reproduces every terminal, and the result does not depend on how walks are split
 // over lanes, warps, launches or GPUs.  Contributions are integer (fixed-point increments or counts)
