@@ -38,6 +38,7 @@ extern "C" {
 #define PPR_E_RANGE (-4)   /* graph exceeds supported ranges (n < 2^31, degree < 2^24, m < 2^40) */
 #define PPR_E_CAPACITY (-5)/* caller buffer too small; required size reported through the count output */
 #define PPR_E_STATE (-6)   /* call sequence error (e.g. export before any query) */
+#define PPR_E_CALLBACK (-7)/* a caller-supplied hook (ppr_reduce_fn) reported failure */
 
 /* flags */
 #define PPR_RESTART_AT_WALK_START 0 /* default: reference behaviour, J/Monte_Carlo.java:87-90 */
@@ -209,6 +210,20 @@ int32_t ppr_fora_shard(ppr_graph* g, int32_t src, double alpha, double eps, uint
                        const ppr_conf* conf, int32_t shard, int32_t nshards, ppr_stats* stats);
 int32_t ppr_monte_carlo_shard(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed,
                               const ppr_conf* conf, int32_t shard, int32_t nshards, ppr_stats* stats);
+
+/* FORA top-k with the walks of every delta-round sharded (BASELINE configs[2]: "walks sharded 1/2/4/8 B200";
+ * the walk loop of J/Fora_Topk.java:161-167).  Every rank replays the deterministic incremental push, runs its
+ * slice of the round's walks into its estimate vector (shard 0's carries the push reserve, J/Fora_Topk.java:143),
+ * and then calls `reduce` ONCE PER ROUND: the hook must sum the n raw uint64 (2^-62 fixed point) values at device
+ * address dev_ptr element-wise over all shards, in place (two's-complement int64 sum: ncclInt64 / ncclSum), and
+ * return 0 when the sum is complete on the device (non-zero aborts the query with PPR_E_CALLBACK).  The library's
+ * stream is idle when the hook runs.  Selection and the stop test (J/Fora_Topk.java:173-178) then run on every
+ * rank on identical data, so all ranks take the same number of rounds and return the same ids and values --
+ * bit-identical to ppr_fora_topk.  reduce may be NULL only when nshards == 1. */
+typedef int32_t (*ppr_reduce_fn)(void* user, uint64_t dev_ptr, int64_t n);
+int32_t ppr_fora_topk_shard(ppr_graph* g, int32_t src, double alpha, double eps, int32_t k, uint64_t seed, int32_t flags,
+                            const ppr_conf* conf, int32_t shard, int32_t nshards, ppr_reduce_fn reduce, void* user,
+                            int32_t* ids_out, double* vals_out, int32_t cap, int32_t* count_out, ppr_stats* stats);
 /* Device pointer and length (elements) of the raw uint64 result vector of the last query on g. */
 int32_t ppr_result_devptr(ppr_graph* g, uint64_t* devptr_out, int64_t* n_out);
 /* Convert the raw result vector to doubles (after an external all-reduce if sharded).

@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libpprb200.so")
 
 PPR_OK = 0
-PPR_E_INVALID, PPR_E_CUDA, PPR_E_NOMEM, PPR_E_RANGE, PPR_E_CAPACITY, PPR_E_STATE = -1, -2, -3, -4, -5, -6
+PPR_E_INVALID, PPR_E_CUDA, PPR_E_NOMEM, PPR_E_RANGE, PPR_E_CAPACITY, PPR_E_STATE, PPR_E_CALLBACK = -1, -2, -3, -4, -5, -6, -7
 RESTART_AT_WALK_START = 0
 RESTART_AT_SOURCE = 1
 FX_ONE = 1 << 62
@@ -25,10 +25,14 @@ EXPORTS = [
     "ppr_host_free", "ppr_graph_create", "ppr_graph_destroy", "ppr_graph_node_count", "ppr_graph_rel_count",
     "ppr_graph_export_csc", "ppr_forward_push", "ppr_monte_carlo", "ppr_fora", "ppr_fora_topk", "ppr_topk",
     "ppr_power_iteration", "ppr_fora_batch", "ppr_backward_search", "ppr_backward_all_pairs", "ppr_pairs_count",
-    "ppr_pairs_export", "ppr_pairs_destroy", "ppr_fora_shard", "ppr_monte_carlo_shard", "ppr_result_devptr",
+    "ppr_pairs_export", "ppr_pairs_destroy", "ppr_fora_shard", "ppr_monte_carlo_shard", "ppr_fora_topk_shard", "ppr_result_devptr",
     "ppr_result_export", "ppr_last_raw", "ppr_push_trace_begin", "ppr_push_trace_step", "ppr_walk_terminals", "ppr_debug_timeline",
     "ppr_rmat_generate", "ppr_version",
 ]
+
+
+# ppr_reduce_fn: int32 (*)(void* user, uint64 dev_ptr, int64 n)
+REDUCE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_uint64, C.c_int64)
 
 
 class Stats(C.Structure):
@@ -116,6 +120,7 @@ def load():
         "ppr_pairs_destroy": (i32, [vp]),
         "ppr_fora_shard": (i32, [vp, i32, f64, f64, u64, i32, vp, i32, i32, SP]),
         "ppr_monte_carlo_shard": (i32, [vp, i32, f64, f64, u64, vp, i32, i32, SP]),
+        "ppr_fora_topk_shard": (i32, [vp, i32, f64, f64, i32, u64, i32, vp, i32, i32, REDUCE_FN, vp, vp, vp, i32, C.POINTER(i32), SP]),
         "ppr_result_devptr": (i32, [vp, C.POINTER(u64), C.POINTER(i64)]),
         "ppr_result_export": (i32, [vp, f64, vp]),
         "ppr_last_raw": (i32, [vp, vp, vp]),
@@ -298,6 +303,29 @@ class Graph:
         ids, vals = np.zeros(cap, np.int32), np.zeros(cap)
         cnt, st = C.c_int32(), Stats()
         self.ctx.check(self.L.ppr_fora_topk(self.h, src, alpha, eps, k, seed, flags, _conf(conf), _ptr(ids), _ptr(vals), cap, C.byref(cnt), C.byref(st)))
+        return ids[:cnt.value].copy(), vals[:cnt.value].copy(), st.as_dict()
+
+    def fora_topk_shard(self, src, alpha, eps, k, seed, shard, nshards, reduce=None, flags=0, conf=None):
+        """ppr_fora_topk_shard; `reduce(dev_ptr, n)` sums the round's raw estimate vector over the shards in place."""
+        cap = self.n
+        ids, vals = np.zeros(cap, np.int32), np.zeros(cap)
+        cnt, st = C.c_int32(), Stats()
+        failure = []
+
+        def hook(_user, dev_ptr, n):
+            try:
+                reduce(int(dev_ptr), int(n))
+                return 0
+            except BaseException as e:   # never let an exception cross the C frame
+                failure.append(e)
+                return 1
+
+        cb = REDUCE_FN(hook) if reduce is not None else C.cast(None, REDUCE_FN)
+        rc = self.L.ppr_fora_topk_shard(self.h, src, alpha, eps, k, seed, flags, _conf(conf), shard, nshards, cb, None,
+                                        _ptr(ids), _ptr(vals), cap, C.byref(cnt), C.byref(st))
+        if failure:
+            raise failure[0]
+        self.ctx.check(rc)
         return ids[:cnt.value].copy(), vals[:cnt.value].copy(), st.as_dict()
 
     def power_iteration(self, src, alpha, iters=100):

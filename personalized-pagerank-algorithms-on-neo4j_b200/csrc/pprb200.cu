@@ -814,12 +814,14 @@ static int32_t fetch_survivors(ppr_graph* g, Workspace& w, std::vector<i32>& ids
     return PPR_OK;
 }
 
-extern "C" int32_t ppr_fora_topk(ppr_graph* g, int32_t src, double alpha, double eps, int32_t k, uint64_t seed, int32_t flags,
-                                 const ppr_conf* conf, int32_t* ids_out, double* vals_out, int32_t cap, int32_t* count_out, ppr_stats* stats) {
-    int32_t rc = check_fora(g, src, alpha, eps, 0, 1, "ppr_fora_topk");
+static int32_t fora_topk_impl(ppr_graph* g, int32_t src, double alpha, double eps, int32_t k, uint64_t seed, int32_t flags,
+                             const ppr_conf* conf, int32_t shard, int32_t nshards, ppr_reduce_fn reduce, void* user,
+                             int32_t* ids_out, double* vals_out, int32_t cap, int32_t* count_out, ppr_stats* stats) {
+    int32_t rc = check_fora(g, src, alpha, eps, shard, nshards, "ppr_fora_topk");
     if (rc) return rc;
     ppr_ctx* ctx = g->ctx;
     if (k < 1 || !count_out || cap < 0 || (cap > 0 && (!ids_out || !vals_out))) return ctx_fail(ctx, PPR_E_INVALID, "ppr_fora_topk: bad k / buffers");
+    if (nshards > 1 && !reduce) return ctx_fail(ctx, PPR_E_INVALID, "ppr_fora_topk_shard: nshards > 1 needs a reduce hook");
     cudaSetDevice(ctx->device);
     Workspace& w = g->ws[0];
     g->trace_active = false;
@@ -847,11 +849,17 @@ extern "C" int32_t ppr_fora_topk(ppr_graph* g, int32_t src, double alpha, double
         fill_push_args(A, g, w);
         A.src = src; A.alpha_q64 = h_alpha_q64(alpha); A.alpha = alpha; A.omega = omega_local; A.rmax0 = rmax_local;
         A.max_rounds = 1; A.mode = PMODE_TOPK; A.init = round == 0;
+        A.prep_adds_push_part = shard == 0;   // only shard 0's estimate starts from the push reserve
         CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
         CUDA_TRY(launch_push(ctx, w, A));
         CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
-        CUDA_TRY(launch_walk(ctx, g, w, w.est, seed, (u64)round, alpha, src, (flags & PPR_RESTART_AT_SOURCE) ? 1 : 0, 0, 0, 1));
+        CUDA_TRY(launch_walk(ctx, g, w, w.est, seed, (u64)round, alpha, src, (flags & PPR_RESTART_AT_SOURCE) ? 1 : 0, 0, (u64)shard, (u64)nshards));
         CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+        if (nshards > 1) {  // sum the round's estimates over the shards (caller's collective) before selecting
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (reduce(user, (uint64_t)(uintptr_t)w.est, n) != 0) return ctx_fail(ctx, PPR_E_CALLBACK, "ppr_fora_topk_shard: the reduce hook failed");
+            CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));   // the collective is not counted as select time
+        }
         rc = run_select(g, w, w.est, n, k); if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
         rc = read_ctl(g, w); if (rc) return rc;
@@ -882,6 +890,17 @@ extern "C" int32_t ppr_fora_topk(ppr_graph* g, int32_t src, double alpha, double
     if ((i64)ids.size() > cap) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_fora_topk: output buffers too small");
     for (size_t i = 0; i < ids.size(); i++) { ids_out[i] = ids[i]; vals_out[i] = (double)vals[i] * FX_INV; }
     return PPR_OK;
+}
+
+extern "C" int32_t ppr_fora_topk(ppr_graph* g, int32_t src, double alpha, double eps, int32_t k, uint64_t seed, int32_t flags,
+                                 const ppr_conf* conf, int32_t* ids_out, double* vals_out, int32_t cap, int32_t* count_out, ppr_stats* stats) {
+    return fora_topk_impl(g, src, alpha, eps, k, seed, flags, conf, 0, 1, nullptr, nullptr, ids_out, vals_out, cap, count_out, stats);
+}
+
+extern "C" int32_t ppr_fora_topk_shard(ppr_graph* g, int32_t src, double alpha, double eps, int32_t k, uint64_t seed, int32_t flags,
+                                       const ppr_conf* conf, int32_t shard, int32_t nshards, ppr_reduce_fn reduce, void* user,
+                                       int32_t* ids_out, double* vals_out, int32_t cap, int32_t* count_out, ppr_stats* stats) {
+    return fora_topk_impl(g, src, alpha, eps, k, seed, flags, conf, shard, nshards, reduce, user, ids_out, vals_out, cap, count_out, stats);
 }
 
 extern "C" int32_t ppr_topk(ppr_ctx* ctx, const double* vec, int64_t n, int32_t k, int32_t* ids_out, double* vals_out,

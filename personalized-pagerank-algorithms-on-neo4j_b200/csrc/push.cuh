@@ -580,7 +580,7 @@ __device__ void walk_prep(const PushArgs& A, cg::grid_group& grid, u64* sm) {
         u64 has = 0, w = 0, y = 0;
         if (v < v_hi) {
             u64 x = A.r[v];
-            u64 base = A.reserve[v];
+            u64 base = (TOPK && !A.prep_adds_push_part) ? 0ull : A.reserve[v];  // top-k shards > 0 hold walk contributions only
             if (x) {
                 u64 a = TOPK ? 0 : mulhi64(x, A.alpha_q64);
                 y = x - a;

@@ -53,6 +53,27 @@ def fora_sharded(graph, src, alpha, eps, seed, rank, world, flags=0, out=None, g
     return graph.result_export(0.0, out), st
 
 
+def _sum_over_ranks(device, ptr, n, group=None):
+    """In-place element-wise sum over ranks of n raw uint64 values at device address `ptr` (int64 bit pattern)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.as_tensor(_DevVec(ptr, n), device="cuda:%d" % device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    else:                                   # gloo (tests: several ranks sharing one GPU): stage through the host
+        h = t.cpu()
+        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+        t.copy_(h)
+    torch.cuda.synchronize(device)
+
+
+def fora_topk_sharded(graph, src, alpha, eps, k, seed, rank, world, flags=0, conf=None, group=None):
+    """FORA top-k with every round's walks sharded over `world` GPUs (ppr_fora_topk_shard); one integer all-reduce
+    of the estimate vector per delta-round.  Every rank returns the same (ids, values, stats)."""
+    reduce = (lambda ptr, n: _sum_over_ranks(graph.ctx.device, ptr, n, group)) if world > 1 else None
+    return graph.fora_topk_shard(src, alpha, eps, k, seed, rank, world, reduce, flags, conf)
+
+
 def monte_carlo_sharded(graph, src, alpha, eps, seed, rank, world, out=None, group=None):
     st = graph.monte_carlo_shard(src, alpha, eps, seed, rank, world)
     if world > 1:

@@ -48,19 +48,24 @@ if a.what == "topk":
     rp, ci = pkg.rmat(n, m, seed=42)
     g = pkg.Graph(ctx, rp, ci)
     S = srcs_of(rp, a.queries + 2)
+    def topk(s, seed):     # N > 1: every round's walks sharded over the ranks, one NCCL all-reduce per delta-round
+        if world > 1:
+            return pkg.dist.fora_topk_sharded(g, s, ALPHA, 0.5, k, seed, rank, world)
+        return g.fora_topk(s, ALPHA, 0.5, k, seed)
+
     for s in S[:2]:
-        g.fora_topk(s, ALPHA, 0.5, k, 1)
+        topk(s, 1)
     sync(); t0 = time.perf_counter()
     agg = {"ms_push": 0.0, "ms_walk": 0.0, "ms_select": 0.0, "rounds": 0, "walks": 0, "edges": 0}
     sizes = []
     for i, s in enumerate(S[2:]):
-        ids, vals, st = g.fora_topk(s, ALPHA, 0.5, k, 100 + i)
+        ids, vals, st = topk(s, 100 + i)
         sizes.append(len(ids))
         assert (np.diff(vals) <= 0).all() and len(ids) >= min(k, 1)
         for kk in agg:
             agg[kk] += st[kk]
     sync(); el = time.perf_counter() - t0
-    out.update(workload="LJ-shape R-MAT n=4.8M m=69M, FORA top-k=500, eps 0.5", queries=a.queries, queries_per_s=a.queries / el,
+    out.update(workload="LJ-shape R-MAT n=4.8M m=69M, FORA top-k=500, eps 0.5" + (", walks sharded over %d GPUs (walks = this rank's share)" % world if world > 1 else ""), queries=a.queries, queries_per_s=a.queries / el,
                ms_per_query=el / a.queries * 1e3, returned=float(np.mean(sizes)), **{kk: v / a.queries for kk, v in agg.items()})
     if a.cpu and rank == 0:
         from oracle import oracle as O

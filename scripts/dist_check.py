@@ -41,6 +41,16 @@ for name, (rp, ci) in (("GOT", pkg.graphio.load_got()[:2]), ("rmat14", pkg.rmat(
         ok = ok and good
         if rank == 0:
             print("%s src %d: sharded FORA + MC over %d GPUs bit-exact: %s (walks on rank0 %d of %d)" % (name, s, world, good, st["walks"], st["walks_total"]), flush=True)
+    for s in srcs:      # FORA top-k: every round's walks sharded, one NCCL all-reduce per delta-round
+        s = int(s)
+        ids, vals, st = pkg.dist.fora_topk_sharded(g, s, ALPHA, EPS, 10, 7, rank, world)
+        raw = g.last_raw(False)[0]
+        ref, rst = O.b_fora_topk(og, s, ALPHA, EPS, 10, 7)
+        rids = O.topk_select(ref, 10)
+        good = bool(np.array_equal(raw, ref)) and set(ids.tolist()) == set(rids.tolist()) and st["rounds"] == rst["rounds"]
+        ok = ok and good
+        if rank == 0:
+            print("%s src %d: sharded FORA top-10 over %d GPUs bit-exact: %s (%d rounds, %d ids)" % (name, s, world, good, st["rounds"], len(ids)), flush=True)
     lo, hi = pkg.dist.target_blocks(og.n, world)[rank]
     local_pairs = g.backward_all_pairs(ALPHA, 1e-3, -1, lo, hi, raw=True)[:3]
     ptr, tgt, val = pkg.dist.gather_pairs(local_pairs, og.n)

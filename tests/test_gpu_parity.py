@@ -288,6 +288,70 @@ def test_fora_walk_shards(G, OG, R12, O):
             assert np.array_equal(acc, full)
 
 
+def test_fora_topk_walk_shards(pkg, ctx, got, rmat12, O):
+    # ppr_fora_topk_shard: every delta-round's walks split over shards, one integer sum per round through the caller's
+    # reduce hook.  The shards run as threads here (one context + graph each, all on this GPU) and the hook sums the
+    # estimate vectors through the host; ids, values, rounds and the raw estimate vector must equal the unsharded run.
+    import threading
+    import torch
+    for (rp, ci), srcs, k in ((got[:2], (0, 63), K), (rmat12, sources(O.OGraph(*rmat12), 2), 50)):
+        og = O.OGraph(rp, ci)
+        g0 = pkg.Graph(ctx, rp, ci)
+        for s in srcs:
+            ids0, vals0, st0 = g0.fora_topk(s, ALPHA, EPS, k, SEED)
+            raw0 = g0.last_raw(False)[0].copy()
+            assert np.array_equal(raw0, O.b_fora_topk(og, s, ALPHA, EPS, k, SEED)[0])
+            ids1, vals1, st1 = g0.fora_topk_shard(s, ALPHA, EPS, k, SEED, 0, 1)
+            assert np.array_equal(ids0, ids1) and np.array_equal(vals0, vals1) and st0["rounds"] == st1["rounds"]
+            for world in (2, 3):
+                ctxs = [pkg.Context(0) for _ in range(world)]
+                graphs = [pkg.Graph(c, rp, ci) for c in ctxs]
+                bar = threading.Barrier(world)
+                parts, out, calls = [None] * world, [None] * world, [0] * world
+
+                def run(r):
+                    def hook(ptr, n):
+                        t = torch.as_tensor(pkg.dist._DevVec(ptr, n), device="cuda:0")
+                        parts[r] = t.cpu()
+                        bar.wait(60)
+                        total = parts[0].clone()
+                        for p_ in parts[1:]:
+                            total += p_
+                        bar.wait(60)
+                        t.copy_(total)
+                        torch.cuda.synchronize()
+                        calls[r] += 1
+                    try:
+                        out[r] = graphs[r].fora_topk_shard(s, ALPHA, EPS, k, SEED, r, world, hook)
+                    except BaseException as e:
+                        out[r] = e
+                        bar.abort()
+
+                th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+                for t_ in th:
+                    t_.start()
+                for t_ in th:
+                    t_.join(120)
+                for r in range(world):
+                    assert not isinstance(out[r], BaseException), out[r]
+                    ids, vals, st = out[r]
+                    assert np.array_equal(ids, ids0) and np.array_equal(vals, vals0), (world, r, s)
+                    assert st["rounds"] == st0["rounds"] == calls[r]
+                    assert np.array_equal(graphs[r].last_raw(False)[0], raw0)
+                assert sum(o[2]["walks"] for o in out) == st0["walks"]
+                for g_ in graphs:
+                    g_.close()
+                for c in ctxs:
+                    c.close()
+        g0.close()
+    with pytest.raises(pkg.PPRError):      # more than one shard needs the hook
+        G_ = pkg.Graph(ctx, *got[:2])
+        try:
+            G_.fora_topk_shard(0, ALPHA, EPS, K, SEED, 0, 2, None)
+        finally:
+            G_.close()
+
+
 def test_fora_batch_equals_single(R12, O):
     g, og = R12
     srcs = sources(og, 5)
