@@ -11,6 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+ORC_REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)   # int (*)(void* user, uint64* est, int64 n)
 _LIB = None
 
 FX_ONE = 1 << 62
@@ -66,6 +67,7 @@ def lib():
         L.orc_b_monte_carlo.restype = C.c_int64
         L.orc_b_fora.argtypes = G + [C.c_int32, C.c_double, C.c_double, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int64, C.c_int64, _u64p, _i64p]
         L.orc_b_fora_topk.argtypes = G + [C.c_int32, C.c_double, C.c_double, C.c_int64, C.c_uint64, C.c_int, _u64p, _i64p]
+        L.orc_b_fora_topk_shard.argtypes = G + [C.c_int32, C.c_double, C.c_double, C.c_int64, C.c_uint64, C.c_int, C.c_int64, C.c_int64, ORC_REDUCE_FN, C.c_void_p, _u64p, _i64p]
         L.orc_b_backward_search.argtypes = G + [C.c_int32, C.c_double, C.c_double, _u64p, _u64p, _i64p]
         L.orc_b_base_all_pairs.argtypes = G + [C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _i64p]
         L.orc_b_base_all_pairs.restype = C.c_int64
@@ -213,9 +215,20 @@ def b_fora(g, s, alpha, eps, seed, walk_cost=6.0, max_rounds=64, restart_at_sour
     return out, dict(zip(_B_STATS, map(int, st)))
 
 
-def b_fora_topk(g, s, alpha, eps, k, seed, restart_at_source=False):
+def b_fora_topk(g, s, alpha, eps, k, seed, restart_at_source=False, shard=0, nshards=1, reduce=None):
+    """FORA top-k estimate vector (fixed point).  Sharded form: `reduce(est)` must sum the uint64 numpy vector `est`
+    over the shards IN PLACE; it is called once per delta-round (the spec of ppr_fora_topk_shard)."""
     out, st = np.zeros(g.n, np.uint64), np.zeros(9, np.int64)
-    lib().orc_b_fora_topk(*g.args(), s, alpha, eps, k, seed, int(restart_at_source), out, st)
+    if nshards == 1 and reduce is None:
+        lib().orc_b_fora_topk(*g.args(), s, alpha, eps, k, seed, int(restart_at_source), out, st)
+        return out, dict(zip(_B_STATS, map(int, st)))
+
+    def hook(_user, ptr, n):
+        reduce(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(n,)))
+        return 0
+
+    cb = ORC_REDUCE_FN(hook)
+    lib().orc_b_fora_topk_shard(*g.args(), s, alpha, eps, k, seed, int(restart_at_source), shard, nshards, cb, None, out, st)
     return out, dict(zip(_B_STATS, map(int, st)))
 
 

@@ -635,8 +635,13 @@ void b_fora(const Graph& g, i32 s, double alpha, double eps, u64 seed, double wa
 // FORA top-k in fixed point (J/Fora_Topk.java:102-184).  The push of each round is the synchronous
 // push to convergence at that round's rmax (equivalent frontier set to the Java's Q/Q_next bookkeeping
 // whenever rmax >= min_rmax).
+// Sharded form (ppr_fora_topk_shard): this shard runs the walks whose global index (sources in ascending id, then
+// walk number) lies in [W*shard/nshards, W*(shard+1)/nshards); only shard 0's estimate starts from the push
+// reserve; `reduce` sums the estimate vector over the shards once per round, after which every shard selects and
+// decides on identical data.
+typedef int (*orc_reduce_fn)(void* user, u64* est, i64 n);
 void b_fora_topk(const Graph& g, i32 s, double alpha, double eps_in, i64 k, u64 seed, bool restart_at_source,
-                 u64* est_out, BForaStats* fs) {
+                 u64* est_out, BForaStats* fs, i64 shard = 0, i64 nshards = 1, orc_reduce_fn reduce = nullptr, void* user = nullptr) {
     i64 n = g.n;
     Conf c = conf_topk(n, k);
     double epsilon = eps_in * 0.5;
@@ -647,8 +652,10 @@ void b_fora_topk(const Graph& g, i32 s, double alpha, double eps_in, i64 k, u64 
     std::vector<u64> est(n, 0);
     BForaStats st; memset(&st, 0, sizeof st);
     int round = 0;
-    if (g.deg(s) == 0) { est[s] = FX_ONE; }
-    else {
+    if (g.deg(s) == 0) {
+        if (shard == 0) est[s] = FX_ONE;
+        if (nshards > 1 && reduce) reduce(user, est.data(), n);
+    } else {
         S.r[s] = FX_ONE;
         while (delta_local >= c.min_delta) {
             double rmax_local = epsilon * std::sqrt(delta_local / 3.0 / (double)g.m / L);
@@ -661,23 +668,38 @@ void b_fora_topk(const Graph& g, i32 s, double alpha, double eps_in, i64 k, u64 
             double rsum_local = (double)rsum_fx * FX_INV;
             double rsum_random_walk = rsum_local * (1.0 - alpha);
             i64 N = (i64)(omega_local * rsum_random_walk);
-            est = S.reserve;
+            if (shard == 0) est = S.reserve; else std::fill(est.begin(), est.end(), 0);
             u64 key = walk_key(seed, (u64)round);
+            // first pass: walk counts per source and their total (the shard boundaries are fractions of it)
+            std::vector<i64> wv(n, 0);
+            i64 W = 0;
             for (i64 v = 0; v < n; v++) {
                 u64 x = S.r[v];
                 if (x == 0 || N <= 0) continue;
                 double xd = (double)x * FX_INV;
                 i64 w = (i64)std::ceil(xd * (double)N);
                 if (w <= 0) continue;
-                if (g.deg(v) == 0) { est[v] += x; continue; }
+                if (g.deg(v) == 0) { if (shard == 0) est[v] += x; continue; }
+                wv[v] = w; W += w;
+            }
+            i64 lo = (i64)(((__int128)W * shard) / nshards), hi = (i64)(((__int128)W * (shard + 1)) / nshards);
+            i64 base = 0;
+            for (i64 v = 0; v < n; v++) {
+                i64 w = wv[v];
+                if (w == 0) continue;
+                u64 x = S.r[v];
                 u64 inc = x / (u64)w, rem = x - inc * (u64)w;
                 i32 restart = restart_at_source ? s : (i32)v;
-                for (i64 j = 0; j < w; j++) {
+                i64 j0 = std::max<i64>(0, lo - base), j1 = std::min<i64>(w, hi - base);
+                for (i64 j = j0; j < j1; j++) {
                     i32 t = walk(g, (i32)v, restart, (u64)j, key, tstop, false, &st.steps);
                     est[t] += inc + (j == 0 ? rem : 0);
                 }
-                st.walks += w; st.walk_sources++;
+                if (j1 > j0) st.walks += j1 - j0;
+                st.walk_sources++;
+                base += w;
             }
+            if (nshards > 1 && reduce) reduce(user, est.data(), n);
             round++;
             std::vector<u64> vals;
             for (i64 v = 0; v < n; v++) if (est[v] > 0) vals.push_back(est[v]);
@@ -957,6 +979,14 @@ void orc_b_fora_topk(i64 n, i64 m, const i64* rp, const i32* ci, i32 s, double a
     Graph g(n, m, rp, ci);
     BForaStats fs;
     b_fora_topk(g, s, alpha, eps, k, seed, restart_at_source != 0, est, &fs);
+    if (stats) { stats[0] = fs.pushes; stats[1] = fs.edges; stats[2] = fs.iters; stats[3] = fs.rounds; stats[4] = fs.walks;
+                 stats[5] = fs.steps; stats[6] = fs.walk_sources; stats[7] = (i64)fs.rmax_fx_final; stats[8] = (i64)fs.rsum_fx; }
+}
+void orc_b_fora_topk_shard(i64 n, i64 m, const i64* rp, const i32* ci, i32 s, double alpha, double eps, i64 k, u64 seed,
+                           int restart_at_source, i64 shard, i64 nshards, orc_reduce_fn reduce, void* user, u64* est, i64* stats) {
+    Graph g(n, m, rp, ci);
+    BForaStats fs;
+    b_fora_topk(g, s, alpha, eps, k, seed, restart_at_source != 0, est, &fs, shard, nshards, reduce, user);
     if (stats) { stats[0] = fs.pushes; stats[1] = fs.edges; stats[2] = fs.iters; stats[3] = fs.rounds; stats[4] = fs.walks;
                  stats[5] = fs.steps; stats[6] = fs.walk_sources; stats[7] = (i64)fs.rmax_fx_final; stats[8] = (i64)fs.rsum_fx; }
 }

@@ -93,6 +93,14 @@ def _gloo_worker(rank, world, port, q):
     ptr, tgt, val = pkg.dist.gather_pairs(local, g.n)
     rptr, rtgt, rval, _ = O.b_base_all_pairs(g, 0.15, 1e-3)
     ok2 = np.array_equal(ptr, rptr) and np.array_equal(tgt, rtgt) and np.array_equal(val, rval)
+    # FORA top-k with every round's walks sharded: one sum of the estimate vector per round, all ranks agree
+    def reduce(est):
+        t = torch.from_numpy(est.view(np.int64))       # shares memory with the oracle's vector
+        dist.all_reduce(t)
+    est, st = O.b_fora_topk(g, 63, 0.15, 0.5, 10, 7, shard=rank, nshards=world, reduce=reduce)
+    ref, rst = O.b_fora_topk(g, 63, 0.15, 0.5, 10, 7)
+    ok3 = bool(np.array_equal(est, ref)) and st["rounds"] == rst["rounds"] and st["walks"] < rst["walks"]
+    ok2 = ok2 and ok3
     q.put((rank, ok1, ok2))
     dist.destroy_process_group()
 
