@@ -16,6 +16,9 @@
 #include <thread>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "backward.cuh"
 #include "common.cuh"
 #include "push.cuh"
@@ -45,6 +48,46 @@ __global__ void k_build_vtx(const i64* __restrict__ ptr, u64* __restrict__ vtx, 
         vtx[v] = ((u64)b << VTX_DEG_BITS) | d;
         if (deg) deg[v] = (u32)d;
         if (invdeg) invdeg[v] = d ? ~0ull / d : 0ull;
+    }
+}
+
+// CSC build on the device (the reference gets `incoming[][]` from HeavyGraph, J/PPR.java:136-152): in-degree histogram,
+// exclusive scan, then a STABLE sort of the edges by target -- the CSR is ordered by source, so sources ascend inside
+// every column, the canonical order of graphio/oracle.  The sort and the scan are CUB calls (one-time export, not a query
+// kernel); everything else is below.
+__global__ void k_indeg(const i32* __restrict__ col_idx, i64 m, i64 n, ull* __restrict__ indeg, u32* __restrict__ err) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    for (i64 e = gtid; e < m; e += gsize) {
+        i32 c = col_idx[e];
+        if (c < 0 || (i64)c >= n) *err = 1u;
+        else atomicAdd(&indeg[c], 1ull);
+    }
+}
+__global__ void k_check_indeg(const ull* __restrict__ indeg, i64 n, u32* __restrict__ err) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    for (i64 v = gtid; v < n; v += gsize) if (indeg[v] > (ull)VTX_MAX_DEG) *err = 2u;
+}
+// source vertex of every edge: one warp per row, coalesced stores
+__global__ void k_edge_src(const u64* __restrict__ out_vtx, i64 n, i32* __restrict__ src) {
+    const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((i64)gridDim.x * blockDim.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
+    for (i64 v = gw; v < n; v += nw) {
+        const u64 pk = out_vtx[v];
+        const u64 b = vtx_begin(pk), d = vtx_deg(pk);
+        for (u64 e = lane; e < d; e += 32) src[b + e] = (i32)v;
+    }
+}
+__global__ void k_set_slots(const u32* __restrict__ hot_id, u32 n_hot, i32* __restrict__ slot_of) {
+    u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_hot) slot_of[hot_id[s]] = (i32)s;
+}
+// push_idx = col_idx with hub targets replaced by HOT_BIT | slot (read by the push kernels only)
+__global__ void k_encode_push_idx(const i32* __restrict__ col_idx, const i32* __restrict__ slot_of, i64 m, u32* __restrict__ push_idx) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    for (i64 e = gtid; e < m; e += gsize) {
+        i32 c = col_idx[e];
+        i32 sl = slot_of[c];
+        push_idx[e] = sl >= 0 ? (HOT_BIT | (u32)sl) : (u32)c;
     }
 }
 
@@ -314,41 +357,6 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
         if (d > VTX_MAX_DEG) return ctx_fail(ctx, PPR_E_RANGE, "ppr_graph_create: out-degree >= 2^24");
         if (d > PUSH_SMALL_MAX) chunk_cap += (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
     }
-    // CSC on the host: stable counting sort, sources ascend inside a column
-    std::vector<i64> cp;
-    std::vector<i32> ri;
-    try { cp.assign((size_t)n + 1, 0); ri.resize((size_t)m); } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed"); }
-    for (i64 e = 0; e < m; e++) {
-        i32 c = col_idx[e];
-        if (c < 0 || c >= n) return ctx_fail(ctx, PPR_E_INVALID, "ppr_graph_create: col_idx out of range");
-        cp[(size_t)c + 1]++;
-    }
-    for (i64 v = 0; v < n; v++) {
-        if (cp[v + 1] > VTX_MAX_DEG) return ctx_fail(ctx, PPR_E_RANGE, "ppr_graph_create: in-degree >= 2^24");
-        cp[v + 1] += cp[v];
-    }
-    {
-        std::vector<i64> pos(cp.begin(), cp.end() - 1);
-        for (i64 v = 0; v < n; v++)
-            for (i64 e = row_ptr[v]; e < row_ptr[v + 1]; e++) ri[(size_t)pos[col_idx[e]]++] = (i32)v;
-    }
-
-    // hub set: the (up to) HOT_SLOTS vertices of highest in-degree, at least hot_min_indeg in-edges each;
-    // push_idx = col_idx with those targets replaced by HOT_BIT | slot (read by the push kernels only)
-    std::vector<u32> hot_id;
-    std::vector<u32> push_idx;
-    try {
-        std::vector<std::pair<i64, i32>> cand;
-        const i64 min_in = std::max<i64>(1, ctx->hot_min_indeg);
-        for (i64 v = 0; v < n; v++) { i64 d = cp[v + 1] - cp[v]; if (d >= min_in) cand.push_back(std::make_pair(-d, (i32)v)); }
-        size_t keep = std::min<size_t>(cand.size(), HOT_SLOTS);
-        std::partial_sort(cand.begin(), cand.begin() + keep, cand.end());
-        std::vector<i32> slot_of((size_t)n, -1);
-        for (size_t s = 0; s < keep; s++) { hot_id.push_back((u32)cand[s].second); slot_of[(size_t)cand[s].second] = (i32)s; }
-        push_idx.resize((size_t)m);
-        for (i64 e = 0; e < m; e++) { i32 sl = slot_of[(size_t)col_idx[e]]; push_idx[(size_t)e] = sl >= 0 ? (HOT_BIT | (u32)sl) : (u32)col_idx[e]; }
-    } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed"); }
-
     cudaSetDevice(ctx->device);
     ppr_graph* g = new (std::nothrow) ppr_graph();
     GraphExtra* x = new (std::nothrow) GraphExtra();
@@ -366,22 +374,77 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     G_TRY(dalloc(&g->d.in_vtx, (size_t)n)); G_TRY(dalloc(&g->d.col_idx, (size_t)m)); G_TRY(dalloc(&g->d.row_idx, (size_t)m));
     G_TRY(dalloc(&d_ptr, (size_t)n + 1));
     G_TRY(dalloc(&g->d.push_idx, (size_t)m)); G_TRY(dalloc(&g->d.hot_id, (size_t)HOT_SLOTS));
-    g->d.n_hot = (u32)hot_id.size();
     int blocks = ctx->sm_count * 8;
     G_TRY(cudaMemcpyAsync(d_ptr, row_ptr, ((size_t)n + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
     k_build_vtx<<<blocks, 256, 0, ctx->stream>>>(d_ptr, g->d.out_vtx, g->d.out_deg, g->d.invdeg, n);
     G_TRY(cudaGetLastError());
-    G_TRY(cudaStreamSynchronize(ctx->stream));
-    G_TRY(cudaMemcpyAsync(d_ptr, cp.data(), ((size_t)n + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
-    k_build_vtx<<<blocks, 256, 0, ctx->stream>>>(d_ptr, g->d.in_vtx, nullptr, nullptr, n);
-    G_TRY(cudaGetLastError());
-    if (m > 0) {
-        G_TRY(cudaMemcpyAsync(g->d.col_idx, col_idx, (size_t)m * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
-        G_TRY(cudaMemcpyAsync(g->d.row_idx, ri.data(), (size_t)m * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
-        G_TRY(cudaMemcpyAsync(g->d.push_idx, push_idx.data(), (size_t)m * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    if (m > 0) G_TRY(cudaMemcpyAsync(g->d.col_idx, col_idx, (size_t)m * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
+
+    // CSC on the device: histogram -> scan -> stable sort by target (temporaries freed at the end of this block)
+    ull* d_indeg = nullptr; u32* d_err = nullptr; i32* d_src = nullptr; u32* d_keys = nullptr; void* d_tmp = nullptr; i32* d_slot = nullptr;
+    auto free_tmp = [&]() { cudaFree(d_indeg); cudaFree(d_err); cudaFree(d_src); cudaFree(d_keys); cudaFree(d_tmp); cudaFree(d_slot);
+                            d_indeg = nullptr; d_err = nullptr; d_src = nullptr; d_keys = nullptr; d_tmp = nullptr; d_slot = nullptr; };
+#define B_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { free_tmp(); return fail(ctx_fail_cuda(ctx, e__, #expr, __FILE__, __LINE__)); } } while (0)
+    B_TRY(dalloc(&d_indeg, (size_t)n + 1)); B_TRY(dalloc(&d_err, 1));
+    B_TRY(cudaMemsetAsync(d_indeg, 0, ((size_t)n + 1) * sizeof(ull), ctx->stream));
+    B_TRY(cudaMemsetAsync(d_err, 0, sizeof(u32), ctx->stream));
+    if (m > 0) { k_indeg<<<blocks, 256, 0, ctx->stream>>>(g->d.col_idx, m, n, d_indeg, d_err); B_TRY(cudaGetLastError()); }
+    k_check_indeg<<<blocks, 256, 0, ctx->stream>>>(d_indeg, n, d_err);
+    B_TRY(cudaGetLastError());
+    u32 h_err = 0;
+    std::vector<ull> h_indeg;
+    try { h_indeg.resize((size_t)n); } catch (...) { free_tmp(); return fail(ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed")); }
+    B_TRY(cudaMemcpyAsync(&h_err, d_err, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    B_TRY(cudaMemcpyAsync(h_indeg.data(), d_indeg, (size_t)n * sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
+    B_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_err == 1u) { free_tmp(); return fail(ctx_fail(ctx, PPR_E_INVALID, "ppr_graph_create: col_idx out of range")); }
+    if (h_err == 2u) { free_tmp(); return fail(ctx_fail(ctx, PPR_E_RANGE, "ppr_graph_create: in-degree >= 2^24")); }
+    {   // column pointers: exclusive scan of the n + 1 counts (the last one is 0, so entry n receives m)
+        size_t tb = 0;
+        B_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_indeg, reinterpret_cast<ull*>(d_ptr), n + 1, ctx->stream));
+        B_TRY(cudaMalloc(&d_tmp, std::max<size_t>(tb, 16)));
+        B_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_indeg, reinterpret_cast<ull*>(d_ptr), n + 1, ctx->stream));
+        k_build_vtx<<<blocks, 256, 0, ctx->stream>>>(d_ptr, g->d.in_vtx, nullptr, nullptr, n);
+        B_TRY(cudaGetLastError());
+        B_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_tmp); d_tmp = nullptr;
     }
-    if (!hot_id.empty()) G_TRY(cudaMemcpyAsync(g->d.hot_id, hot_id.data(), hot_id.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-    G_TRY(cudaStreamSynchronize(ctx->stream));
+    if (m > 0) {   // rows of the CSC: sources of the edges, stably sorted by target
+        B_TRY(dalloc(&d_src, (size_t)m)); B_TRY(dalloc(&d_keys, (size_t)m));
+        k_edge_src<<<blocks, 256, 0, ctx->stream>>>(g->d.out_vtx, n, d_src);
+        B_TRY(cudaGetLastError());
+        int bits = 1;
+        while (bits < 31 && ((i64)1 << bits) < n) bits++;
+        size_t tb = 0;
+        B_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, reinterpret_cast<const u32*>(g->d.col_idx), d_keys, d_src, g->d.row_idx, (i64)m, 0, bits, ctx->stream));
+        B_TRY(cudaMalloc(&d_tmp, std::max<size_t>(tb, 16)));
+        B_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tb, reinterpret_cast<const u32*>(g->d.col_idx), d_keys, d_src, g->d.row_idx, (i64)m, 0, bits, ctx->stream));
+        B_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_tmp); d_tmp = nullptr; cudaFree(d_src); d_src = nullptr; cudaFree(d_keys); d_keys = nullptr;
+    }
+    // hub set: the (up to) HOT_SLOTS vertices of highest in-degree (ties: lower id first), at least hot_min_indeg in-edges
+    // each -- an O(n) selection on the host from the downloaded histogram; the O(m) encoding runs on the device
+    std::vector<u32> hot_id;
+    try {
+        std::vector<std::pair<i64, i32>> cand;
+        const i64 min_in = std::max<i64>(1, ctx->hot_min_indeg);
+        for (i64 v = 0; v < n; v++) { i64 d = (i64)h_indeg[(size_t)v]; if (d >= min_in) cand.push_back(std::make_pair(-d, (i32)v)); }
+        size_t keep = std::min<size_t>(cand.size(), HOT_SLOTS);
+        std::partial_sort(cand.begin(), cand.begin() + keep, cand.end());
+        for (size_t k = 0; k < keep; k++) hot_id.push_back((u32)cand[k].second);
+    } catch (...) { free_tmp(); return fail(ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed")); }
+    g->d.n_hot = (u32)hot_id.size();
+    if (!hot_id.empty()) B_TRY(cudaMemcpyAsync(g->d.hot_id, hot_id.data(), hot_id.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    if (m > 0) {
+        B_TRY(dalloc(&d_slot, (size_t)n));
+        B_TRY(cudaMemsetAsync(d_slot, 0xff, (size_t)n * sizeof(i32), ctx->stream));   // -1 everywhere
+        if (!hot_id.empty()) { k_set_slots<<<(unsigned)((hot_id.size() + 255) / 256), 256, 0, ctx->stream>>>(g->d.hot_id, g->d.n_hot, d_slot); B_TRY(cudaGetLastError()); }
+        k_encode_push_idx<<<blocks, 256, 0, ctx->stream>>>(g->d.col_idx, d_slot, m, g->d.push_idx);
+        B_TRY(cudaGetLastError());
+    }
+    B_TRY(cudaStreamSynchronize(ctx->stream));
+    free_tmp();
+#undef B_TRY
     cudaFree(d_ptr); d_ptr = nullptr;
 #undef G_TRY
     rc = ws_alloc(ctx, g->ws[0], n, chunk_cap);
