@@ -298,12 +298,19 @@ class Graph:
         self.ctx.check(self.L.ppr_fora_batch(self.h, _ptr(srcs), nq, alpha, eps, seed, flags, _conf(conf), _ptr(out), st if want_stats else None))
         return out, [st[i].as_dict() for i in range(nq)] if want_stats else None
 
-    def fora_topk(self, src, alpha, eps, k, seed, flags=0, conf=None):
-        cap = self.n
-        ids, vals = np.zeros(cap, np.int32), np.zeros(cap)
-        cnt, st = C.c_int32(), Stats()
-        self.ctx.check(self.L.ppr_fora_topk(self.h, src, alpha, eps, k, seed, flags, _conf(conf), _ptr(ids), _ptr(vals), cap, C.byref(cnt), C.byref(st)))
-        return ids[:cnt.value].copy(), vals[:cnt.value].copy(), st.as_dict()
+    def fora_topk(self, src, alpha, eps, k, seed, flags=0, conf=None, cap=None):
+        # buffers for k + ties (cap: first-call capacity, for tests); a result with more ties than that reports the needed size (PPR_E_CAPACITY) and is
+        # fetched by a second call with room for everything
+        cap = int(min(self.n, max(4 * k, k + 4096))) if cap is None else int(cap)
+        while True:
+            ids, vals = np.empty(cap, np.int32), np.empty(cap)
+            cnt, st = C.c_int32(), Stats()
+            rc = self.L.ppr_fora_topk(self.h, src, alpha, eps, k, seed, flags, _conf(conf), _ptr(ids), _ptr(vals), cap, C.byref(cnt), C.byref(st))
+            if rc == PPR_E_CAPACITY and cnt.value > cap:
+                cap = cnt.value
+                continue
+            self.ctx.check(rc)
+            return ids[:cnt.value].copy(), vals[:cnt.value].copy(), st.as_dict()
 
     def fora_topk_shard(self, src, alpha, eps, k, seed, shard, nshards, reduce=None, flags=0, conf=None):
         """ppr_fora_topk_shard; `reduce(dev_ptr, n)` sums the round's raw estimate vector over the shards in place."""

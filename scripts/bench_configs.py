@@ -56,7 +56,7 @@ if a.what == "topk":
     for s in S[:2]:
         topk(s, 1)
     sync(); t0 = time.perf_counter()
-    agg = {"ms_push": 0.0, "ms_walk": 0.0, "ms_select": 0.0, "rounds": 0, "walks": 0, "edges": 0}
+    agg = {"ms_push": 0.0, "ms_walk": 0.0, "ms_select": 0.0, "ms_total": 0.0, "rounds": 0, "walks": 0, "edges": 0}
     sizes = []
     for i, s in enumerate(S[2:]):
         ids, vals, st = topk(s, 100 + i)

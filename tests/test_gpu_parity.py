@@ -352,6 +352,15 @@ def test_fora_topk_walk_shards(pkg, ctx, got, rmat12, O):
             G_.close()
 
 
+def test_fora_topk_output_grows_on_capacity_error(G, OG, O):
+    # the binding offers k + ties slots first; a result that does not fit reports the needed size (PPR_E_CAPACITY)
+    # and is fetched by a second call -- forced here with a first-call capacity of 3
+    ids0, vals0, st0 = G.fora_topk(63, ALPHA, EPS, K, SEED)
+    ids1, vals1, st1 = G.fora_topk(63, ALPHA, EPS, K, SEED, cap=3)
+    assert len(ids0) >= K and np.array_equal(ids0, ids1) and np.array_equal(vals0, vals1)
+    assert np.array_equal(G.last_raw(False)[0], O.b_fora_topk(OG, 63, ALPHA, EPS, K, SEED)[0])
+
+
 def test_fora_batch_equals_single(R12, O):
     g, og = R12
     srcs = sources(og, 5)
