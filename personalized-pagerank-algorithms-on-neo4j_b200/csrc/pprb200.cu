@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -320,7 +321,9 @@ struct GraphExtra {  // host-side bookkeeping kept beside ppr_graph
     double last_divisor;
 };
 static std::vector<std::pair<ppr_graph*, GraphExtra*>> g_extras;
+static std::mutex g_extras_mu;   // graphs of different contexts may be created / queried / destroyed from different threads
 static GraphExtra* extra_of(ppr_graph* g) {
+    std::lock_guard<std::mutex> lk(g_extras_mu);
     for (auto& p : g_extras) if (p.first == g) return p.second;
     return nullptr;
 }
@@ -337,7 +340,10 @@ extern "C" int32_t ppr_graph_destroy(ppr_graph* g) {
     if (x && x->bws_ready) bws_free(x->bws);
     cudaFree(g->d.out_vtx); cudaFree(g->d.col_idx); cudaFree(g->d.out_deg);
     cudaFree(g->d.in_vtx); cudaFree(g->d.row_idx); cudaFree(g->d.invdeg); cudaFree(g->d.push_idx); cudaFree(g->d.hot_id);
-    for (size_t i = 0; i < g_extras.size(); i++) if (g_extras[i].first == g) { delete g_extras[i].second; g_extras.erase(g_extras.begin() + i); break; }
+    {
+        std::lock_guard<std::mutex> lk(g_extras_mu);
+        for (size_t i = 0; i < g_extras.size(); i++) if (g_extras[i].first == g) { delete g_extras[i].second; g_extras.erase(g_extras.begin() + i); break; }
+    }
     delete g;
     return PPR_OK;
 }
@@ -364,7 +370,7 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     memset(&g->d, 0, sizeof g->d); memset(g->ws, 0, sizeof g->ws);
     g->ctx = ctx; g->last_ws = 0; g->last_kind = 0; g->trace_active = false;
     memset(x, 0, sizeof *x);
-    g_extras.push_back(std::make_pair(g, x));
+    { std::lock_guard<std::mutex> lk(g_extras_mu); g_extras.push_back(std::make_pair(g, x)); }
     g->d.n = n; g->d.m = m;
     i64* d_ptr = nullptr;
     int32_t rc = PPR_OK;
