@@ -1157,6 +1157,7 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     int launches = 0;
     CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
     i64 curT = T;
+    bool adapted = false;
     for (i64 t0 = t_lo; t0 < t_hi;) {
         i64 Tb = std::min<i64>(curT, t_hi - t0);
         PushCtl h;
@@ -1181,6 +1182,18 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
             CUDA_TRY(cudaMemcpyAsync(hval.data() + old, b.out_val, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             tm.mark("download");
+        }
+        if (!adapted && ctx->bwd_batch <= 0 && Tb == curT) {
+            // (after the download: growing reallocates the batch buffers)
+            // cheap targets (large thresholds: a few thousand edges each) are bound by the per-iteration cost of a batch,
+            // not by its atomics: quadruple the batch for them (scripts/sweep_bwd.py: 3.6e9 -> 5.5e9 edges/s at 1e-3,
+            // but 1.5e10 -> 1.3e10 at 5e-5, hence the test on the work per target)
+            adapted = true;
+            const i64 Tmax = std::min<i64>(4096, (i64)std::max<size_t>(1, budget / ((size_t)16 * (size_t)n)));
+            if ((double)h.edges / (double)Tb < 65536.0 && Tmax > curT && t_hi - (t0 + Tb) > curT) {
+                rc = bwd_ensure(g, (i32)Tmax); if (rc) return rc;
+                curT = std::min<i64>(Tmax, b.T);
+            }
         }
         t0 += Tb;
     }

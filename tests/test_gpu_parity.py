@@ -449,6 +449,18 @@ def test_all_pairs(G, OG, R12, O):
     assert np.array_equal(mptr, optr) and np.array_equal(mtgt, otgt) and np.array_equal(mval, oval)
 
 
+def test_all_pairs_batch_growth(R16, O):
+    # n = 65536: the first batch holds 1464 targets (residue matrix ~ 768 MB); targets this cheap (threshold 1e-3)
+    # make the library quadruple the batch after it -- the index must not depend on how targets are batched
+    g, og = R16
+    hi = 12000
+    optr, otgt, oval, ost = O.b_base_all_pairs(og, ALPHA, 1e-3, 0, hi)
+    ptr, tgt, val, st = g.backward_all_pairs(ALPHA, 1e-3, -1, 0, hi, raw=True)
+    assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval)
+    assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"])
+    assert st["launches"] <= 4, st["launches"]      # 1464 + 4096 + 4096 + rest instead of 9 batches of 1464
+
+
 def test_all_pairs_topk_rows(G, OG, O):
     ptr, tgt, val, _ = G.backward_all_pairs(ALPHA, 1e-3, 3, raw=True)
     fptr, ftgt, fval, _ = O.b_base_all_pairs(OG, ALPHA, 1e-3)
