@@ -312,11 +312,10 @@ class Graph:
             self.ctx.check(rc)
             return ids[:cnt.value].copy(), vals[:cnt.value].copy(), st.as_dict()
 
-    def fora_topk_shard(self, src, alpha, eps, k, seed, shard, nshards, reduce=None, flags=0, conf=None):
-        """ppr_fora_topk_shard; `reduce(dev_ptr, n)` sums the round's raw estimate vector over the shards in place."""
-        cap = self.n
-        ids, vals = np.zeros(cap, np.int32), np.zeros(cap)
-        cnt, st = C.c_int32(), Stats()
+    def fora_topk_shard(self, src, alpha, eps, k, seed, shard, nshards, reduce=None, flags=0, conf=None, cap=None):
+        """ppr_fora_topk_shard; `reduce(dev_ptr, n)` sums the round's raw estimate vector over the shards in place.
+        Output buffers as in fora_topk (every shard sees the same count, so all of them repeat or none does)."""
+        cap = int(min(self.n, max(4 * k, k + 4096))) if cap is None else int(cap)
         failure = []
 
         def hook(_user, dev_ptr, n):
@@ -328,12 +327,18 @@ class Graph:
                 return 1
 
         cb = REDUCE_FN(hook) if reduce is not None else C.cast(None, REDUCE_FN)
-        rc = self.L.ppr_fora_topk_shard(self.h, src, alpha, eps, k, seed, flags, _conf(conf), shard, nshards, cb, None,
-                                        _ptr(ids), _ptr(vals), cap, C.byref(cnt), C.byref(st))
-        if failure:
-            raise failure[0]
-        self.ctx.check(rc)
-        return ids[:cnt.value].copy(), vals[:cnt.value].copy(), st.as_dict()
+        while True:
+            ids, vals = np.empty(cap, np.int32), np.empty(cap)
+            cnt, st = C.c_int32(), Stats()
+            rc = self.L.ppr_fora_topk_shard(self.h, src, alpha, eps, k, seed, flags, _conf(conf), shard, nshards, cb, None,
+                                            _ptr(ids), _ptr(vals), cap, C.byref(cnt), C.byref(st))
+            if failure:
+                raise failure[0]
+            if rc == PPR_E_CAPACITY and cnt.value > cap:
+                cap = cnt.value
+                continue
+            self.ctx.check(rc)
+            return ids[:cnt.value].copy(), vals[:cnt.value].copy(), st.as_dict()
 
     def power_iteration(self, src, alpha, iters=100):
         out = np.zeros(self.n)
