@@ -31,16 +31,20 @@ typedef unsigned long long ull;
 #define VTX_MAX_EDGES (1ll << 40)
 
 // Forward-push work classes
+#ifndef PUSH_SMALL_MAX
 #define PUSH_SMALL_MAX 64   // degree <= this: warp-cooperative gather over 32 vertices
+#endif
 #define PUSH_MINI_MAX PUSH_THREADS  // frontiers up to this size are iterated by one CTA without grid barriers
 #define PUSH_MINI_EDGES 4096        // ... owning at most this many edges
 #define PUSH_CHUNK 256      // larger rows are cut into chunks of this many edges, one warp per chunk
 
 #define DBG_ITERS 4096
 #define DBG_FIELDS 6   // t_start, t_after_A, t_after_B (globaltimer ns), frontier size, cumulative edges, mode
-#define HOT_SLOTS 4096      // hub vertices whose incoming adds are staged in shared memory (32 KB per CTA)
+#ifndef HOT_SLOTS
+#define HOT_SLOTS 4096      // hub vertices whose incoming adds are staged in shared memory (32 KB per CTA); a power of two
+#endif
 #define HOT_BIT 0x80000000u
-#define HOT_MASK 0x00000fffu
+#define HOT_MASK ((unsigned)HOT_SLOTS - 1u)
 #define PUSH_THREADS 512
 #define PUSH_CTAS_PER_SM (1024 / PUSH_THREADS)   // 32 resident warps per SM at 64 registers per thread
 #define WALK_THREADS 256
