@@ -57,6 +57,35 @@ __global__ void __launch_bounds__(512, 2) k_sweep(const ull* __restrict__ r_in, 
     if (acc == 0x123456789ull) *sink = acc;
 }
 
+// Double-buffered variant (design probe): read r_cur[v] and the vertex record, zero r_cur[v], carry the residue
+// (leftover of a taker, everything of a non-taker) to r_next[v] with one coalesced RED; takers also update reserve.
+// No staging, no compaction: in the real kernel the taker would relax its edges right here.
+template <int V>
+__global__ void __launch_bounds__(512, 2) k_sweep2(ull* r_cur, ull* r_next, const ull* __restrict__ vtx, ull* reserve, ull* sink, long n, ull thr) {
+    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long)gridDim.x * blockDim.x;
+    const unsigned lane = threadIdx.x & 31;
+    const long gwarp = gtid >> 5, nwarps = gsize >> 5;
+    ull acc = 0;
+    for (long tile = gwarp * 128; tile < n; tile += nwarps * 128) {
+        ull x[4], pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { long i = tile + k * 32 + lane; x[k] = i < n ? r_cur[i] : 0; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { long i = tile + k * 32 + lane; pk[k] = x[k] ? vtx[i] : 1; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            long i = tile + k * 32 + lane;
+            if (!x[k]) continue;
+            bool take = x[k] >= thr * (pk[k] & 0xff);
+            ull carry = x[k];
+            if (take) { ull a = x[k] / 7; if (V >= 1) reserve[i] += a; carry = 5; acc += a; }
+            r_cur[i] = 0;
+            atomicAdd(&r_next[i], carry);
+        }
+    }
+    if (acc == 0x123456789ull) *sink = acc;
+}
+
 __global__ void k_fill(ull* r, ull* vtx, long n, ull thr, unsigned pct) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -81,6 +110,24 @@ static void run(const char* name, long n, unsigned pct, ull* r, ull* vtx, ull* r
     printf("n %8ld takers %2u%%  %-44s %7.2f us per sweep\n", n, pct, name, ms * 1000 / reps);
 }
 
+template <int V>
+static void run2(const char* name, long n, unsigned pct, ull* r, ull* r2, ull* vtx, ull* reserve, ull* sink) {
+    const ull thr = 1000;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int reps = 20;
+    float tot = 0;
+    for (int i = 0; i < reps + 3; i++) {     // refill every time: the sweep consumes r_cur
+        k_fill<<<(unsigned)((n + 255) / 256), 256>>>(r, vtx, n, thr, pct);
+        cudaMemset(r2, 0, n * 8);
+        cudaEventRecord(e0);
+        k_sweep2<V><<<296, 512>>>(r, r2, vtx, reserve, sink, n, thr);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= 3) tot += ms;
+    }
+    printf("n %8ld takers %2u%%  %-44s %7.2f us per sweep\n", n, pct, name, tot * 1000 / reps);
+}
+
 int main() {
     const long nmax = 1L << 24;
     ull *r, *vtx, *reserve, *sp, *sq, *counter, *sink;
@@ -95,6 +142,8 @@ int main() {
             run<3>("V3 + compaction (1 ATOM / tile) + staging", n, pct, r, vtx, reserve, sp, sq, counter, sink);
             run<4>("V4 + compaction inside the tile, no atomic", n, pct, r, vtx, reserve, sp, sq, counter, sink);
             run<5>("V5 = V4 + one RED / tile", n, pct, r, vtx, reserve, sp, sq, counter, sink);
+            run2<0>("D0 double-buffered: zero + carry RED", n, pct, r, sp, vtx, reserve, sink);
+            run2<1>("D1 = D0 + reserve update of takers", n, pct, r, sp, vtx, reserve, sink);
         }
     }
     printf("cuda status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
