@@ -32,6 +32,9 @@ public final class PprB200 implements AutoCloseable {
     private static final MethodHandle MONTE_CARLO = fn("ppr_monte_carlo", FunctionDescriptor.of(I32, PTR, I32, F64, F64, I64, PTR, PTR, PTR));
     private static final MethodHandle FORA = fn("ppr_fora", FunctionDescriptor.of(I32, PTR, I32, F64, F64, I64, I32, PTR, PTR, PTR));
     private static final MethodHandle FORA_TOPK = fn("ppr_fora_topk", FunctionDescriptor.of(I32, PTR, I32, F64, F64, I32, I64, I32, PTR, PTR, PTR, I32, PTR, PTR));
+    private static final MethodHandle FORA_TOPK_SHARD = fn("ppr_fora_topk_shard", FunctionDescriptor.of(I32, PTR, I32, F64, F64, I32, I64, I32, PTR, I32, I32, PTR, PTR, PTR, PTR, I32, PTR, PTR));
+    /** ppr_reduce_fn: int32 (*)(void* user, uint64 dev_ptr, int64 n) */
+    private static final FunctionDescriptor REDUCE_FN = FunctionDescriptor.of(I32, PTR, I64, I64);
     private static final MethodHandle TOPK = fn("ppr_topk", FunctionDescriptor.of(I32, PTR, PTR, I64, I32, PTR, PTR, I32, PTR, PTR));
     private static final MethodHandle POWER = fn("ppr_power_iteration", FunctionDescriptor.of(I32, PTR, I32, F64, I32, PTR));
     private static final MethodHandle BACKWARD = fn("ppr_backward_search", FunctionDescriptor.of(I32, PTR, I32, F64, F64, PTR, PTR));
@@ -126,6 +129,24 @@ public final class PprB200 implements AutoCloseable {
             MemorySegment ids = a.allocate(I32, n), vals = a.allocate(F64, n), cnt = a.allocate(I32), conf = a.allocate(F64, 3);
             conf.setAtIndex(F64, 0, delta); conf.setAtIndex(F64, 1, pfail); conf.setAtIndex(F64, 2, minDelta);
             check((int) FORA_TOPK.invokeExact(graph, adjM.toMappedNodeId(nodeIdStart), alpha, eps, k, seed, 0, conf, ids, vals, n, cnt, MemorySegment.NULL), ctx);
+            java.util.Vector<Long> out = new java.util.Vector<>();
+            for (int i = 0; i < cnt.get(I32, 0); i++) out.add(originalIds[ids.getAtIndex(I32, i)]);
+            return out;
+        }
+    }
+
+    /** Sums n int64 values at a device address over all ranks, in place (e.g. ncclAllReduce(ptr, ptr, n, ncclInt64, ncclSum, comm, stream) + stream sync). */
+    public interface DeviceSum { int sum(long devPtr, long n); }
+
+    /** Fora_Topk with every delta-round's walks sharded over GPUs: same result on every rank, identical to foraTopk. */
+    public java.util.Vector<Long> foraTopkSharded(long nodeIdStart, double alpha, double eps, int k, long seed, int shard, int nshards, DeviceSum reduce) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            int cap = (int) Math.min((long) n, Math.max(4L * k, k + 4096L));
+            MemorySegment ids = a.allocate(I32, cap), vals = a.allocate(F64, cap), cnt = a.allocate(I32);
+            MethodHandle target = java.lang.invoke.MethodHandles.lookup().findVirtual(DeviceSum.class, "sum", java.lang.invoke.MethodType.methodType(int.class, long.class, long.class)).bindTo(reduce);
+            target = java.lang.invoke.MethodHandles.dropArguments(target, 0, MemorySegment.class);   // (user, devPtr, n) -> sum(devPtr, n)
+            MemorySegment hook = nshards > 1 ? LINKER.upcallStub(target, REDUCE_FN, a) : MemorySegment.NULL;
+            check((int) FORA_TOPK_SHARD.invokeExact(graph, adjM.toMappedNodeId(nodeIdStart), alpha, eps, k, seed, 0, MemorySegment.NULL, shard, nshards, hook, MemorySegment.NULL, ids, vals, cap, cnt, MemorySegment.NULL), ctx);
             java.util.Vector<Long> out = new java.util.Vector<>();
             for (int i = 0; i < cnt.get(I32, 0); i++) out.add(originalIds[ids.getAtIndex(I32, i)]);
             return out;
