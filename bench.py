@@ -1,21 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- FORA single-source PPR throughput on a synthetic R-MAT graph (BASELINE.json metric).
+"""bench.py -- FORA single-source PPR throughput on R-MAT scale-22 (BASELINE.json metric), walks/s and all-pair seconds.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale 20]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale 22]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one batch of --queries-per-step FORA queries (alpha 0.15, eps 0.5, delta = p_f = 1/n as in
-J/Algo_Conf.java:45-53) from distinct random sources.  Rank 0 prints ONE JSON line.
+Protocol (J/Gen_Util.java:99-107,146-151): query sources are drawn uniformly from ALL n vertices (seed 1234), every source
+is one `Fora_Whole_Graph.computeWholeGraphPPR(src, eps)` call, the mean over the sources is reported.  alpha 0.15,
+eps 0.5, delta = p_f = 1/n (J/Algo_Conf.java:45-53).  One "step" = one batch of --queries-per-step sources.
 
-* value  : queries/s with the graph resident in HBM and results left on the device (C-ABI call
-           ppr_fora_shard per query; only the 200-byte control block comes back).
-* e2e    : queries/s through the reference-facing call (ppr_fora_batch = Fora_Whole_Graph.computeWholeGraphPPR
-           per source): host source ids in, dense n-vector of doubles copied to pinned host memory, inside the timed region.
+Rank 0 prints ONE JSON line:
+* value   : queries/s, graph resident in HBM, results left on the device (C-ABI ppr_fora_shard per query).
+* e2e     : queries/s through the reference-facing call (ppr_fora_batch = computeWholeGraphPPR per source): host source ids
+            in, dense n-vector of doubles copied to pinned host memory, inside the timed region.
 * roofline: dominant kernel k_push_query; algorithmic bytes 48*V_p + 24*E_p over its CUDA-event time.
-* cpu_baseline / --impl reference: the line-by-line C++ restatement of the Java loops (oracle mode A; the
-           reference itself is Java on Neo4j and cannot run in this image), timed on the box's host cores.
-Multi-GPU (N > 1): queries are independent, so they are dealt to ranks with no data-path collective
-("weak": every rank runs --queries-per-step queries per step); timing is max over ranks.
+* walks_per_s / allpairs_s: the other two parts of BASELINE.json's metric (Monte-Carlo on the same graph; all-pair
+            backward search on the 100K-node symmetrised R-MAT of configs[3]).
+* cpu_baseline / --impl reference: the line-by-line C++ restatement of the Java loops (oracle mode A; the reference
+            itself is Java on Neo4j and cannot run in this image), timed on the box's host cores.
+N > 1: `value`/`e2e` deal disjoint source sets to the ranks (no data-path collective, "weak"); the `sharded` block times
+the paths that shard with the library's NCCL collectives inside the timed region: Monte-Carlo walks/s,
+FORA with sharded walks, all-pair backward search over target blocks.  All timing is CUDA events, max over ranks.
 """
 import argparse
 import importlib
@@ -32,26 +36,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "personalized-pagerank-algorithms-on-neo4j_b200"
 ALPHA, EPS = 0.15, 0.5
-# Push/walk balance (stand-in for the reference's wall-clock balancer, J/Fora_Whole_Graph.java:93-103, which
-# adapts to the machine it runs on): each arm uses the constant that matches its own measured costs.
-GPU_WALK_COST = None   # library default: 6 while the graph fits in L2, 24 beyond (ppr_set_balance)
-CPU_WALK_COST = 32.0   # host core: one walk ~ 32 relaxed edges (the reference's 400 ns / walk)
+# Push/walk balance constant: stand-in for the reference's wall-clock balancer (J/Fora_Whole_Graph.java:93-103, 400 ns per
+# walk against its own push cost).  BOTH arms use the same constant so that they do the same work per query.
+WALK_COST = 24.0
+SRC_SEED = 1234
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scale", type=int, default=20, help="R-MAT scale (configs[1] of BASELINE.json is scale 20)")
+    ap.add_argument("--scale", type=int, default=22, help="R-MAT scale (BASELINE.json's metric is quoted on scale 22)")
     ap.add_argument("--edge-factor", type=int, default=16)
-    ap.add_argument("--queries-per-step", type=int, default=8)
+    ap.add_argument("--queries-per-step", type=int, default=50, help="GPU arm: sources per step (20 steps x 50 = 1000 timed queries)")
+    ap.add_argument("--ref-queries-per-step", type=int, default=0, help="reference arm: sources per step (0 = 3/8 of the host threads)")
     ap.add_argument("--eps", type=float, default=EPS)
-    ap.add_argument("--walk-cost", type=float, default=None, help="override the push/walk balance constant")
-    ap.add_argument("--also-scale", type=int, default=22, help="extra short measurement at this scale (0 = off)")
+    ap.add_argument("--walk-cost", type=float, default=WALK_COST, help="push/walk balance constant (both arms)")
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--ref-threads", type=int, default=0)
+    ap.add_argument("--extras", type=int, default=1, help="walks/s, all-pair seconds, sharded block (0 = headline only)")
     return ap.parse_args()
 
 
@@ -62,20 +67,17 @@ def make_graph(pkg, scale, ef, seed=42):
     return rp, ci, time.time() - t0
 
 
-def pick_sources(rp, count, seed=1234):
-    """Uniform over vertices with out-degree > 0 (a dangling source is answered by {s: 1} without any work;
-    48 % of the R-MAT vertices are dangling)."""
-    deg = np.diff(rp)
-    cand = np.flatnonzero(deg > 0)
-    rng = np.random.default_rng(seed)
-    return cand[rng.integers(0, len(cand), count)].astype(np.int32)
+def pick_sources(n, count, seed=SRC_SEED):
+    """Uniform over all n vertices, as ThreadLocalRandom.nextInt(node_amount) in J/Gen_Util.java:99-107 (a source without
+    out-edges is answered by {s: 1}, J/Fora_Whole_Graph.java / Forward_Push.java:72-76; ~48 % of R-MAT vertices)."""
+    return np.random.default_rng(seed).integers(0, n, count).astype(np.int32)
 
 
 class ClockSampler:
     """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, device):
-        self.device, self.proc, self.rows = device, None, []
+        self.device, self.proc = device, None
 
     def start(self):
         try:
@@ -122,19 +124,30 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_push_query launch, from `ncu --set full` captures of
-# scripts/one_query.py at library defaults (profiles/r01_ncu_full_summary.txt); bytes per launch, keyed by R-MAT scale
-NCU_PUSH_TRAFFIC = {20: 0.334086e9 + 48.295680e6, 22: 6.547190e9 + 1.555525e9}
+def ncu_traffic(scale):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE k_push_query launch from the committed `ncu --set full` capture of
+    scripts/one_query.py at this scale (profiles/r02_push_traffic.json, written by scripts/ncu_summary.py); None if absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_push_traffic.json")))[str(scale)]
+        return float(d["dram_bytes"]), d["source"]
+    except Exception:
+        return None, None
 
 
-def cpu_port_query(O, og, src, eps, seed, walk_cost):
-    t0 = time.perf_counter()
-    _, st = O.a_fora(og, int(src), ALPHA, eps, seed, walk_cost=walk_cost)
-    return time.perf_counter() - t0, st
+def workload_config(args):
+    n = 1 << args.scale
+    return {"workload": "R-MAT scale-%d (n=%d, m=%d, a/b/c/d=0.57/0.19/0.19/0.05, relabelled, seed 42) FORA single-source PPR "
+                        "(BASELINE.json metric config)" % (args.scale, n, n * args.edge_factor),
+            "alpha": ALPHA, "eps": args.eps, "delta": "1/n", "p_f": "1/n",
+            "sources": "uniform over all n vertices (J/Gen_Util.java:99-107), seed %d; sources without out-edges are answered {s: 1}" % SRC_SEED,
+            "walk_cost": args.walk_cost,
+            "l2": "inputs exceed the L2 (edge arrays 2 x %d MB per graph copy vs 126 MB); the GPU arm also writes a 256 MiB buffer before every step" % (4 * n * args.edge_factor >> 20)}
 
 
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path = oracle mode A (C++ port), all host threads."""
+    """--impl reference: the reference's CPU implementation of the path = oracle mode A (C++ port of the Java loops), all
+    host threads busy for the whole timed window.  Maps libpprgen.so (graph generator) and the oracle only."""
     if rank != 0:
         return
     pkg = importlib.import_module(PKG)
@@ -142,127 +155,223 @@ def run_reference(args, rank, world):
     O.lib()
     rp, ci, _ = make_graph(pkg, args.scale, args.edge_factor)
     og = O.OGraph(rp, ci)
+    n = 1 << args.scale
     threads = args.ref_threads or max(1, min(os.cpu_count() or 1, 64))
-    walk_cost = CPU_WALK_COST if args.walk_cost is None else args.walk_cost
-    srcs = pick_sources(rp, (args.steps + args.warmup) * threads)
+    q = args.ref_queries_per_step or max(1, (3 * threads) // 8)
+    K, W = args.steps, args.warmup
+    need = (K + W) * q
+    srcs = pick_sources(n, need + 4 * threads)   # same list as the GPU arm (a prefix of it) + spare work that keeps the pool busy
+    lock = threading.Lock()
+    state = {"next": 0, "done": 0, "t_start": None, "t_end": None, "edges": 0, "walks": 0, "pushes": 0, "nd": 0}
 
-    def step(i):
-        res = [None] * threads
+    def worker():
+        while True:
+            with lock:
+                i = state["next"]
+                if i >= len(srcs) or state["t_end"] is not None:
+                    return
+                state["next"] = i + 1
+            _, st = O.a_fora(og, int(srcs[i]), ALPHA, args.eps, 1000 + i, walk_cost=args.walk_cost)
+            now = time.perf_counter()
+            with lock:
+                state["done"] += 1
+                d = state["done"]
+                if state["t_start"] is not None and state["t_end"] is None:
+                    state["edges"] += st["edges"]; state["walks"] += st["walks"]; state["pushes"] += st["pushes"]
+                    state["nd"] += 1 if st["edges"] else 0
+                if d == W * q and state["t_start"] is None:
+                    state["t_start"] = now
+                if d == need:
+                    state["t_end"] = now
 
-        def work(t):
-            res[t] = cpu_port_query(O, og, srcs[i * threads + t], args.eps, 1000 + i * threads + t, walk_cost)
-        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-        t0 = time.perf_counter()
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        return time.perf_counter() - t0
-
-    for i in range(args.warmup):
-        step(i)
-    t0 = time.perf_counter()
-    for i in range(args.warmup, args.warmup + args.steps):
-        step(i)
-    el = time.perf_counter() - t0
-    qps = args.steps * threads / el
+    t_all = time.perf_counter()
+    if W == 0:
+        state["t_start"] = t_all
+    ths = [threading.Thread(target=worker) for _ in range(threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    el = (state["t_end"] or time.perf_counter()) - state["t_start"]
+    nq = K * q
+    qps = nq / el
     line = {
         "impl": "reference", "metric": "FORA SSPPR queries/s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+        "steps": K, "warmup": W, "ms_per_step": el / K * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, threads),
+        "config": workload_config(args), "queries_per_step": q, "oracle_pinned": False,
+        "work_per_query": {"edges": state["edges"] / nq, "walks": state["walks"] / nq, "pushes": state["pushes"] / nq,
+                           "non_dangling_fraction": state["nd"] / nq},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": "%d queries per step, one per host thread (oracle mode A: C++ restatement of the Java loops; "
-                                   "the Java/Neo4j reference cannot run in this image)" % threads},
+                         "sample": "%d sources per step (the first %d of the GPU arm's source list), drained by a pool of %d host threads that "
+                                   "stays busy across step boundaries; window = from the %d-th to the %d-th completed query. oracle mode A = C++ "
+                                   "restatement of the Java loops (array state instead of boxed HashMaps: faster than the Java); the Java/Neo4j "
+                                   "reference cannot run in this image (no JDK, J/Fora_Topk.java:136 does not compile)" % (q, need, threads, W * q, need)},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, q):
-    n = 1 << args.scale
-    return {"workload": "R-MAT scale-%d (n=%d, m=%d, a/b/c/d=0.57/0.19/0.19/0.05, relabelled, seed 42) FORA single-source PPR "
-                        "(BASELINE.json configs[1] shape)" % (args.scale, n, n * args.edge_factor),
-            "alpha": ALPHA, "eps": args.eps, "delta": "1/n", "p_f": "1/n", "queries_per_step": q,
-            "sources": "uniform over vertices with out-degree > 0, seed 1234", "cpu_walk_cost": CPU_WALK_COST,
-            "l2": "L2 flushed (256 MiB write) before every step; working set at scale 20 is ~100 MB vs 126 MB L2"}
+# ------------------------------------------------------------------------------------------------ product arm (GPU)
+class Ranks:
+    """Barrier and max over ranks.  torch.distributed (NCCL) is the process plumbing the driver launches; the data-path
+    collectives are the library's own (ppr_comm_init)."""
 
+    def __init__(self, world, local):
+        self.world, self.dist, self.dev = world, None, local
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+            self.dist, self.torch = dist, torch
 
-def measure_ours(pkg, ctx, g, rp, args, srcs, steps, warmup, q, rank, world, dist, sample_clocks):
-    """Timed region of the product arm.  Returns dict with device-resident and e2e numbers + per-kernel sums."""
-    n = g.n
-    out = ctx.pinned((q, n), np.float64)
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
 
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
+    def max(self, x):
+        if self.dist is None:
             return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % ctx.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda:%d" % self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    acc = {"pushes": 0, "edges": 0, "walks": 0, "steps": 0, "ms_push": 0.0, "ms_walk": 0.0, "launches": 0, "iters": 0, "rounds": 0}
+    def bcast_bytes(self, b):
+        if self.dist is None:
+            return b
+        box = [b]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
 
-    def resident_step(i, record):
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed(ctx, R, fn, steps, warmup, slots=(0, 1)):
+    """W untimed + K timed calls of fn(i), bracketed by barrier + device sync, CUDA events on the library's stream, max over ranks."""
+    for i in range(warmup):
+        fn(i)
+    ctx.sync(); R.barrier()
+    ctx.timer_record(slots[0])
+    for i in range(warmup, warmup + steps):
+        fn(i)
+    ctx.timer_record(slots[1])
+    ms = ctx.timer_elapsed_ms(*slots)
+    ctx.sync(); R.barrier()
+    return R.max(ms)
+
+
+def headline(pkg, ctx, g, args, srcs, R, sample_clocks):
+    n, q, K, W = g.n, args.queries_per_step, args.steps, args.warmup
+    acc = {"pushes": 0, "edges": 0, "walks": 0, "steps": 0, "ms_push": 0.0, "ms_walk": 0.0, "launches": 0, "iters": 0, "rounds": 0, "nd": 0}
+
+    def resident_step(i):
         ctx.flush_l2()
         for j in range(q):
             st = g.fora_shard(int(srcs[i * q + j]), ALPHA, args.eps, 1000 + i * q + j, 0, 1)
-            if record:
+            if i >= W:
                 for k in acc:
-                    acc[k] += st[k]
+                    if k != "nd":
+                        acc[k] += st[k]
+                acc["nd"] += 1 if st["edges"] else 0
 
-    for i in range(warmup):
-        resident_step(i, False)
-    barrier()
     sampler = ClockSampler(ctx.device) if sample_clocks else None
+    for i in range(W):
+        resident_step(i)
+    ctx.sync(); R.barrier()
     if sampler:
         sampler.start()
     ctx.timer_record(0)
-    for i in range(warmup, warmup + steps):
-        resident_step(i, True)
+    for i in range(W, W + K):
+        resident_step(i)
     ctx.timer_record(1)
     ms = ctx.timer_elapsed_ms(0, 1)
-    barrier()
+    ctx.sync(); R.barrier()
     clocks = sampler.stop() if sampler else None
-    ms = max_over_ranks(ms)
+    ms = R.max(ms)
 
-    # end to end: host source ids -> ppr_fora_batch -> dense doubles in pinned host memory
+    # end to end: host source ids -> ppr_fora_batch -> dense doubles in pinned host memory (sub-batches of 10 sources)
+    sub = min(10, q)
+    out = ctx.pinned((sub, n), np.float64)
+
     def e2e_step(i):
         ctx.flush_l2()
-        g.fora_batch(srcs[i * q:(i + 1) * q], ALPHA, args.eps, 1000 + i * q, out=out, want_stats=False)
+        for b in range(0, q, sub):
+            s = srcs[i * q + b:i * q + min(b + sub, q)]
+            g.fora_batch(s, ALPHA, args.eps, 1000 + i * q + b, out=out[:len(s)], want_stats=False)
 
-    for i in range(warmup):
-        e2e_step(i)
-    barrier()
-    ctx.timer_record(2)
-    for i in range(warmup, warmup + steps):
-        e2e_step(i)
-    ctx.timer_record(3)
-    ms_e2e = ctx.timer_elapsed_ms(2, 3)
-    barrier()
-    ms_e2e = max_over_ranks(ms_e2e)
-    chk = float(out[q - 1].sum())
+    ms_e2e = timed(ctx, R, e2e_step, K, W, (2, 3))
+    return {"ms": ms, "ms_e2e": ms_e2e, "acc": acc, "clocks": clocks, "check_sum": float(out[0].sum())}
 
-    # device-resident, pipelined (same batch call, results left on the device): what the overlap of two queries buys
-    def pipe_step(i):
-        ctx.flush_l2()
-        g.fora_batch(srcs[i * q:(i + 1) * q], ALPHA, args.eps, 1000 + i * q, want_stats=False, resident=True)
 
-    for i in range(warmup):
-        pipe_step(i)
-    barrier()
-    ctx.timer_record(0)
-    for i in range(warmup, warmup + steps):
-        pipe_step(i)
-    ctx.timer_record(1)
-    ms_pipe = max_over_ranks(ctx.timer_elapsed_ms(0, 1))
-    barrier()
-    return {"ms": ms, "ms_e2e": ms_e2e, "ms_pipe": ms_pipe, "acc": acc, "clocks": clocks, "check_sum": chk}
+def extras(pkg, ctx, g, rp, args, R, rank, world):
+    """walks/s (Monte-Carlo, same graph) and all-pair seconds (configs[3]); for world > 1 the sharded forms with the library's
+    NCCL collectives inside the timed region."""
+    out = {}
+    n = g.n
+    nd = np.flatnonzero(np.diff(rp) > 0)
+    mc_src = nd[np.random.default_rng(77).integers(0, len(nd), 16)].astype(np.int32)   # a dangling source is answered without walks
+    acc = {"walks": 0, "steps": 0, "ms_walk": 0.0, "ms_comm": 0.0}
+
+    def mc_step(i):
+        if world > 1:
+            _, st = g.monte_carlo_sharded(int(mc_src[i]), ALPHA, args.eps, 500 + i, resident=True)
+        else:
+            st = g.monte_carlo_shard(int(mc_src[i]), ALPHA, args.eps, 500 + i, 0, 1)
+        if i >= 2:
+            acc["walks"] += st["walks_total"]; acc["steps"] += st["steps"]; acc["ms_walk"] += st["ms_walk"]; acc["ms_comm"] += st["ms_comm"]
+
+    ms = timed(ctx, R, mc_step, 5, 2)
+    out["walks_per_s"] = {"value": acc["walks"] / (ms / 1e3), "unit": "walks/s", "algo": "Monte_Carlo.computeWholeGraphPPR (eps %.2g): %d walks per query" % (args.eps, acc["walks"] // 5),
+                          "queries": 5, "ms_per_query": ms / 5, "n_gpus": world, "walk_kernel_ms_per_query": acc["ms_walk"] / 5,
+                          "allreduce_ms_per_query": acc["ms_comm"] / 5 if world > 1 else 0.0,
+                          "moves_per_s_per_gpu": acc["steps"] / (acc["ms_walk"] / 1e3) if acc["ms_walk"] else 0,
+                          "note": "walks of one query sharded over the GPUs + one ncclAllReduce(uint64) of the count vector, inside the timed region" if world > 1 else "one GPU"}
+
+    if world > 1:   # FORA with sharded walks (strong scaling of single queries; push replicated, balance per shard)
+        fs = nd[np.random.default_rng(78).integers(0, len(nd), 24)].astype(np.int32)
+        fa = {"ms_push": 0.0, "ms_walk": 0.0, "ms_comm": 0.0}
+
+        def fora_step(i):
+            for j in range(2):
+                _, st = g.fora_sharded(int(fs[2 * i + j]), ALPHA, args.eps, 900 + 2 * i + j, flags=pkg._native.BALANCE_PER_SHARD, resident=True)
+                if i >= 2:
+                    for k in fa:
+                        fa[k] += st[k]
+        ms = timed(ctx, R, fora_step, 8, 2)
+        out["fora_sharded"] = {"value": 16 / (ms / 1e3), "unit": "queries/s (non-dangling sources, one query at a time over all GPUs)", "n_gpus": world,
+                               "ms_per_query": ms / 16, "push_ms": fa["ms_push"] / 16, "walk_ms": fa["ms_walk"] / 16, "allreduce_ms": fa["ms_comm"] / 16,
+                               "note": "PPR_BALANCE_PER_SHARD: walk_cost / n_gpus; push replicated on every rank"}
+
+    # all-pair backward search, BASELINE configs[3]: n = 100 000, m = 1.6 M symmetrised, thresholds of J/Gen_Util.java:467
+    rp4, ci4 = pkg.rmat(100000, 1600000, seed=42, symmetric=True)
+    g4 = pkg.Graph(ctx, rp4, ci4)
+    ap = {}
+    try:
+        for thr in (1e-3, 5e-4, 5e-5):
+            res = {}
+
+            def ap_step(i, thr=thr, res=res):
+                if world > 1:
+                    ptr, tgt, val, st = g4.backward_all_pairs_sharded(ALPHA, thr, -1)
+                else:
+                    ptr, tgt, val, st = g4.backward_all_pairs(ALPHA, thr, -1)
+                res.update(pairs=int(ptr[-1]), edges=st["edges"], pushes=st["pushes"], kernel_ms=st["ms_push"], comm_ms=st["ms_comm"])
+            ms = timed(ctx, R, ap_step, 1, 1 if thr == 1e-3 else 0)
+            gbs = (48.0 * res["pushes"] + 24.0 * res["edges"]) / (res["kernel_ms"] / 1e3) / 1e9 if res["kernel_ms"] else 0.0
+            ap["%g" % thr] = {"seconds": ms / 1e3, "pairs": res["pairs"], "kernel_ms": res["kernel_ms"], "gather_ms": res["comm_ms"],
+                              "edges_relaxed_this_rank": res["edges"], "kernel_algorithmic_GBs": gbs}
+    finally:
+        g4.close()
+    out["allpairs_s"] = {"graph": "R-MAT n=100000 m=1600000 symmetrised (configs[3])", "n_gpus": world,
+                         "what": "Base_Whole_Graph.preprocessing(threshold, -1) compute part: all n backward searches + index grouped by source in host memory"
+                                 + ("; targets block-partitioned, gather = ncclAllGather of counts + one variable-length exchange" if world > 1 else ""),
+                         "thresholds": ap}
+    return out
 
 
 def main():
@@ -274,29 +383,25 @@ def main():
         run_reference(args, rank, world)
         return
     pkg = importlib.import_module(PKG)
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+    R = Ranks(world, local)
     ctx = pkg.Context(local)
-    if args.walk_cost is not None:
-        ctx.set_balance(args.walk_cost, 64)
-    walk_cost = GPU_WALK_COST if args.walk_cost is None else args.walk_cost
-    cpu_walk_cost = CPU_WALK_COST if args.walk_cost is None else args.walk_cost
-    q = args.queries_per_step
+    ctx.set_balance(args.walk_cost, 64)
+    if world > 1:   # the library's own communicator: NCCL behind the C ABI (data-path collectives)
+        uid = R.bcast_bytes(pkg.Context.comm_unique_id() if rank == 0 else None)
+        ctx.comm_init(uid, rank, world)
+    q, K, W = args.queries_per_step, args.steps, args.warmup
     rp, ci, gen_s = make_graph(pkg, args.scale, args.edge_factor)
     t0 = time.time()
     g = pkg.Graph(ctx, rp, ci)
     export_s = time.time() - t0
-    total_q = (args.steps + args.warmup) * q
-    all_srcs = pick_sources(rp, total_q * world)
-    srcs = all_srcs[rank * total_q:(rank + 1) * total_q]   # ranks work on disjoint query sets, no collective on the data path
+    n = g.n
+    total_q = (K + W) * q
+    all_srcs = pick_sources(n, total_q * world)
+    srcs = all_srcs[rank * total_q:(rank + 1) * total_q]   # ranks work on disjoint source sets, no collective on this path
 
-    m = measure_ours(pkg, ctx, g, rp, args, srcs, args.steps, args.warmup, q, rank, world, dist, rank == 0)
+    m = headline(pkg, ctx, g, args, srcs, R, rank == 0)
     acc = m["acc"]
-    nq_rank = args.steps * q
+    nq_rank = K * q
     qps = nq_rank * world / (m["ms"] / 1e3)
     qps_e2e = nq_rank * world / (m["ms_e2e"] / 1e3)
     peak, peak_src = measured_peak()
@@ -304,73 +409,68 @@ def main():
     push_gbs = push_bytes / (acc["ms_push"] / 1e3) / 1e9 if acc["ms_push"] > 0 else 0.0
     walk_bytes = 20.0 * acc["steps"] + 16.0 * acc["walks"]
     walk_gbs = walk_bytes / (acc["ms_walk"] / 1e3) / 1e9 if acc["ms_walk"] > 0 else 0.0
+    traffic, traffic_src = ncu_traffic(args.scale)
+    nd = max(acc["nd"], 1)
 
     line = {
-        "metric": "FORA SSPPR queries/s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": "FORA SSPPR queries/s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": m["ms"] / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (2^-62 fixed point; f64 only at the boundary)", "data": "synthetic",
-        "config": dict(workload_config(args, q), walk_cost=walk_cost if walk_cost is not None else "auto (6 in L2, 24 beyond)", parallelism="%d independent query streams (one per GPU)" % world),
-        "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": 4 * q, "d2h_bytes_per_step": 8 * g.n * q,
-                "api": "ppr_fora_batch (Fora_Whole_Graph.computeWholeGraphPPR per source), dense f64 result to pinned host memory; "
-                       "the batch call keeps two queries in flight while the graph fits in L2, which is why e2e can exceed `value` "
-                       "(measured one query at a time so that per-kernel CUDA-event times are unambiguous)"},
-        "resident_pipelined": {"value": nq_rank * world / (m["ms_pipe"] / 1e3), "unit": "queries/s",
-                               "api": "ppr_fora_batch with results left on the device"},
+        "config": workload_config(args), "queries_per_step": q, "timed_queries": nq_rank * world, "oracle_pinned": False,
+        "parallelism": "%d independent query streams (one per GPU), no data-path collective; see `sharded` for the paths that shard" % world,
+        "work_per_query": {"edges": acc["edges"] / nq_rank, "walks": acc["walks"] / nq_rank, "pushes": acc["pushes"] / nq_rank,
+                           "non_dangling_fraction": acc["nd"] / nq_rank},
+        "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": 4 * q, "d2h_bytes_per_step": 8 * n * q,
+                "api": "ppr_fora_batch (Fora_Whole_Graph.computeWholeGraphPPR per source), 10 sources per call, dense f64 result vectors to pinned host memory"},
         "gpu_launches": int(acc["launches"]),
         "clocks": m["clocks"],
         "roofline": {"bound": "hbm", "kernel": "k_push_query", "achieved": push_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": push_gbs / peak, "traffic": NCU_PUSH_TRAFFIC.get(args.scale) if args.walk_cost is None else None,
-                     "traffic_note": "DRAM bytes per launch from the ncu --set full capture in profiles/ (same scale, library defaults); "
-                                     "algorithmic bytes per launch = %.3g" % (push_bytes / max(nq_rank, 1)),
-                     "peak_source": peak_src,
-                     "algorithmic_bytes": "48*V_p + 24*E_p", "V_p": acc["pushes"], "E_p": acc["edges"],
-                     "launches": nq_rank, "avg_launch_ms": acc["ms_push"] / max(nq_rank, 1),
-                     "share_of_step": acc["ms_push"] / m["ms"]},
+                     "frac": push_gbs / peak, "traffic": traffic,
+                     "traffic_note": ("DRAM bytes of one launch (non-dangling source), ncu --set full: %s; " % traffic_src if traffic_src else "no ncu capture committed for this scale; ")
+                                     + "algorithmic bytes per non-dangling launch = %.4g" % (push_bytes / nd),
+                     "peak_source": peak_src, "algorithmic_bytes": "48*V_p + 24*E_p", "V_p": acc["pushes"], "E_p": acc["edges"],
+                     "launches": nq_rank, "launches_with_work": acc["nd"], "avg_launch_ms": acc["ms_push"] / max(nq_rank, 1),
+                     "avg_launch_ms_with_work": acc["ms_push"] / nd, "share_of_step": acc["ms_push"] / m["ms"]},
         "kernels": {"k_push_query": {"ms": acc["ms_push"], "edges_per_s": acc["edges"] / (acc["ms_push"] / 1e3) if acc["ms_push"] else 0,
-                                     "iters_per_query": acc["iters"] / max(nq_rank, 1), "rounds_per_query": acc["rounds"] / max(nq_rank, 1)},
+                                     "iters_per_query": acc["iters"] / nd, "rounds_per_query": acc["rounds"] / nd},
                     "k_walk": {"ms": acc["ms_walk"], "walks_per_s": acc["walks"] / (acc["ms_walk"] / 1e3) if acc["ms_walk"] else 0,
-                               "steps_per_s": acc["steps"] / (acc["ms_walk"] / 1e3) if acc["ms_walk"] else 0,
-                               "algorithmic_GBs": walk_gbs, "frac_of_peak": walk_gbs / peak,
-                               "walks_per_query": acc["walks"] / max(nq_rank, 1)}},
+                               "moves_per_s": acc["steps"] / (acc["ms_walk"] / 1e3) if acc["ms_walk"] else 0,
+                               "algorithmic_GBs": walk_gbs, "frac_of_peak": walk_gbs / peak, "share_of_step": acc["ms_walk"] / m["ms"]}},
         "setup": {"rmat_gen_s": gen_s, "graph_export_s": export_s},
     }
+    if args.extras:
+        try:
+            ex = extras(pkg, ctx, g, rp, args, R, rank, world)
+            line["walks_per_s"] = ex["walks_per_s"]
+            line["allpairs_s"] = ex["allpairs_s"]
+            if world > 1:
+                line["sharded"] = {"fora": ex["fora_sharded"], "monte_carlo": ex["walks_per_s"], "allpairs": ex["allpairs_s"],
+                                   "comm": ctx.comm_info()}
+        except Exception as e:  # never lose the headline
+            line["extras_error"] = repr(e)
 
-    if rank == 0 and args.cpu_baseline:
+    if rank == 0 and args.cpu_baseline and world == 1:
         from oracle import oracle as O   # checker/baseline only: never on the product path
         O.lib()
         og = O.OGraph(rp, ci)
-        el, st = cpu_port_query(O, og, srcs[args.warmup * q], args.eps, 1000 + args.warmup * q, cpu_walk_cost)
-        line["cpu_baseline"] = {"value": 1.0 / el, "unit": "queries/s", "cores": 1, "kind": "port",
-                                "sample": "1 query (first timed source) with oracle mode A, the C++ restatement of the reference's "
-                                          "Java loops (walk_cost %g): %.1f s, %d edges relaxed, %d walks" % (cpu_walk_cost, el, st["edges"], st["walks"])}
+        deg = np.diff(rp)
+        timed_srcs = srcs[W * q:]
+        s0 = int(next((s for s in timed_srcs if deg[s] > 0), timed_srcs[0]))
+        t0 = time.perf_counter()
+        _, st = O.a_fora(og, s0, ALPHA, args.eps, 1000, walk_cost=args.walk_cost)
+        el = time.perf_counter() - t0
+        frac = acc["nd"] / nq_rank
+        line["cpu_baseline"] = {"value": 1.0 / (el * max(frac, 1e-9)), "unit": "queries/s", "cores": 1, "kind": "port",
+                                "sample": "ONE query: the first timed source with out-edges, oracle mode A (C++ restatement of the reference's Java loops), "
+                                          "one host core: %.1f s, %d edges relaxed, %d walks; value = 1 / (that time x %.3f, the share of timed sources with "
+                                          "out-edges -- the others are answered {s: 1} at no cost)" % (el, st["edges"], st["walks"], frac)}
     g.close()
-
-    if rank == 0 and args.also_scale and args.also_scale != args.scale and world == 1:
-        # the headline shape of BASELINE.json's metric string (R-MAT-22): short extra measurement, same code path
-        try:
-            a2 = argparse.Namespace(**vars(args))
-            a2.scale = args.also_scale
-            rp2, ci2, gen2 = make_graph(pkg, a2.scale, a2.edge_factor)
-            g2 = pkg.Graph(ctx, rp2, ci2)
-            q2, steps2, warm2 = 4, 2, 3
-            s2 = pick_sources(rp2, (steps2 + warm2) * q2)
-            m2 = measure_ours(pkg, ctx, g2, rp2, a2, s2, steps2, warm2, q2, 0, 1, None, False)
-            a = m2["acc"]
-            pg = (48.0 * a["pushes"] + 24.0 * a["edges"]) / (a["ms_push"] / 1e3) / 1e9
-            line["rmat%d" % a2.scale] = {"value": steps2 * q2 / (m2["ms"] / 1e3), "unit": "queries/s",
-                                         "e2e": steps2 * q2 / (m2["ms_e2e"] / 1e3), "queries": steps2 * q2,
-                                         "push_GBs": pg, "push_frac": pg / peak,
-                                         "walks_per_s": a["walks"] / (a["ms_walk"] / 1e3), "edges_per_query": a["edges"] / (steps2 * q2),
-                                         "walks_per_query": a["walks"] / (steps2 * q2)}
-            g2.close()
-        except Exception as e:  # never lose the main line
-            line["rmat%d" % args.also_scale] = {"error": str(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        ctx.comm_destroy()
     ctx.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    R.close()
 
 
 if __name__ == "__main__":

@@ -43,6 +43,8 @@ extern "C" {
 /* flags */
 #define PPR_RESTART_AT_WALK_START 0 /* default: reference behaviour, J/Monte_Carlo.java:87-90 */
 #define PPR_RESTART_AT_SOURCE 1     /* dangling vertices send a walk back to the query source */
+#define PPR_BALANCE_PER_SHARD 2     /* sharded FORA: balance push against walk_cost / nshards (walks are nshards times cheaper) */
+#define PPR_E_COMM (-8)     /* NCCL unavailable or a collective failed */
 
 #define PPR_FX_ONE (1ull << 62) /* fixed-point scale of the raw uint64 vectors */
 
@@ -78,7 +80,7 @@ typedef struct ppr_stats {
     float ms_select;       /* CUDA-event time of top-k selection */
     float ms_total;        /* CUDA-event time of the whole device part of the call */
     int32_t launches;      /* kernels launched by the call */
-    int32_t reserved;
+    float ms_comm;         /* CUDA-event time of the call's NCCL collectives (sharded entry points) */
 } ppr_stats;
 
 /* ---------------------------------------------------------------- lifecycle
@@ -113,12 +115,7 @@ int32_t ppr_set_batch_streams(ppr_ctx* ctx, int32_t streams);
  * batch's residue matrix stays near the L2 capacity). */
 int32_t ppr_set_bwd_batch(ppr_ctx* ctx, int32_t targets_per_batch);
 
-/* Measurement helpers (bench.py): CUDA events on the context's compute stream, the stream every kernel
- * of this library is launched on (after joining the download stream), and an L2 flush (a write of a
- * 256 MiB scratch buffer, larger than the 126 MB L2).  slot is 0..3. */
-int32_t ppr_timer_record(ppr_ctx* ctx, int32_t slot);
-int32_t ppr_timer_elapsed_ms(ppr_ctx* ctx, int32_t slot_a, int32_t slot_b, float* ms_out); /* synchronises */
-int32_t ppr_flush_l2(ppr_ctx* ctx);
+/* Wait for everything queued on the context's streams. */
 int32_t ppr_device_sync(ppr_ctx* ctx);
 
 /* Pinned host memory for result buffers (optional). */
@@ -224,41 +221,49 @@ typedef int32_t (*ppr_reduce_fn)(void* user, uint64_t dev_ptr, int64_t n);
 int32_t ppr_fora_topk_shard(ppr_graph* g, int32_t src, double alpha, double eps, int32_t k, uint64_t seed, int32_t flags,
                             const ppr_conf* conf, int32_t shard, int32_t nshards, ppr_reduce_fn reduce, void* user,
                             int32_t* ids_out, double* vals_out, int32_t cap, int32_t* count_out, ppr_stats* stats);
+/* ---------------------------------------------------------------- multi-GPU: NCCL behind the ABI
+ * One process (or thread) and one context per GPU, graph replicated.  The library owns the communicator and
+ * issues its collectives on its own stream; NCCL is bound at run time (an NCCL the host process has already
+ * loaded, else $PPR_NCCL_LIB, else libnccl.so.2), so single-GPU use needs no NCCL at all.
+ *   rank 0:    ppr_comm_unique_id(id)  ->  ship the 128 bytes to every rank (any side channel)
+ *   all ranks: ppr_comm_init(ctx, id, rank, world)  (collective)
+ * The *_sharded entry points below are collective calls: every rank makes the same call with the same
+ * arguments.  Walks shard by global walk index, results are summed with ncclAllReduce(ncclUint64, ncclSum) --
+ * integer sums, so every rank ends with the same bits, identical to the single-GPU result unless
+ * PPR_BALANCE_PER_SHARD is set. */
+int32_t ppr_comm_unique_id(void* id_out /* 128 bytes */);
+int32_t ppr_comm_init(ppr_ctx* ctx, const void* id /* 128 bytes */, int32_t rank, int32_t world);
+int32_t ppr_comm_destroy(ppr_ctx* ctx);
+int32_t ppr_comm_info(ppr_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version);
+/* Barrier + element-wise MAX of `count` doubles over the ranks (timing plumbing for multi-rank harnesses). */
+int32_t ppr_comm_max_f64(ppr_ctx* ctx, double* inout, int32_t count);
+
+/* Fora_Whole_Graph.computeWholeGraphPPR with the walk loop (J/Fora_Whole_Graph.java:119-140) sharded over the
+ * communicator's ranks and one all-reduce of the reserve vector.  ppr_out may be NULL (result stays on the device). */
+int32_t ppr_fora_sharded(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed, int32_t flags,
+                         const ppr_conf* conf, double* ppr_out, ppr_stats* stats);
+/* Monte_Carlo.computeWholeGraphPPR with the walk loop (J/Monte_Carlo.java:149-154) sharded + one all-reduce of the counts. */
+int32_t ppr_monte_carlo_sharded(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed, const ppr_conf* conf,
+                                double* ppr_out, ppr_stats* stats);
+/* ppr_fora_topk_shard with the library's own all-reduce as the per-round reduction (J/Fora_Topk.java:155-168). */
+int32_t ppr_fora_topk_sharded(ppr_graph* g, int32_t src, double alpha, double eps, int32_t k, uint64_t seed, int32_t flags,
+                              const ppr_conf* conf, int32_t* ids_out, double* vals_out, int32_t cap, int32_t* count_out, ppr_stats* stats);
+/* Base_Whole_Graph.preprocessing with the target loop (J/Base_Whole_Graph.java:76-92) block-partitioned over the
+ * ranks: no communication until the final gather (ncclAllGather of the per-source counts, then one variable-length
+ * exchange straight into the grouped layout).  Every rank receives the complete index. */
+int32_t ppr_backward_all_pairs_sharded(ppr_graph* g, double alpha, double threshold, int32_t k, ppr_pairs** out, ppr_stats* stats);
+
 /* Device pointer and length (elements) of the raw uint64 result vector of the last query on g. */
 int32_t ppr_result_devptr(ppr_graph* g, uint64_t* devptr_out, int64_t* n_out);
 /* Convert the raw result vector to doubles (after an external all-reduce if sharded).
  * divisor = 0: value * 2^-62 (push / FORA); divisor > 0: count / divisor (Monte-Carlo omega). */
 int32_t ppr_result_export(ppr_graph* g, double divisor, double* out);
 
-/* ---------------------------------------------------------------- raw state of the last query (parity tests)
- * Fixed-point vectors exactly as the kernels left them: reserve (or FORA estimate / Monte-Carlo
- * counts) and residue.  Either pointer may be NULL. */
-int32_t ppr_last_raw(ppr_graph* g, uint64_t* reserve_fx, uint64_t* residue_fx);
-
-/* Stepped forward push for schedule tests: same device code as ppr_forward_push, one synchronous
- * iteration per call.  begin() seeds the frontier for (src, rmax); each step() returns the frontier
- * it pushed (ids in frontier_out, unordered; count in *count_out; 0 = converged). */
-int32_t ppr_push_trace_begin(ppr_graph* g, int32_t src, double alpha, double rmax);
-int32_t ppr_push_trace_step(ppr_graph* g, int32_t* frontier_out, int64_t cap, int64_t* count_out);
-
-/* Per-iteration timeline of the last push kernel (profiling aid): 6 uint64 per synchronous iteration =
- * {t_start, t_after_phase_A, t_after_phase_B (GPU globaltimer, ns), frontier size, cumulative edges relaxed, mode}. */
-int32_t ppr_debug_timeline(ppr_graph* g, uint64_t* out, int64_t cap_entries, int64_t* count_out);
-
 /* Terminal vertex of walk `j` started at `start` (Monte_Carlo.random_walk / random_walk_no_zero_hop,
  * J/Monte_Carlo.java:60-133), for `count` consecutive walk indices starting at j0; runs the walk
  * kernel's device function one walk per thread. */
 int32_t ppr_walk_terminals(ppr_graph* g, int32_t start, int32_t restart, uint64_t j0, int64_t count, uint64_t seed,
                            uint64_t tag, double alpha, int32_t no_zero_hop, int32_t* terminals_out);
-
-/* ---------------------------------------------------------------- synthetic inputs (bench / tests)
- * Seeded R-MAT generator (a, b, c; d = 1-a-b-c), `m` directed edges over `n` vertices (n need not be
- * a power of two: out-of-range endpoints are redrawn), self loops and duplicates kept, optional
- * random relabelling and symmetrisation (each generated edge also inserted reversed; m counts both).
- * Host-only (no CUDA), deterministic for a given argument list and independent of thread count.
- * row_ptr[n+1] and col_idx[m] are caller-allocated; rows come out in ascending target order. */
-int32_t ppr_rmat_generate(int64_t n, int64_t m, double a, double b, double c, uint64_t seed, int32_t permute,
-                          int32_t symmetric, int64_t* row_ptr, int32_t* col_idx);
 
 const char* ppr_version(void);
 

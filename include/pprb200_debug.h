@@ -1,0 +1,45 @@
+/* pprb200_debug.h -- measurement and test hooks of libpprb200.so.
+ *
+ * NOT part of the reference-facing boundary (include/pprb200.h): nothing here corresponds to a method of the
+ * reference.  bench.py uses the timers and the L2 flush; the parity tests use the raw-state readers, the stepped push
+ * and the walk-variant switch; profiling scripts use the timeline.  Same conventions as pprb200.h.
+ */
+#ifndef PPRB200_DEBUG_H
+#define PPRB200_DEBUG_H
+#include "pprb200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Measurement helpers (bench.py), per context: CUDA events on the context's compute stream, the stream every kernel
+ * of this library is launched on (after joining the download stream), and an L2 flush (a write of a
+ * 256 MiB scratch buffer, larger than the 126 MB L2).  slot is 0..3. */
+int32_t ppr_timer_record(ppr_ctx* ctx, int32_t slot);
+int32_t ppr_timer_elapsed_ms(ppr_ctx* ctx, int32_t slot_a, int32_t slot_b, float* ms_out); /* synchronises */
+int32_t ppr_flush_l2(ppr_ctx* ctx);
+
+
+/* Walk kernel variant: -1 automatic (L2 eviction-priority hints once the graph exceeds the L2), 0 plain loads, 1 hints.
+ * Results are identical; the parity tests force each variant on graphs of any size. */
+int32_t ppr_set_walk_variant(ppr_ctx* ctx, int32_t hint);
+
+/* ---------------------------------------------------------------- raw state of the last query (parity tests)
+ * Fixed-point vectors exactly as the kernels left them: reserve (or FORA estimate / Monte-Carlo
+ * counts) and residue.  Either pointer may be NULL. */
+int32_t ppr_last_raw(ppr_graph* g, uint64_t* reserve_fx, uint64_t* residue_fx);
+
+/* Stepped forward push for schedule tests: same device code as ppr_forward_push, one synchronous
+ * iteration per call.  begin() seeds the frontier for (src, rmax); each step() returns the frontier
+ * it pushed (ids in frontier_out, unordered; count in *count_out; 0 = converged). */
+int32_t ppr_push_trace_begin(ppr_graph* g, int32_t src, double alpha, double rmax);
+int32_t ppr_push_trace_step(ppr_graph* g, int32_t* frontier_out, int64_t cap, int64_t* count_out);
+
+/* Per-iteration timeline of the last push kernel (profiling aid): 6 uint64 per synchronous iteration =
+ * {t_start, t_after_phase_A, t_after_phase_B (GPU globaltimer, ns), frontier size, cumulative edges relaxed, mode}. */
+int32_t ppr_debug_timeline(ppr_graph* g, uint64_t* out, int64_t cap_entries, int64_t* count_out);
+
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPRB200_DEBUG_H */

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpprb200.so")
+# PPRB200_LIB: tuning runs load an A/B build of the same library (csrc/Makefile `variant`); never a different implementation
+LIB_PATH = os.environ.get("PPRB200_LIB") or os.path.join(_PKG, "libpprb200.so")
 
 PPR_OK = 0
 PPR_E_INVALID, PPR_E_CUDA, PPR_E_NOMEM, PPR_E_RANGE, PPR_E_CAPACITY, PPR_E_STATE, PPR_E_CALLBACK = -1, -2, -3, -4, -5, -6, -7
@@ -19,16 +20,24 @@ RESTART_AT_SOURCE = 1
 FX_ONE = 1 << 62
 FX_INV = 1.0 / float(1 << 62)
 
-# every symbol include/pprb200.h declares (checked by tests/test_abi.py against the header text)
+# every symbol include/pprb200.h (product ABI) and include/pprb200_debug.h (measurement / test hooks) declare;
+# checked by tests/test_abi.py against the header texts
 EXPORTS = [
-    "ppr_init", "ppr_shutdown", "ppr_set_tuning", "ppr_set_bwd_batch", "ppr_set_batch_streams", "ppr_timer_record", "ppr_timer_elapsed_ms", "ppr_flush_l2", "ppr_device_sync", "ppr_last_error", "ppr_device_info", "ppr_set_balance", "ppr_host_alloc",
+    "ppr_init", "ppr_shutdown", "ppr_set_tuning", "ppr_set_bwd_batch", "ppr_set_batch_streams", "ppr_device_sync", "ppr_last_error", "ppr_device_info", "ppr_set_balance", "ppr_host_alloc",
     "ppr_host_free", "ppr_graph_create", "ppr_graph_destroy", "ppr_graph_node_count", "ppr_graph_rel_count",
     "ppr_graph_export_csc", "ppr_forward_push", "ppr_monte_carlo", "ppr_fora", "ppr_fora_topk", "ppr_topk",
     "ppr_power_iteration", "ppr_fora_batch", "ppr_backward_search", "ppr_backward_all_pairs", "ppr_pairs_count",
     "ppr_pairs_export", "ppr_pairs_destroy", "ppr_fora_shard", "ppr_monte_carlo_shard", "ppr_fora_topk_shard", "ppr_result_devptr",
-    "ppr_result_export", "ppr_last_raw", "ppr_push_trace_begin", "ppr_push_trace_step", "ppr_walk_terminals", "ppr_debug_timeline",
-    "ppr_rmat_generate", "ppr_version",
+    "ppr_result_export", "ppr_walk_terminals", "ppr_version",
+    "ppr_comm_unique_id", "ppr_comm_init", "ppr_comm_destroy", "ppr_comm_info", "ppr_comm_max_f64", "ppr_fora_sharded", "ppr_monte_carlo_sharded",
+    "ppr_fora_topk_sharded", "ppr_backward_all_pairs_sharded",
 ]
+DEBUG_EXPORTS = ["ppr_timer_record", "ppr_timer_elapsed_ms", "ppr_flush_l2", "ppr_set_walk_variant", "ppr_last_raw", "ppr_push_trace_begin",
+                 "ppr_push_trace_step", "ppr_debug_timeline"]
+GEN_EXPORTS = ["ppr_rmat_generate"]   # include/pprgen.h, libpprgen.so (host only)
+GEN_PATH = os.path.join(_PKG, "libpprgen.so")
+PPR_E_COMM = -8
+BALANCE_PER_SHARD = 2
 
 
 # ppr_reduce_fn: int32 (*)(void* user, uint64 dev_ptr, int64 n)
@@ -41,11 +50,11 @@ class Stats(C.Structure):
         ("walks", C.c_int64), ("walks_total", C.c_int64), ("steps", C.c_int64), ("walk_sources", C.c_int64),
         ("rmax_fx", C.c_uint64), ("rsum_fx", C.c_uint64), ("omega", C.c_double),
         ("ms_push", C.c_float), ("ms_walk", C.c_float), ("ms_select", C.c_float), ("ms_total", C.c_float),
-        ("launches", C.c_int32), ("reserved", C.c_int32),
+        ("launches", C.c_int32), ("ms_comm", C.c_float),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class Conf(C.Structure):
@@ -68,6 +77,7 @@ class PPRError(RuntimeError):
 
 
 _lib = None
+_gen = None
 
 
 def _ptr(a):
@@ -128,8 +138,17 @@ def load():
         "ppr_push_trace_step": (i32, [vp, vp, i64, C.POINTER(i64)]),
         "ppr_walk_terminals": (i32, [vp, i32, i32, u64, i64, u64, u64, f64, i32, vp]),
         "ppr_debug_timeline": (i32, [vp, vp, i64, C.POINTER(i64)]),
-        "ppr_rmat_generate": (i32, [i64, i64, f64, f64, f64, u64, i32, i32, vp, vp]),
         "ppr_version": (C.c_char_p, []),
+        "ppr_set_walk_variant": (i32, [vp, i32]),
+        "ppr_comm_unique_id": (i32, [vp]),
+        "ppr_comm_init": (i32, [vp, vp, i32, i32]),
+        "ppr_comm_destroy": (i32, [vp]),
+        "ppr_comm_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "ppr_comm_max_f64": (i32, [vp, vp, i32]),
+        "ppr_fora_sharded": (i32, [vp, i32, f64, f64, u64, i32, vp, vp, SP]),
+        "ppr_monte_carlo_sharded": (i32, [vp, i32, f64, f64, u64, vp, vp, SP]),
+        "ppr_fora_topk_sharded": (i32, [vp, i32, f64, f64, i32, u64, i32, vp, vp, vp, i32, C.POINTER(i32), SP]),
+        "ppr_backward_all_pairs_sharded": (i32, [vp, f64, f64, i32, C.POINTER(vp), SP]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header / library mismatch
@@ -139,12 +158,25 @@ def load():
     return L
 
 
+def load_gen():
+    """dlopen libpprgen.so, the host-only synthetic-input generator (never maps libpprb200.so)."""
+    global _gen
+    if _gen is None:
+        if not os.path.exists(GEN_PATH):
+            raise ImportError("libpprgen.so is not built (%s). Run `make -C %s`." % (GEN_PATH, os.path.join(_PKG, "csrc")))
+        G = C.CDLL(GEN_PATH)
+        G.ppr_rmat_generate.restype = C.c_int32
+        G.ppr_rmat_generate.argtypes = [C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        _gen = G
+    return _gen
+
+
 def rmat(n, m, a=0.57, b=0.19, c=0.19, seed=42, permute=True, symmetric=False):
     """Seeded R-MAT graph as canonical CSR (host only, no GPU needed)."""
-    L = load()
+    G = load_gen()
     row_ptr = np.zeros(n + 1, np.int64)
     col_idx = np.zeros(max(m, 1), np.int32)
-    rc = L.ppr_rmat_generate(n, m, a, b, c, seed, int(permute), int(symmetric), _ptr(row_ptr), _ptr(col_idx))
+    rc = G.ppr_rmat_generate(n, m, a, b, c, seed, int(permute), int(symmetric), _ptr(row_ptr), _ptr(col_idx))
     if rc != PPR_OK:
         raise PPRError(rc, "ppr_rmat_generate failed")
     return row_ptr, col_idx[:m]
@@ -182,6 +214,35 @@ class Context:
 
     def set_bwd_batch(self, targets_per_batch=0):
         self.check(self.L.ppr_set_bwd_batch(self.h, targets_per_batch))
+
+    def set_walk_variant(self, hint=-1):
+        self.check(self.L.ppr_set_walk_variant(self.h, hint))
+
+    # ---- multi-GPU (NCCL inside the library)
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        rc = load().ppr_comm_unique_id(buf)
+        if rc != PPR_OK:
+            raise PPRError(rc, (load().ppr_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, uid, rank, world):
+        self.check(self.L.ppr_comm_init(self.h, C.c_char_p(uid), rank, world))
+        self.rank, self.world = rank, world
+
+    def comm_destroy(self):
+        self.check(self.L.ppr_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, w, v = C.c_int32(), C.c_int32(), C.c_int32()
+        self.check(self.L.ppr_comm_info(self.h, C.byref(r), C.byref(w), C.byref(v)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
+    def comm_max(self, values):
+        a = np.ascontiguousarray(values, np.float64).copy()
+        self.check(self.L.ppr_comm_max_f64(self.h, _ptr(a), a.shape[0]))
+        return a
 
     def timer_record(self, slot):
         self.check(self.L.ppr_timer_record(self.h, slot))
@@ -289,6 +350,47 @@ class Graph:
         self.ctx.check(self.L.ppr_monte_carlo_shard(self.h, src, alpha, eps, seed, _conf(conf), shard, nshards, C.byref(st)))
         return st.as_dict()
 
+    # ---- collective forms (every rank calls with the same arguments; ppr_comm_init first)
+    def fora_sharded(self, src, alpha, eps, seed, flags=0, out=None, conf=None, resident=False):
+        out = None if resident else (np.zeros(self.n) if out is None else out)
+        st = Stats()
+        self.ctx.check(self.L.ppr_fora_sharded(self.h, src, alpha, eps, seed, flags, _conf(conf), _ptr(out), C.byref(st)))
+        return out, st.as_dict()
+
+    def monte_carlo_sharded(self, src, alpha, eps, seed, out=None, conf=None, resident=False):
+        out = None if resident else (np.zeros(self.n) if out is None else out)
+        st = Stats()
+        self.ctx.check(self.L.ppr_monte_carlo_sharded(self.h, src, alpha, eps, seed, _conf(conf), _ptr(out), C.byref(st)))
+        return out, st.as_dict()
+
+    def fora_topk_sharded(self, src, alpha, eps, k, seed, flags=0, conf=None, cap=None):
+        cap = int(min(self.n, max(4 * k, k + 4096))) if cap is None else int(cap)
+        while True:
+            ids, vals = np.empty(cap, np.int32), np.empty(cap)
+            cnt, st = C.c_int32(), Stats()
+            rc = self.L.ppr_fora_topk_sharded(self.h, src, alpha, eps, k, seed, flags, _conf(conf), _ptr(ids), _ptr(vals), cap, C.byref(cnt), C.byref(st))
+            if rc == PPR_E_CAPACITY and cnt.value > cap:
+                cap = cnt.value
+                continue
+            self.ctx.check(rc)
+            return ids[:cnt.value].copy(), vals[:cnt.value].copy(), st.as_dict()
+
+    def backward_all_pairs_sharded(self, alpha, threshold, k=-1, raw=False):
+        p, st = C.c_void_p(), Stats()
+        self.ctx.check(self.L.ppr_backward_all_pairs_sharded(self.h, alpha, threshold, k, C.byref(p), C.byref(st)))
+        return self._pairs_out(p, raw) + (st.as_dict(),)
+
+    def _pairs_out(self, p, raw):
+        try:
+            cnt = int(self.L.ppr_pairs_count(p))
+            ptr, tgt = np.zeros(self.n + 1, np.int64), np.zeros(max(cnt, 1), np.int32)
+            val = np.zeros(max(cnt, 1)) if not raw else None
+            vfx = np.zeros(max(cnt, 1), np.uint64) if raw else None
+            self.ctx.check(self.L.ppr_pairs_export(p, _ptr(ptr), _ptr(tgt), _ptr(val), _ptr(vfx)))
+        finally:
+            self.L.ppr_pairs_destroy(p)
+        return ptr, tgt[:cnt], (vfx[:cnt] if raw else val[:cnt])
+
     def fora_batch(self, srcs, alpha, eps, seed, flags=0, out=None, want_stats=True, conf=None, resident=False):
         srcs = np.ascontiguousarray(srcs, np.int32)
         nq = srcs.shape[0]
@@ -354,15 +456,7 @@ class Graph:
         t_hi = self.n if t_hi is None else t_hi
         p, st = C.c_void_p(), Stats()
         self.ctx.check(self.L.ppr_backward_all_pairs(self.h, alpha, threshold, k, t_lo, t_hi, C.byref(p), C.byref(st)))
-        try:
-            cnt = int(self.L.ppr_pairs_count(p))
-            ptr, tgt = np.zeros(self.n + 1, np.int64), np.zeros(max(cnt, 1), np.int32)
-            val = np.zeros(max(cnt, 1))
-            vfx = np.zeros(max(cnt, 1), np.uint64) if raw else None
-            self.ctx.check(self.L.ppr_pairs_export(p, _ptr(ptr), _ptr(tgt), _ptr(val), _ptr(vfx)))
-        finally:
-            self.L.ppr_pairs_destroy(p)
-        return ptr, tgt[:cnt], (vfx[:cnt] if raw else val[:cnt]), st.as_dict()
+        return self._pairs_out(p, raw) + (st.as_dict(),)
 
     # ---- raw state / replay hooks (parity tests, multi-GPU plumbing)
     def last_raw(self, want_residue=True):

@@ -35,6 +35,7 @@ typedef unsigned long long ull;
 #define PUSH_SMALL_MAX 64   // degree <= this: warp-cooperative gather over 32 vertices
 #endif
 #define PUSH_MINI_MAX PUSH_THREADS  // frontiers up to this size are iterated by one CTA without grid barriers
+#define PUSH_MINI_POW2 (PUSH_THREADS <= 256 ? 256 : PUSH_THREADS <= 512 ? 512 : 1024)   // power of two >= PUSH_MINI_MAX
 #define PUSH_MINI_EDGES 4096        // ... owning at most this many edges
 #define PUSH_CHUNK 256      // larger rows are cut into chunks of this many edges, one warp per chunk
 
@@ -45,8 +46,17 @@ typedef unsigned long long ull;
 #endif
 #define HOT_BIT 0x80000000u
 #define HOT_MASK ((unsigned)HOT_SLOTS - 1u)
+#ifndef PUSH_THREADS
 #define PUSH_THREADS 512
+#endif
+// "small regime": frontiers of at most midi_v vertices owning at most midi_e edges are iterated by the first
+// midi_ctas CTAs with a barrier among themselves; the rest of the grid waits at the next grid barrier
+#define PUSH_MIDI_CTAS 32
+#define PUSH_MIDI_V 4096
+#define PUSH_MIDI_E (1 << 16)
+#ifndef PUSH_CTAS_PER_SM
 #define PUSH_CTAS_PER_SM (1024 / PUSH_THREADS)   // 32 resident warps per SM at 64 registers per thread
+#endif
 #define WALK_THREADS 256
 #ifndef WALK_PER_LANE
 #define WALK_PER_LANE 2      // walks in flight per lane
@@ -149,7 +159,7 @@ struct PushCtl {
     u32 err_a;         // error raised during a phase A (kept apart from err so each flag is only read behind a barrier)
     u32 mini_par;      // forward push: frontier parity after a run of single-CTA iterations
     u32 dbg_count;     // timeline entries written
-    u32 pad3;
+    u32 sub_bar;       // forward push: arrival counter of the sub-grid barrier (small regime)
     u64 pairs;         // all-pair backward search: (v, t) pairs written by the batch
     u64 pairs_needed;  // ... and the number that qualified (> capacity means the batch must be rerun)
 };
@@ -171,6 +181,16 @@ struct ppr_ctx {
     i32 batch_streams;     // ppr_fora_batch: 1 = queries back to back, 2 = two queries in flight
     i32 bwd_batch;         // all-pair backward search: targets per batch (0 = automatic)
     i32 hot_min_indeg;     // a vertex needs at least this in-degree to get a hub slot (graphs created afterwards)
+    i32 midi_ctas;         // forward push, small regime: CTAs taking part (<= 1: off), vertex and edge limits
+    i64 midi_v, midi_e;
+    i32 walk_hint;         // walk kernel variant: -1 automatic (L2 eviction hints once the graph exceeds the L2), 0 plain, 1 hints
+    // measurement helpers (pprb200_debug.h): per context, created on first use, destroyed by ppr_shutdown
+    cudaEvent_t timer_ev[4]; bool timer_init;
+    void* flush_buf;
+    // top-k over caller vectors (ppr_topk): grow-only device scratch
+    void* topk_buf; size_t topk_bytes;
+    // multi-GPU (ppr_comm_init): NCCL communicator of this rank, bound at run time (comm.hpp)
+    void* comm; i32 rank, world;
 };
 
 struct DevGraph {

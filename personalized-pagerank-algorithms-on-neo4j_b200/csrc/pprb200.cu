@@ -21,11 +21,14 @@
 #include <cub/device/device_scan.cuh>
 
 #include "backward.cuh"
+#include "comm.hpp"
 #include "common.cuh"
+#include "../../include/pprb200_debug.h"
 #include "push.cuh"
 #include "select.cuh"
 #include "walk.cuh"
 
+#define PUSH_DYN_SMEM ((size_t)HOT_SLOTS * 8)   // dynamic shared memory of k_push_query: the per-CTA hub accumulators
 static thread_local std::string g_init_err;
 
 int32_t ctx_fail(ppr_ctx* ctx, int32_t code, const std::string& msg) {
@@ -115,6 +118,15 @@ extern "C" int32_t ppr_init(int32_t device, ppr_ctx** out) {
     ctx->hot_min_indeg = 64;
     ctx->bwd_batch = 0;
     ctx->batch_streams = 0;
+    ctx->walk_hint = -1;
+    ctx->timer_init = false; ctx->flush_buf = nullptr; ctx->topk_buf = nullptr; ctx->topk_bytes = 0;
+    ctx->comm = nullptr; ctx->rank = 0; ctx->world = 1;
+    {   // small-regime knobs of the forward push (debug overrides: PPR_MIDI_CTAS / PPR_MIDI_V / PPR_MIDI_E)
+        const char* e;
+        ctx->midi_ctas = (e = getenv("PPR_MIDI_CTAS")) ? atoi(e) : PUSH_MIDI_CTAS;
+        ctx->midi_v = (e = getenv("PPR_MIDI_V")) ? atoll(e) : PUSH_MIDI_V;
+        ctx->midi_e = (e = getenv("PPR_MIDI_E")) ? atoll(e) : PUSH_MIDI_E;
+    }
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
         delete ctx;
@@ -141,6 +153,9 @@ extern "C" int32_t ppr_shutdown(ppr_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy);
     for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->timer_init) for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->timer_ev[i]);
+    cudaFree(ctx->flush_buf); cudaFree(ctx->topk_buf);
+    if (ctx->comm) { NcclApi* api = nccl_api(nullptr); if (api) api->CommDestroy((ncclComm_t)ctx->comm); }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->copy);
@@ -185,36 +200,36 @@ extern "C" int32_t ppr_set_bwd_batch(ppr_ctx* ctx, int32_t targets_per_batch) {
     return PPR_OK;
 }
 
-static cudaEvent_t g_timer_ev[4];
-static bool g_timer_init = false;
-static void* g_flush_buf = nullptr;
 extern "C" int32_t ppr_timer_record(ppr_ctx* ctx, int32_t slot) {
     if (!ctx || slot < 0 || slot > 3) return PPR_E_INVALID;
     cudaSetDevice(ctx->device);
-    if (!g_timer_init) { for (int i = 0; i < 4; i++) cudaEventCreate(&g_timer_ev[i]); g_timer_init = true; }
-    cudaEvent_t join;  // the compute stream waits for everything queued on the download stream
-    CUDA_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-    cudaEventRecord(join, ctx->copy);
-    cudaStreamWaitEvent(ctx->stream, join, 0);
-    cudaEventRecord(join, ctx->stream2);
-    cudaStreamWaitEvent(ctx->stream, join, 0);
-    cudaEventDestroy(join);
-    CUDA_TRY(cudaEventRecord(g_timer_ev[slot], ctx->stream));
+    if (!ctx->timer_init) { for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ctx->timer_ev[i])); ctx->timer_init = true; }
+    // the compute stream waits for everything queued on the download stream and the second compute stream
+    CUDA_TRY(cudaEventRecord(ctx->ev[6], ctx->copy));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev[6], 0));
+    CUDA_TRY(cudaEventRecord(ctx->ev[7], ctx->stream2));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev[7], 0));
+    CUDA_TRY(cudaEventRecord(ctx->timer_ev[slot], ctx->stream));
     return PPR_OK;
 }
 extern "C" int32_t ppr_timer_elapsed_ms(ppr_ctx* ctx, int32_t a, int32_t b, float* ms_out) {
-    if (!ctx || a < 0 || a > 3 || b < 0 || b > 3 || !ms_out || !g_timer_init) return PPR_E_INVALID;
+    if (!ctx || a < 0 || a > 3 || b < 0 || b > 3 || !ms_out || !ctx->timer_init) return PPR_E_INVALID;
     cudaSetDevice(ctx->device);
-    CUDA_TRY(cudaEventSynchronize(g_timer_ev[b]));
-    CUDA_TRY(cudaEventElapsedTime(ms_out, g_timer_ev[a], g_timer_ev[b]));
+    CUDA_TRY(cudaEventSynchronize(ctx->timer_ev[b]));
+    CUDA_TRY(cudaEventElapsedTime(ms_out, ctx->timer_ev[a], ctx->timer_ev[b]));
     return PPR_OK;
 }
 extern "C" int32_t ppr_flush_l2(ppr_ctx* ctx) {
     if (!ctx) return PPR_E_INVALID;
     cudaSetDevice(ctx->device);
     const size_t bytes = (size_t)256 << 20;
-    if (!g_flush_buf) CUDA_TRY(cudaMalloc(&g_flush_buf, bytes));
-    CUDA_TRY(cudaMemsetAsync(g_flush_buf, 0x5a, bytes, ctx->stream));
+    if (!ctx->flush_buf) CUDA_TRY(cudaMalloc(&ctx->flush_buf, bytes));
+    CUDA_TRY(cudaMemsetAsync(ctx->flush_buf, 0x5a, bytes, ctx->stream));
+    return PPR_OK;
+}
+extern "C" int32_t ppr_set_walk_variant(ppr_ctx* ctx, int32_t hint) {
+    if (!ctx || hint < -1 || hint > 1) return PPR_E_INVALID;
+    ctx->walk_hint = hint;
     return PPR_OK;
 }
 extern "C" int32_t ppr_device_sync(ppr_ctx* ctx) {
@@ -261,7 +276,8 @@ static int32_t ws_alloc(ppr_ctx* ctx, Workspace& w, i64 n, i64 chunk_cap) {
     CUDA_TRY(dalloc(&w.chunks, (size_t)chunk_cap));
     CUDA_TRY(dalloc(&w.ws_v, N)); CUDA_TRY(dalloc(&w.ws_begin, N + 64)); CUDA_TRY(dalloc(&w.ws_inc, N)); CUDA_TRY(dalloc(&w.ws_rem, N));
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_push_query, PUSH_THREADS, 0));
+    if (PUSH_DYN_SMEM) CUDA_TRY(cudaFuncSetAttribute(k_push_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH_DYN_SMEM));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_push_query, PUSH_THREADS, PUSH_DYN_SMEM));
     int occ2 = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_topk_select, SEL_THREADS, 0));
     int occ3 = 0;
@@ -319,6 +335,12 @@ struct GraphExtra {  // host-side bookkeeping kept beside ppr_graph
     BwdWorkspace bws; bool bws_ready;
     int walk_blocks;
     double last_divisor;
+    // ppr_fora_batch: events and the pinned control-block snapshots are created once and reused by every call
+    std::vector<cudaEvent_t> batch_ev;      // 4 timing events per query (only when the caller asks for stats)
+    cudaEvent_t done_ev[2], copied_ev[2];   // per workspace: result ready / result downloaded (no timing)
+    bool batch_ev_ready;
+    PushCtl* snaps; size_t snaps_cap;       // pinned
+    i64 bwd_chunks_per_target;              // chunk descriptors one reverse-push target can need in one iteration
 };
 static std::vector<std::pair<ppr_graph*, GraphExtra*>> g_extras;
 static std::mutex g_extras_mu;   // graphs of different contexts may be created / queried / destroyed from different threads
@@ -338,6 +360,11 @@ extern "C" int32_t ppr_graph_destroy(ppr_graph* g) {
     ws_free(g->ws[0]);
     if (x && x->ws1_ready) ws_free(g->ws[1]);
     if (x && x->bws_ready) bws_free(x->bws);
+    if (x) {
+        for (auto& e : x->batch_ev) cudaEventDestroy(e);
+        if (x->batch_ev_ready) for (int i = 0; i < 2; i++) { cudaEventDestroy(x->done_ev[i]); cudaEventDestroy(x->copied_ev[i]); }
+        if (x->snaps) cudaFreeHost(x->snaps);
+    }
     cudaFree(g->d.out_vtx); cudaFree(g->d.col_idx); cudaFree(g->d.out_deg);
     cudaFree(g->d.in_vtx); cudaFree(g->d.row_idx); cudaFree(g->d.invdeg); cudaFree(g->d.push_idx); cudaFree(g->d.hot_id);
     {
@@ -369,7 +396,8 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     if (!g || !x) { delete g; delete x; return ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed"); }
     memset(&g->d, 0, sizeof g->d); memset(g->ws, 0, sizeof g->ws);
     g->ctx = ctx; g->last_ws = 0; g->last_kind = 0; g->trace_active = false;
-    memset(x, 0, sizeof *x);
+    x->ws1_ready = false; x->bws_ready = false; x->walk_blocks = 0; x->last_divisor = 0.0; memset(&x->bws, 0, sizeof x->bws);
+    x->batch_ev_ready = false; x->snaps = nullptr; x->snaps_cap = 0; x->bwd_chunks_per_target = 1;
     { std::lock_guard<std::mutex> lk(g_extras_mu); g_extras.push_back(std::make_pair(g, x)); }
     g->d.n = n; g->d.m = m;
     i64* d_ptr = nullptr;
@@ -496,11 +524,12 @@ static void fill_push_args(PushArgs& A, ppr_graph* g, Workspace& w) {
     A.blk_a = w.blk_a; A.blk_b = w.blk_b; A.ctl = w.ctl; A.dbg = w.dbg;
     A.prep_adds_push_part = 1;
     A.scan_threshold = g->ctx->scan_threshold < 0 ? std::max<i64>(1, g->d.n / 4) : g->ctx->scan_threshold;
+    A.midi_ctas = g->ctx->midi_ctas; A.midi_v = (u32)g->ctx->midi_v; A.midi_e = (u64)g->ctx->midi_e;
 }
 
 static cudaError_t launch_push(ppr_ctx* ctx, Workspace& w, PushArgs& A, cudaStream_t st = nullptr, int blocks = 0) {
     void* args[] = {&A};
-    return cudaLaunchCooperativeKernel((const void*)k_push_query, dim3(blocks ? blocks : w.coop_blocks), dim3(PUSH_THREADS), args, 0, st ? st : ctx->stream);
+    return cudaLaunchCooperativeKernel((const void*)k_push_query, dim3(blocks ? blocks : w.coop_blocks), dim3(PUSH_THREADS), args, PUSH_DYN_SMEM, st ? st : ctx->stream);
 }
 
 static cudaError_t launch_walk(ppr_ctx* ctx, ppr_graph* g, Workspace& w, u64* target, u64 seed, u64 tag, double alpha, i32 src,
@@ -513,7 +542,8 @@ static cudaError_t launch_walk(ppr_ctx* ctx, ppr_graph* g, Workspace& w, u64* ta
     W.k0 = (u32)key; W.k1 = (u32)(key >> 32);
     W.tstop = h_stop_threshold(alpha);
     W.src = src; W.restart_at_source = restart_at_source; W.no_zero_hop = no_zero_hop;
-    const bool big = 4.0 * (double)g->d.m + 8.0 * (double)g->d.n > 96.0 * 1024 * 1024;   // graph beyond the L2: use eviction hints
+    const bool big = ctx->walk_hint >= 0 ? ctx->walk_hint == 1
+                                         : 4.0 * (double)g->d.m + 8.0 * (double)g->d.n > 96.0 * 1024 * 1024;   // graph beyond the L2: use eviction hints
     if (big) k_walk<true, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
     else k_walk<false, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
     return cudaGetLastError();
@@ -615,6 +645,7 @@ static int32_t fora_launch(ppr_graph* g, Workspace& w, i32 src, double alpha, do
     PushArgs A;
     fill_push_args(A, g, w);
     A.src = src; A.alpha_q64 = h_alpha_q64(alpha); A.alpha = alpha; A.omega = p.omega; A.walk_cost = effective_walk_cost(g);
+    if (flags & PPR_BALANCE_PER_SHARD) A.walk_cost = A.walk_cost / (double)nshards;   // walks are nshards times cheaper than on one GPU
     A.rmax0 = p.rmax; A.max_rounds = ctx->max_rounds; A.mode = PMODE_FORA; A.init = 1;
     A.zero_reserve_after_push = shard != 0; A.prep_adds_push_part = shard == 0;
     if (omega_out) *omega_out = p.omega;
@@ -688,66 +719,76 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
     }
     g->trace_active = false;
     const i64 n = g->d.n;
-    // per-query events and control-block snapshots
-    std::vector<cudaEvent_t> ev((size_t)nq * 4);
-    for (auto& e : ev) cudaEventCreate(&e);
-    PushCtl* snaps = nullptr;
-    cudaError_t me = cudaHostAlloc((void**)&snaps, std::max<size_t>(1, (size_t)nq) * sizeof(PushCtl), cudaHostAllocDefault);
-    std::vector<double> omegas((size_t)nq, 0.0);
+    // events and snapshot memory live with the graph: nothing is created per call once they have grown to the batch size
+    if (!x->batch_ev_ready) {
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&x->done_ev[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&x->copied_ev[i], cudaEventDisableTiming));
+        }
+        x->batch_ev_ready = true;
+    }
+    if (stats_out) {
+        try { x->batch_ev.reserve((size_t)nq * 3); } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_fora_batch: host allocation failed"); }
+        while (x->batch_ev.size() < (size_t)nq * 3) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); x->batch_ev.push_back(e); }
+        if (x->snaps_cap < (size_t)nq) {
+            if (x->snaps) cudaFreeHost(x->snaps);
+            x->snaps = nullptr; x->snaps_cap = 0;
+            CUDA_TRY(cudaHostAlloc((void**)&x->snaps, (size_t)nq * sizeof(PushCtl), cudaHostAllocDefault));
+            x->snaps_cap = (size_t)nq;
+        }
+    }
+    std::vector<double> omegas;
+    try { omegas.assign((size_t)std::max(nq, 1), 0.0); } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_fora_batch: host allocation failed"); }
+    cudaError_t ce = cudaSuccess;
     int32_t rc = PPR_OK;
-    auto cleanup = [&]() { for (auto& e : ev) cudaEventDestroy(e); if (snaps) cudaFreeHost(snaps); };
-    if (me != cudaSuccess) { cleanup(); return ctx_fail_cuda(ctx, me, "cudaHostAlloc", __FILE__, __LINE__); }
-    cudaEvent_t copied[2] = {nullptr, nullptr};
-    cudaEventCreateWithFlags(&copied[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&copied[1], cudaEventDisableTiming);
+#define Q_TRY(expr) do { if (ce == cudaSuccess) { ce = (expr); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, #expr, __FILE__, __LINE__); } } while (0)
     bool used[2] = {false, false};
     // automatic: two queries in flight only while both working sets fit in the L2 together (measured: +17 % at
     // R-MAT scale 20, -1.5 % at scale 22)
     const bool small_graph = 4.0 * (double)g->d.m + 8.0 * (double)g->d.n <= 96.0 * 1024 * 1024;
     const bool dual = nq > 1 && (ctx->batch_streams == 2 || (ctx->batch_streams == 0 && small_graph));
-    auto issue_copy = [&](int q) -> cudaError_t {
+    auto issue_copy = [&](int q) {
         // download of query q on the copy stream, overlapping the kernels of query q+1
         Workspace& w = g->ws[q & 1];
-        cudaError_t e = cudaStreamWaitEvent(ctx->copy, ev[(size_t)q * 4 + 3], 0);
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpyAsync(ppr_out + (size_t)q * n, w.out_f64, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy);
-        if (e != cudaSuccess) return e;
-        return cudaEventRecord(copied[q & 1], ctx->copy);
+        Q_TRY(cudaStreamWaitEvent(ctx->copy, x->done_ev[q & 1], 0));
+        Q_TRY(cudaMemcpyAsync(ppr_out + (size_t)q * n, w.out_f64, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy));
+        Q_TRY(cudaEventRecord(x->copied_ev[q & 1], ctx->copy));
     };
     for (int q = 0; q < nq && rc == PPR_OK; q++) {
         Workspace& w = g->ws[q & 1];
-        cudaEvent_t* e = &ev[(size_t)q * 4];
+        cudaEvent_t* e = stats_out ? &x->batch_ev[(size_t)q * 3] : nullptr;
         // Two compute streams: query q+1 (other workspace, other stream) runs concurrently with query q, so the
         // nearly idle tail iterations of one push overlap the dense phases / walks of the other.  Each cooperative
         // kernel then takes one CTA per SM so that both are resident together.
         cudaStream_t st = dual ? (q & 1 ? ctx->stream2 : ctx->stream) : ctx->stream;
-        if (used[q & 1]) cudaStreamWaitEvent(st, copied[q & 1], 0);  // out_f64 of this workspace is free again
-        rc = fora_launch(g, w, srcs[q], alpha, eps, seed + (u64)q, flags, conf, 0, 1, e[0], e[1], e[2], &omegas[q], st, dual ? ctx->sm_count : 0);
+        if (used[q & 1] && !resident) Q_TRY(cudaStreamWaitEvent(st, x->copied_ev[q & 1], 0));  // out_f64 of this workspace is free again
         if (rc) break;
-        if (!resident) k_export_f64<<<ctx->sm_count * 8, 256, 0, st>>>(w.reserve, w.out_f64, n, 0.0);
-        cudaMemcpyAsync(&snaps[q], w.ctl, sizeof(PushCtl), cudaMemcpyDeviceToHost, st);
-        cudaEventRecord(e[3], st);
+        rc = fora_launch(g, w, srcs[q], alpha, eps, seed + (u64)q, flags, conf, 0, 1, e ? e[0] : nullptr, e ? e[1] : nullptr, e ? e[2] : nullptr,
+                         &omegas[q], st, dual ? ctx->sm_count : 0);
+        if (rc) break;
+        if (!resident) { k_export_f64<<<ctx->sm_count * 8, 256, 0, st>>>(w.reserve, w.out_f64, n, 0.0); Q_TRY(cudaGetLastError()); }
+        if (stats_out) Q_TRY(cudaMemcpyAsync(&x->snaps[q], w.ctl, sizeof(PushCtl), cudaMemcpyDeviceToHost, st));
+        Q_TRY(cudaEventRecord(x->done_ev[q & 1], st));
         used[q & 1] = true;
-        if (q > 0 && !resident) { cudaError_t ce = issue_copy(q - 1); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, "batch download", __FILE__, __LINE__); }
+        if (q > 0 && !resident && rc == PPR_OK) issue_copy(q - 1);
     }
-    if (rc == PPR_OK && nq > 0 && !resident) { cudaError_t ce = issue_copy(nq - 1); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, "batch download", __FILE__, __LINE__); }
+    if (rc == PPR_OK && nq > 0 && !resident) issue_copy(nq - 1);
+#undef Q_TRY
     cudaError_t s1 = cudaStreamSynchronize(ctx->stream), s2 = cudaStreamSynchronize(ctx->copy);
     { cudaError_t s3 = cudaStreamSynchronize(ctx->stream2); if (s1 == cudaSuccess) s1 = s3; }
     if (rc == PPR_OK && (s1 != cudaSuccess || s2 != cudaSuccess)) rc = ctx_fail_cuda(ctx, s1 != cudaSuccess ? s1 : s2, "batch sync", __FILE__, __LINE__);
     if (rc == PPR_OK) {
         if (stats_out) for (int q = 0; q < nq; q++) {
             ppr_stats* st = &stats_out[q];
-            stats_from_ctl(st, &snaps[q], omegas[q]);
-            cudaEvent_t* e = &ev[(size_t)q * 4];
+            stats_from_ctl(st, &x->snaps[q], omegas[q]);
+            cudaEvent_t* e = &x->batch_ev[(size_t)q * 3];
             cudaEventElapsedTime(&st->ms_push, e[0], e[1]);
             cudaEventElapsedTime(&st->ms_walk, e[1], e[2]);
-            cudaEventElapsedTime(&st->ms_total, e[0], e[3]);
+            cudaEventElapsedTime(&st->ms_total, e[0], e[2]);
             st->launches = resident ? 2 : 3;
         }
         if (nq > 0) { g->last_ws = (nq - 1) & 1; g->last_kind = 1; x->last_divisor = 0.0; }
     }
-    cudaEventDestroy(copied[0]); cudaEventDestroy(copied[1]);
-    cleanup();
     return rc;
 }
 
@@ -1010,6 +1051,136 @@ extern "C" int32_t ppr_topk(ppr_ctx* ctx, const double* vec, int64_t n, int32_t 
     return rc;
 }
 
+// ============================================================================================= multi-GPU (NCCL behind the ABI)
+#define NCCL_TRY(api, expr) do { ncclResult_t r__ = (expr); if (r__ != ncclSuccess) return ctx_fail(ctx, PPR_E_COMM, std::string("NCCL: ") + (api)->GetErrorString(r__) + " in " #expr); } while (0)
+
+extern "C" int32_t ppr_comm_unique_id(void* id_out) {
+    if (!id_out) return PPR_E_INVALID;
+    std::string err;
+    NcclApi* api = nccl_api(&err);
+    if (!api) return ctx_fail(nullptr, PPR_E_COMM, err);
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) return ctx_fail(nullptr, PPR_E_COMM, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id_out, &id, sizeof id);
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_comm_init(ppr_ctx* ctx, const void* id, int32_t rank, int32_t world) {
+    if (!ctx) return PPR_E_INVALID;
+    if (!id || world < 1 || rank < 0 || rank >= world) return ctx_fail(ctx, PPR_E_INVALID, "ppr_comm_init: bad arguments");
+    if (ctx->comm) return ctx_fail(ctx, PPR_E_STATE, "ppr_comm_init: the context already has a communicator");
+    std::string err;
+    NcclApi* api = nccl_api(&err);
+    if (!api) return ctx_fail(ctx, PPR_E_COMM, err);
+    cudaSetDevice(ctx->device);
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    ncclComm_t comm = nullptr;
+    NCCL_TRY(api, api->CommInitRank(&comm, world, uid, rank));
+    ctx->comm = comm; ctx->rank = rank; ctx->world = world;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_comm_destroy(ppr_ctx* ctx) {
+    if (!ctx) return PPR_E_INVALID;
+    if (ctx->comm) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        NcclApi* api = nccl_api(nullptr);
+        if (api) api->CommDestroy((ncclComm_t)ctx->comm);
+        ctx->comm = nullptr; ctx->rank = 0; ctx->world = 1;
+    }
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_comm_info(ppr_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version) {
+    if (!ctx) return PPR_E_INVALID;
+    if (rank) *rank = ctx->rank;
+    if (world) *world = ctx->world;
+    if (nccl_version) { *nccl_version = 0; NcclApi* api = nccl_api(nullptr); if (api) { int v = 0; api->GetVersion(&v); *nccl_version = v; } }
+    return PPR_OK;
+}
+
+// in-place integer sum of n raw uint64 values over the ranks, on the library's stream (no-op for a single rank)
+static int32_t comm_allreduce_u64(ppr_ctx* ctx, u64* buf, i64 n) {
+    if (ctx->world <= 1) return PPR_OK;
+    NcclApi* api = nccl_api(nullptr);
+    if (!api || !ctx->comm) return ctx_fail(ctx, PPR_E_COMM, "sharded call without a communicator (ppr_comm_init)");
+    NCCL_TRY(api, api->AllReduce(buf, buf, (size_t)n, ncclUint64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_comm_max_f64(ppr_ctx* ctx, double* inout, int32_t count) {
+    if (!ctx || !inout || count < 0 || count > 64) return PPR_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (ctx->world <= 1) return PPR_OK;
+    NcclApi* api = nccl_api(nullptr);
+    if (!api || !ctx->comm) return ctx_fail(ctx, PPR_E_COMM, "ppr_comm_max_f64 without a communicator (ppr_comm_init)");
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, 64 * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d, inout, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t r = e == cudaSuccess ? api->AllReduce(d, d, (size_t)count, ncclDouble, ncclMax, (ncclComm_t)ctx->comm, ctx->stream) : ncclSuccess;
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpyAsync(inout, d, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (r != ncclSuccess) return ctx_fail(ctx, PPR_E_COMM, std::string("NCCL: ") + api->GetErrorString(r));
+    CUDA_TRY(e);
+    return PPR_OK;
+}
+
+static int32_t require_comm(ppr_graph* g, const char* who) {
+    if (!g) return PPR_E_INVALID;
+    if (g->ctx->world > 1 && !g->ctx->comm) return ctx_fail(g->ctx, PPR_E_COMM, std::string(who) + ": no communicator");
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_fora_sharded(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed, int32_t flags,
+                                    const ppr_conf* conf, double* ppr_out, ppr_stats* stats) {
+    int32_t rc = require_comm(g, "ppr_fora_sharded"); if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    rc = ppr_fora_shard(g, src, alpha, eps, seed, flags, conf, ctx->rank, ctx->world, stats); if (rc) return rc;
+    Workspace& w = g->ws[0];
+    CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+    rc = comm_allreduce_u64(ctx, w.reserve, g->d.n); if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (ppr_out) { rc = export_vec(g, w, w.reserve, 0.0, ppr_out, ctx->stream); if (rc) return rc; }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) { cudaEventElapsedTime(&stats->ms_comm, ctx->ev[3], ctx->ev[4]); stats->ms_total += stats->ms_comm; stats->launches += ppr_out ? 2 : 1; }
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_monte_carlo_sharded(ppr_graph* g, int32_t src, double alpha, double eps, uint64_t seed, const ppr_conf* conf,
+                                           double* ppr_out, ppr_stats* stats) {
+    int32_t rc = require_comm(g, "ppr_monte_carlo_sharded"); if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    rc = ppr_monte_carlo_shard(g, src, alpha, eps, seed, conf, ctx->rank, ctx->world, stats); if (rc) return rc;
+    Workspace& w = g->ws[0];
+    CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+    rc = comm_allreduce_u64(ctx, w.reserve, g->d.n); if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (ppr_out) { rc = export_vec(g, w, w.reserve, extra_of(g)->last_divisor, ppr_out, ctx->stream); if (rc) return rc; }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) { cudaEventElapsedTime(&stats->ms_comm, ctx->ev[3], ctx->ev[4]); stats->ms_total += stats->ms_comm; stats->launches += ppr_out ? 2 : 1; }
+    return PPR_OK;
+}
+
+static int32_t nccl_reduce_hook(void* user, uint64_t dev_ptr, int64_t n) {
+    ppr_ctx* ctx = (ppr_ctx*)user;
+    if (comm_allreduce_u64(ctx, (u64*)(uintptr_t)dev_ptr, n) != PPR_OK) return 1;
+    return cudaStreamSynchronize(ctx->stream) == cudaSuccess ? 0 : 1;
+}
+
+extern "C" int32_t ppr_fora_topk_sharded(ppr_graph* g, int32_t src, double alpha, double eps, int32_t k, uint64_t seed, int32_t flags,
+                                         const ppr_conf* conf, int32_t* ids_out, double* vals_out, int32_t cap, int32_t* count_out, ppr_stats* stats) {
+    int32_t rc = require_comm(g, "ppr_fora_topk_sharded"); if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    return fora_topk_impl(g, src, alpha, eps, k, seed, flags, conf, ctx->rank, ctx->world, ctx->world > 1 ? nccl_reduce_hook : nullptr, ctx,
+                          ids_out, vals_out, cap, count_out, stats);
+}
+
 // ============================================================================================= power iteration
 extern "C" int32_t ppr_power_iteration(ppr_graph* g, int32_t src, double alpha, int32_t iters, double* out) {
     int32_t rc = check_query(g, src, alpha, "ppr_power_iteration");
@@ -1123,6 +1294,8 @@ extern "C" int32_t ppr_backward_search(ppr_graph* g, int32_t target, double alph
     return PPR_OK;
 }
 
+static void apply_topk_rows(ppr_pairs* P, int32_t k);
+
 extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double threshold, int32_t k, int32_t t_lo, int32_t t_hi,
                                           ppr_pairs** out, ppr_stats* stats) {
     if (!g) return PPR_E_INVALID;
@@ -1235,26 +1408,7 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
             u32* h = hist.data() + (size_t)c * n;   // now: offset of this chunk's next entry inside row v
             for (size_t i = lo; i < hi; i++) { u32 v = hv[i]; size_t p = (size_t)P->src_ptr[v] + h[v]++; P->tgt[p] = (i32)ht[i]; P->val[p] = hval[i]; }
         });
-        if (k >= 0) {  // J/Base_Whole_Graph.java:133-148: keep >= k-th largest, sort descending (stable)
-            std::vector<i64> nptr((size_t)n + 1, 0);
-            std::vector<i32> ntgt; std::vector<u64> nval;
-            std::vector<i64> ord; std::vector<u64> tmp;
-            for (i64 v = 0; v < n; v++) {
-                i64 lo = P->src_ptr[(size_t)v], hi = P->src_ptr[(size_t)v + 1], len = hi - lo;
-                u64 kth = 0; bool have = false;
-                if (k >= 1 && k <= len) {
-                    tmp.assign(P->val.begin() + lo, P->val.begin() + hi);
-                    std::nth_element(tmp.begin(), tmp.begin() + (k - 1), tmp.end(), [](u64 a, u64 c) { return a > c; });
-                    kth = tmp[(size_t)k - 1]; have = true;
-                }
-                ord.clear();
-                for (i64 i = lo; i < hi; i++) if (!have || P->val[(size_t)i] >= kth) ord.push_back(i);
-                std::stable_sort(ord.begin(), ord.end(), [&](i64 a, i64 c) { return P->val[(size_t)a] > P->val[(size_t)c]; });
-                for (i64 i : ord) { ntgt.push_back(P->tgt[(size_t)i]); nval.push_back(P->val[(size_t)i]); }
-                nptr[(size_t)v + 1] = (i64)ntgt.size();
-            }
-            P->src_ptr.swap(nptr); P->tgt.swap(ntgt); P->val.swap(nval);
-        }
+        if (k >= 0) apply_topk_rows(P, k);
     } catch (...) { delete P; return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
     tm.mark("group by source");
     if (stats) {
@@ -1263,6 +1417,140 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
         cudaEventElapsedTime(&stats->ms_push, ctx->ev[0], ctx->ev[1]);
         stats->ms_total = stats->ms_push; stats->launches = launches; stats->rounds = launches;
     }
+    *out = P;
+    return PPR_OK;
+}
+
+
+// J/Base_Whole_Graph.java:133-148: per source keep the entries >= the k-th largest, sorted descending (stable: ties by ascending target)
+static void apply_topk_rows(ppr_pairs* P, int32_t k) {
+    const i64 n = P->n;
+    std::vector<i64> nptr((size_t)n + 1, 0);
+    std::vector<i32> ntgt; std::vector<u64> nval;
+    std::vector<i64> ord; std::vector<u64> tmp;
+    for (i64 v = 0; v < n; v++) {
+        i64 lo = P->src_ptr[(size_t)v], hi = P->src_ptr[(size_t)v + 1], len = hi - lo;
+        u64 kth = 0; bool have = false;
+        if (k >= 1 && k <= len) {
+            tmp.assign(P->val.begin() + lo, P->val.begin() + hi);
+            std::nth_element(tmp.begin(), tmp.begin() + (k - 1), tmp.end(), [](u64 a, u64 c) { return a > c; });
+            kth = tmp[(size_t)k - 1]; have = true;
+        }
+        ord.clear();
+        for (i64 i = lo; i < hi; i++) if (!have || P->val[(size_t)i] >= kth) ord.push_back(i);
+        std::stable_sort(ord.begin(), ord.end(), [&](i64 a, i64 c) { return P->val[(size_t)a] > P->val[(size_t)c]; });
+        for (i64 i : ord) { ntgt.push_back(P->tgt[(size_t)i]); nval.push_back(P->val[(size_t)i]); }
+        nptr[(size_t)v + 1] = (i64)ntgt.size();
+    }
+    P->src_ptr.swap(nptr); P->tgt.swap(ntgt); P->val.swap(nval);
+}
+
+// ---------------------------------------------------------------------------------------------- all pairs over the ranks
+// Targets are block-partitioned (same split as the walk shards); no communication until the index is complete.  Gather:
+// ncclAllGather of the per-source counts, then every rank's (target, value) arrays travel once (one broadcast per
+// rank inside one NCCL group) into a rank-major device buffer, and a merge kernel writes row v of the result as the
+// concatenation, in rank order = ascending targets, of the ranks' rows v.
+__global__ void k_merge_rows(const i64* __restrict__ cnt_all /*[world][n]*/, const i64* __restrict__ rank_base /*[world]*/, int world, i64 n,
+                             const i64* __restrict__ mptr /*[n+1]*/, const i32* __restrict__ tgt_in, const u64* __restrict__ val_in,
+                             const i64* __restrict__ row_in /*[world][n]: start of row v inside rank r's slice*/,
+                             i32* __restrict__ tgt_out, u64* __restrict__ val_out) {
+    const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((i64)gridDim.x * blockDim.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
+    for (i64 v = gw; v < n; v += nw) {
+        i64 dst = mptr[v];
+        for (int r = 0; r < world; r++) {
+            const i64 c = cnt_all[(i64)r * n + v], src = rank_base[r] + row_in[(i64)r * n + v];
+            for (i64 i = lane; i < c; i += 32) { tgt_out[dst + i] = tgt_in[src + i]; val_out[dst + i] = val_in[src + i]; }
+            dst += c;
+        }
+    }
+}
+__global__ void k_rows_excl(const i64* __restrict__ cnt_all, int world, i64 n, i64* __restrict__ row_in) {
+    // exclusive prefix of every rank's row counts (one CTA per rank; n is a few 10^5 for the all-pair configs)
+    __shared__ i64 carry, part[1024];
+    const int r = blockIdx.x;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (i64 base = 0; base < n; base += blockDim.x) {
+        const i64 v = base + threadIdx.x;
+        const i64 c = v < n ? cnt_all[(i64)r * n + v] : 0;
+        part[threadIdx.x] = c;
+        __syncthreads();
+        for (unsigned o = 1; o < blockDim.x; o <<= 1) { i64 t = threadIdx.x >= o ? part[threadIdx.x - o] : 0; __syncthreads(); part[threadIdx.x] += t; __syncthreads(); }
+        if (v < n) row_in[(i64)r * n + v] = carry + part[threadIdx.x] - c;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += part[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+extern "C" int32_t ppr_backward_all_pairs_sharded(ppr_graph* g, double alpha, double threshold, int32_t k, ppr_pairs** out, ppr_stats* stats) {
+    int32_t rc = require_comm(g, "ppr_backward_all_pairs_sharded"); if (rc) return rc;
+    ppr_ctx* ctx = g->ctx;
+    if (!out) return ctx_fail(ctx, PPR_E_INVALID, "ppr_backward_all_pairs_sharded: out is NULL");
+    const i64 n = g->d.n;
+    const int world = ctx->world, rank = ctx->rank;
+    const i32 lo = (i32)((n * rank) / world), hi = (i32)((n * (rank + 1)) / world);
+    ppr_pairs* L = nullptr;
+    rc = ppr_backward_all_pairs(g, alpha, threshold, world > 1 ? -1 : k, lo, hi, &L, stats); if (rc) return rc;
+    if (world == 1) { *out = L; return PPR_OK; }
+    NcclApi* api = nccl_api(nullptr);
+    cudaSetDevice(ctx->device);
+    i64 *d_cnt = nullptr, *d_all = nullptr, *d_rows = nullptr, *d_base = nullptr, *d_mptr = nullptr;
+    i32 *d_tin = nullptr, *d_tout = nullptr; u64 *d_vin = nullptr, *d_vout = nullptr;
+    ppr_pairs* P = nullptr;
+    auto done = [&]() { cudaFree(d_cnt); cudaFree(d_all); cudaFree(d_rows); cudaFree(d_base); cudaFree(d_mptr); cudaFree(d_tin); cudaFree(d_tout); cudaFree(d_vin); cudaFree(d_vout); };
+    auto fail = [&](int32_t code) { done(); delete L; delete P; return code; };
+#define S_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail(ctx_fail_cuda(ctx, e__, #expr, __FILE__, __LINE__)); } while (0)
+#define SN_TRY(expr) do { ncclResult_t r__ = (expr); if (r__ != ncclSuccess) return fail(ctx_fail(ctx, PPR_E_COMM, std::string("NCCL: ") + api->GetErrorString(r__) + " in " #expr)); } while (0)
+    cudaEvent_t e0 = ctx->ev[3], e1 = ctx->ev[4];
+    S_TRY(cudaEventRecord(e0, ctx->stream));
+    std::vector<i64> cnt((size_t)n), all((size_t)n * world), base((size_t)world + 1, 0), mptr((size_t)n + 1, 0);
+    for (i64 v = 0; v < n; v++) cnt[(size_t)v] = L->src_ptr[(size_t)v + 1] - L->src_ptr[(size_t)v];
+    S_TRY(dalloc(&d_cnt, (size_t)n)); S_TRY(dalloc(&d_all, (size_t)n * world)); S_TRY(dalloc(&d_rows, (size_t)n * world));
+    S_TRY(dalloc(&d_base, (size_t)world)); S_TRY(dalloc(&d_mptr, (size_t)n + 1));
+    S_TRY(cudaMemcpyAsync(d_cnt, cnt.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SN_TRY(api->AllGather(d_cnt, d_all, (size_t)n, ncclInt64, (ncclComm_t)ctx->comm, ctx->stream));
+    S_TRY(cudaMemcpyAsync(all.data(), d_all, (size_t)n * world * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    S_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < world; r++) { i64 t = 0; for (i64 v = 0; v < n; v++) t += all[(size_t)r * n + v]; base[(size_t)r + 1] = base[(size_t)r] + t; }
+    for (i64 v = 0; v < n; v++) { i64 t = 0; for (int r = 0; r < world; r++) t += all[(size_t)r * n + v]; mptr[(size_t)v + 1] = mptr[(size_t)v] + t; }
+    const i64 total = base[(size_t)world];
+    S_TRY(dalloc(&d_tin, (size_t)total)); S_TRY(dalloc(&d_vin, (size_t)total)); S_TRY(dalloc(&d_tout, (size_t)total)); S_TRY(dalloc(&d_vout, (size_t)total));
+    const i64 mine = base[(size_t)rank + 1] - base[(size_t)rank];
+    if (mine) {
+        S_TRY(cudaMemcpyAsync(d_tin + base[(size_t)rank], L->tgt.data(), (size_t)mine * 4, cudaMemcpyHostToDevice, ctx->stream));
+        S_TRY(cudaMemcpyAsync(d_vin + base[(size_t)rank], L->val.data(), (size_t)mine * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    SN_TRY(api->GroupStart());
+    for (int r = 0; r < world; r++) {
+        const i64 c = base[(size_t)r + 1] - base[(size_t)r];
+        if (!c) continue;
+        SN_TRY(api->Broadcast(d_tin + base[(size_t)r], d_tin + base[(size_t)r], (size_t)c, ncclInt32, r, (ncclComm_t)ctx->comm, ctx->stream));
+        SN_TRY(api->Broadcast(d_vin + base[(size_t)r], d_vin + base[(size_t)r], (size_t)c, ncclUint64, r, (ncclComm_t)ctx->comm, ctx->stream));
+    }
+    SN_TRY(api->GroupEnd());
+    S_TRY(cudaMemcpyAsync(d_base, base.data(), (size_t)world * 8, cudaMemcpyHostToDevice, ctx->stream));
+    S_TRY(cudaMemcpyAsync(d_mptr, mptr.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_rows_excl<<<world, 1024, 0, ctx->stream>>>(d_all, world, n, d_rows);
+    k_merge_rows<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_all, d_base, world, n, d_mptr, d_tin, d_vin, d_rows, d_tout, d_vout);
+    S_TRY(cudaGetLastError());
+    P = new (std::nothrow) ppr_pairs();
+    if (!P) return fail(ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs_sharded: host allocation failed"));
+    try { P->n = n; P->src_ptr = mptr; P->tgt.resize((size_t)total); P->val.resize((size_t)total); }
+    catch (...) { return fail(ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs_sharded: host allocation failed")); }
+    if (total) {
+        S_TRY(cudaMemcpyAsync(P->tgt.data(), d_tout, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        S_TRY(cudaMemcpyAsync(P->val.data(), d_vout, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    S_TRY(cudaEventRecord(e1, ctx->stream));
+    S_TRY(cudaStreamSynchronize(ctx->stream));
+#undef S_TRY
+#undef SN_TRY
+    if (stats) { cudaEventElapsedTime(&stats->ms_comm, e0, e1); stats->ms_total += stats->ms_comm; }
+    done();
+    delete L;
+    if (k >= 0) apply_topk_rows(P, k);
     *out = P;
     return PPR_OK;
 }

@@ -64,6 +64,9 @@ struct PushArgs {
     int prep_adds_push_part;      // shard == 0
     i64 scan_threshold;           // frontier edges >= this: next frontier is found by a dense sweep (SCAN mode)
     int mini;                     // 1: frontiers of <= PUSH_MINI_MAX vertices are iterated by one CTA (push_mini)
+    int midi_ctas;                // > 1: frontiers of <= midi_v vertices / midi_e edges are iterated by this many CTAs (push_small)
+    u32 midi_v;
+    u64 midi_e;
 };
 
 #define PMODE_PUSH 0
@@ -112,6 +115,25 @@ __device__ __forceinline__ void warp_append4_u32(u32* list, u32* counter, EdgeCo
 
 __device__ __forceinline__ u64 globaltimer_ns() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
+// --------------------------------------------------------------------------------- PTX helpers (sm_100a)
+// Result-less adds are written as explicit `red`: with a fence anywhere in the kernel ptxas otherwise turns
+// `atomicAdd` with an unused result into ATOMG ... RZ, which costs the dense phase B ~30 %.
+__device__ __forceinline__ void red_add_u64(u64* p, u64 v) { asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u32 ld_acquire_u32(const u32* p) { u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void red_release_u32(u32* p, u32 v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+// Barrier among the first K CTAs of the grid (the "small regime" below): one release-add and an acquire spin per
+// CTA on a monotonic counter.  ~1.5 us for K = 32, against ~5 us for a barrier over all 296 CTAs.
+__device__ __forceinline__ void sub_sync(u32* bar, u32 K, u32& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += K;
+        red_release_u32(bar, 1u);
+        while (ld_acquire_u32(bar) < target) {}
+    }
+    __syncthreads();
+}
+
 // floor: below 1/alpha units mulhi64(x, alpha_q64) is 0 and a push would move nothing into the reserve
 __device__ __forceinline__ u64 rmax_to_fx_dev(double rmax, u64 alpha_q64) {
     const u64 lo = ~0ull / alpha_q64 + 2;
@@ -139,54 +161,87 @@ __device__ void push_scan(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64
 }
 
 // --------------------------------------------------------------------------------- phase A
-// Per-vertex capture shared by both frontier modes.  SCAN = true sweeps all vertices (coalesced reads of
-// r[] and the vertex table) and keeps those at or above threshold; SCAN = false walks the frontier list.
-// Work is warp-granular: a warp takes 128 consecutive items (4 per lane, loads issued together), counts
-// its short rows and long-row chunks with ballots, reserves staging slots for the whole tile with ONE
-// packed 64-bit atomic (chunks << 32 | short rows) and writes.  No CTA barrier inside the loop: an earlier
-// version reserved per CTA tile behind __syncthreads and spent ~11 us per tile on the atomic round trip.
-template <bool SCAN>
-__device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u32* sm_cnt /*16 words, 8-byte aligned*/) {
-    PushCtl* ctl = A.ctl;
-    const i64 cnt = SCAN ? A.n : (i64)*(volatile u32*)&ctl->cnt[par];
-    if (gtid == 0) {  // recycle the other parity's counters (last read before the preceding barrier)
-        ctl->cnt[par ^ 1] = 0; ctl->stage[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
-        ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0; ctl->nedge[par ^ 1] = 0;
+// Per-vertex capture: x = r[v]; reserve[v] += mulhi(x, alpha); r[v] = leftover; stage (vertex record, per-edge amount)
+// by degree class.  Two front ends:
+//   push_phase_a_list : walks the frontier list (LIST mode), 128 consecutive items per warp, every load of a stage
+//                       issued for all four items of a lane before anything is stored;
+//   push_sweep_warp   : dense sweep over all vertices (SCAN mode), 128 consecutive vertices per warp; r[] and out_deg[] of
+//                       the warp's next tile are requested before the current one is processed.
+// The sweep moves ~170 MB per iteration at R-MAT scale 22 (r, degrees, vertex records and reserves of the takers in, r,
+// reserve and staging out) and runs at about half of the DRAM bandwidth.  A version that streamed r[]/out_deg[] through
+// shared memory with 1-D bulk copies (cp.async.bulk + mbarrier, 2048-vertex CTA tiles, two stages) was measured slower
+// (75 vs 54 us per sweep at scale 22: two CTA barriers and the slot-reserving atomic sit in every tile's critical path)
+// and was removed; profiles/r02_push_variants.txt.
+struct PhaseATotals { u64 edges, resv, dang, pushed; };
+
+__device__ __forceinline__ void phase_a_publish(PushCtl* ctl, int par, PhaseATotals t, u32* sm_cnt /*16 words, 8-byte aligned*/) {
+    // CTA-level totals first (shared-memory atomics), then one global atomic per counter per CTA
+    u64* sm_acc = reinterpret_cast<u64*>(sm_cnt + 8);
+    const u32 lane = lane_id();
+    __syncthreads();
+    if (threadIdx.x < 4) sm_acc[threadIdx.x] = 0;
+    __syncthreads();
+    t.edges = warp_sum_u64(t.edges);
+    t.resv = warp_sum_u64(t.resv);
+    t.dang = warp_sum_u64(t.dang);
+    t.pushed = warp_sum_u64(t.pushed);
+    if (lane == 0) {
+        if (t.pushed) atomicAdd((ull*)&sm_acc[0], (ull)t.pushed);
+        if (t.edges) atomicAdd((ull*)&sm_acc[1], (ull)t.edges);
+        if (t.resv) atomicAdd((ull*)&sm_acc[2], (ull)t.resv);
+        if (t.dang) atomicAdd((ull*)&sm_acc[3], (ull)t.dang);
     }
-    u64 edges_local = 0, resv_local = 0, dang_local = 0, pushed_local = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sm_acc[0]) atomicAdd(&ctl->fcnt[par], (u32)sm_acc[0]);
+        if (sm_acc[1]) atomicAdd((ull*)&ctl->fedges[par], (ull)sm_acc[1]);
+        if (sm_acc[2]) atomicAdd((ull*)&ctl->reserve_total, (ull)sm_acc[2]);
+        if (sm_acc[3]) atomicAdd((ull*)&ctl->dang[par], (ull)sm_acc[3]);
+    }
+}
+
+__device__ __forceinline__ void phase_a_recycle(PushCtl* ctl, int par) {  // the other parity's counters (last read before the preceding barrier)
+    ctl->cnt[par ^ 1] = 0; ctl->stage[par ^ 1] = 0; ctl->dang[par ^ 1] = 0;
+    ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0; ctl->nedge[par ^ 1] = 0;
+}
+
+constexpr int PA_ITEMS = 4;
+
+__device__ void push_phase_a_list(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u32* sm_cnt) {
+    PushCtl* ctl = A.ctl;
+    const i64 cnt = (i64)*(volatile u32*)&ctl->cnt[par];
+    if (gtid == 0) phase_a_recycle(ctl, par);
+    PhaseATotals tot = {0, 0, 0, 0};
     const u32* F = A.front[par];
     const u32 lane = lane_id();
     const i64 gwarp = gtid >> 5, nwarps = gsize >> 5;
-    constexpr int PA_ITEMS = 4;
     for (i64 tile = gwarp * (32 * PA_ITEMS); tile < cnt; tile += nwarps * (32 * PA_ITEMS)) {
-        u64 pk[PA_ITEMS], q[PA_ITEMS], x[PA_ITEMS];
-        u32 v[PA_ITEMS], cls[PA_ITEMS];  // cls: 0 none, 1 short row, 2 long row
+        u64 pk[PA_ITEMS], x[PA_ITEMS], rs[PA_ITEMS];
+        u32 v[PA_ITEMS];
 #pragma unroll
-        for (int k = 0; k < PA_ITEMS; k++) {
-            i64 i = tile + (i64)k * 32 + lane;
-            v[k] = i < cnt ? (SCAN ? (u32)i : F[i]) : 0xffffffffu;
+        for (int k = 0; k < PA_ITEMS; k++) { i64 i = tile + (i64)k * 32 + lane; v[k] = i < cnt ? F[i] : 0xffffffffu; }
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) {   // every listed vertex is a taker: all three loads go out together
+            const bool ok = v[k] != 0xffffffffu;
+            x[k] = ok ? A.r[v[k]] : 0;
+            pk[k] = ok ? A.out_vtx[v[k]] : 0;
+            rs[k] = ok ? A.reserve[v[k]] : 0;
         }
-#pragma unroll
-        for (int k = 0; k < PA_ITEMS; k++) x[k] = v[k] != 0xffffffffu ? A.r[v[k]] : 0;
-#pragma unroll
-        for (int k = 0; k < PA_ITEMS; k++) pk[k] = (v[k] != 0xffffffffu && (!SCAN || x[k])) ? A.out_vtx[v[k]] : 0;
-        u32 my_nch = 0;
+        u64 q[PA_ITEMS];
+        u32 cls[PA_ITEMS], my_nch = 0;  // cls: 0 none, 1 short row, 2 long row
 #pragma unroll
         for (int k = 0; k < PA_ITEMS; k++) {
             q[k] = 0; cls[k] = 0;
-            bool take = v[k] != 0xffffffffu && (!SCAN || (x[k] && x[k] >= thr_fwd(rmax_fx, vtx_deg(pk[k]))));
-            if (take) {
-                u32 d = vtx_deg(pk[k]);
-                u64 a = mulhi64(x[k], A.alpha_q64);
-                u64 y = x[k] - a;
+            if (v[k] != 0xffffffffu) {
+                const u32 d = vtx_deg(pk[k]);
+                const u64 a = mulhi64(x[k], A.alpha_q64);
+                const u64 y = x[k] - a;
                 u64 left;
-                if (d == 0) { left = 0; dang_local += y; }
+                if (d == 0) { left = 0; tot.dang += y; }
                 else { q[k] = y / (u64)d; left = y - q[k] * (u64)d; }
                 A.r[v[k]] = left;
-                A.reserve[v[k]] += a;   // (a RED here was measured 2x slower than this load + store)
-                resv_local += a;
-                edges_local += d;
-                pushed_local += 1;
+                A.reserve[v[k]] = rs[k] + a;
+                tot.resv += a; tot.edges += d; tot.pushed += 1;
                 cls[k] = d == 0 ? 0u : (d <= PUSH_SMALL_MAX ? 1u : 2u);
                 if (cls[k] == 2) my_nch += (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
             }
@@ -220,34 +275,99 @@ __device__ void push_phase_a(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
             }
         }
     }
-    // CTA-level totals first (shared-memory atomics), then one global atomic per counter per CTA
-    u64* sm_acc = reinterpret_cast<u64*>(sm_cnt + 8);
-    __syncthreads();
-    if (threadIdx.x < 4) sm_acc[threadIdx.x] = 0;
-    __syncthreads();
-    edges_local = warp_sum_u64(edges_local);
-    resv_local = warp_sum_u64(resv_local);
-    dang_local = warp_sum_u64(dang_local);
-    pushed_local = warp_sum_u64(pushed_local);
-    if (lane == 0) {
-        if (pushed_local) atomicAdd((ull*)&sm_acc[0], (ull)pushed_local);
-        if (edges_local) atomicAdd((ull*)&sm_acc[1], (ull)edges_local);
-        if (resv_local) atomicAdd((ull*)&sm_acc[2], (ull)resv_local);
-        if (dang_local) atomicAdd((ull*)&sm_acc[3], (ull)dang_local);
+    phase_a_publish(ctl, par, tot, sm_cnt);
+}
+
+// Warp-granular dense sweep: a warp takes 128 consecutive vertices at a time; r[] and out_deg[] of its NEXT tile are
+// requested before the current tile is processed, vertex records and reserves of the current tile's takers are fetched
+// together with the slot-reserving atomic, so a tile costs one dependent round trip instead of seven.
+__device__ void push_sweep_warp(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u32* sm_cnt) {
+    PushCtl* ctl = A.ctl;
+    if (gtid == 0) phase_a_recycle(ctl, par);
+    PhaseATotals tot = {0, 0, 0, 0};
+    const u32 lane = lane_id();
+    const i64 n = A.n, gwarp = gtid >> 5, stride = (gsize >> 5) * (32 * PA_ITEMS);
+    u64 xn[PA_ITEMS];
+    u32 dn[PA_ITEMS];
+    i64 tile = gwarp * (32 * PA_ITEMS);
+#pragma unroll
+    for (int k = 0; k < PA_ITEMS; k++) { const i64 v = tile + k * 32 + lane; xn[k] = v < n ? A.r[v] : 0; dn[k] = v < n ? A.out_deg[v] : 0; }
+    for (; tile < n; tile += stride) {
+        u64 x[PA_ITEMS], pk[PA_ITEMS], rs[PA_ITEMS];
+        u32 d[PA_ITEMS], cls[PA_ITEMS], my_nch = 0;
+        bool take[PA_ITEMS];
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) { x[k] = xn[k]; d[k] = dn[k]; }
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) {
+            const i64 v = tile + k * 32 + lane;
+            take[k] = x[k] != 0 && x[k] >= thr_fwd(rmax_fx, d[k]);
+            pk[k] = (take[k] && d[k]) ? A.out_vtx[v] : 0;
+            rs[k] = take[k] ? A.reserve[v] : 0;
+            cls[k] = (!take[k] || d[k] == 0) ? 0u : (d[k] <= PUSH_SMALL_MAX ? 1u : 2u);
+            if (cls[k] == 2) my_nch += (d[k] + PUSH_CHUNK - 1) / PUSH_CHUNK;
+        }
+        {   // next tile
+            const i64 nt = tile + stride;
+#pragma unroll
+            for (int k = 0; k < PA_ITEMS; k++) { const i64 v = nt + k * 32 + lane; xn[k] = v < n ? A.r[v] : 0; dn[k] = v < n ? A.out_deg[v] : 0; }
+        }
+        u32 ms[PA_ITEMS], small_total = 0;
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) { ms[k] = __ballot_sync(0xffffffffu, cls[k] == 1); small_total += __popc(ms[k]); }
+        u32 chunk_incl = 0, chunk_total = 0;
+        if (__any_sync(0xffffffffu, my_nch != 0)) {
+            chunk_incl = my_nch;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { u32 c = __shfl_up_sync(0xffffffffu, chunk_incl, o); if (lane >= o) chunk_incl += c; }
+            chunk_total = __shfl_sync(0xffffffffu, chunk_incl, 31);
+        }
+        u64 base = 0;
+        if (lane == 0 && (small_total | chunk_total)) base = atomicAdd((ull*)&ctl->stage[par], ((ull)chunk_total << 32) | (ull)small_total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        u32 off = (u32)base;
+        u32 cb = (u32)(base >> 32) + chunk_incl - my_nch;
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) {
+            if (take[k]) {
+                const i64 v = tile + k * 32 + lane;
+                const u64 a = mulhi64(x[k], A.alpha_q64);
+                const u64 y = x[k] - a;
+                u64 left, q = 0;
+                if (d[k] == 0) { left = 0; tot.dang += y; }
+                else { q = y / (u64)d[k]; left = y - q * (u64)d[k]; }
+                A.r[v] = left;
+                A.reserve[v] = rs[k] + a;
+                tot.resv += a; tot.edges += d[k]; tot.pushed += 1;
+                if (cls[k] == 1) { const u32 sl = off + __popc(ms[k] & lanemask_lt()); A.s_pack[sl] = pk[k]; A.s_q[sl] = q; }
+                if (cls[k] == 2) {
+                    const u32 nch = (d[k] + PUSH_CHUNK - 1) / PUSH_CHUNK;
+                    A.l_pack[cb] = pk[k]; A.l_q[cb] = q;
+                    for (u32 c = 0; c < nch; c++) A.chunks[cb + c] = make_uint2(cb, c);
+                    cb += nch;
+                }
+            }
+            off += __popc(ms[k]);
+        }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (sm_acc[0]) atomicAdd(&ctl->fcnt[par], (u32)sm_acc[0]);
-        if (sm_acc[1]) atomicAdd((ull*)&ctl->fedges[par], (ull)sm_acc[1]);
-        if (sm_acc[2]) atomicAdd((ull*)&ctl->reserve_total, (ull)sm_acc[2]);
-        if (sm_acc[3]) atomicAdd((ull*)&ctl->dang[par], (ull)sm_acc[3]);
-    }
+    phase_a_publish(ctl, par, tot, sm_cnt);
 }
 
 // --------------------------------------------------------------------------------- phase B
 // One relaxed edge.  LIST: returning atomic + crossing test; otherwise a fire-and-forget reduction.
+// Hub accumulator in shared memory: value = hi * 2^32 + lo.  Shared memory has no native 64-bit add (atomicAdd on u64
+// compiles to an LDS + ATOMS.CAS retry loop, 14 % of all stall samples of the kernel in round 1's profile); two native
+// 32-bit atomics do it exactly: the returning add on the low word detects its own wrap-around, which is carried into
+// the high word.
+__device__ __forceinline__ void hot_add(u32* sm_hot, u32 slot, u64 q) {
+    const u32 lo = (u32)q;
+    const u32 old = atomicAdd(&sm_hot[slot], lo);
+    const u32 hi = (u32)(q >> 32) + ((old + lo) < old ? 1u : 0u);
+    if (hi) atomicAdd(&sm_hot[HOT_SLOTS + slot], hi);
+}
+
 template <bool LIST>
-__device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32& u, u64 q, u64* sm_hot, u32& deg) {
+__device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32& u, u64 q, u32* sm_hot, u32& deg) {
     // `u` comes from push_idx: hub targets are encoded as HOT_BIT | slot.
     if (LIST) {
         if (u & HOT_BIT) u = __ldg(&A.hot_id[u & HOT_MASK]);
@@ -259,15 +379,15 @@ __device__ __forceinline__ bool relax_edge(const PushArgs& A, u64 rmax_fx, u32& 
         // dense frontiers: adds to hub vertices are accumulated per CTA in shared memory and flushed once
         // per phase -- same-address RED.64 serialises at ~0.7 ns in L2, and a hub receives up to
         // max-in-degree adds per iteration (scripts/microbench: 1/256 of the adds on one address costs 30 %)
-        if (u & HOT_BIT) atomicAdd((ull*)&sm_hot[u & HOT_MASK], (ull)q);
-        else atomicAdd((ull*)&A.r[u], (ull)q);  // result unused: compiles to RED.E.ADD.64
+        if (u & HOT_BIT) hot_add(sm_hot, u & HOT_MASK, q);
+        else red_add_u64(&A.r[u], q);
         return false;
     }
 }
 
 template <bool LIST>
 __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u64* sm_excl /*[warps][32]*/,
-                             u64* sm_beg, u64* sm_q, u64* sm_hot /*[HOT_SLOTS], all zero on entry and exit; unused when LIST*/) {
+                             u64* sm_beg, u64* sm_q, u32* sm_hot /*[2][HOT_SLOTS], all zero on entry and exit; unused when LIST*/) {
     PushCtl* ctl = A.ctl;
     const u64 pol_stream = l2_policy_evict_first();  // the edge array is streamed once per iteration: do not let it evict r[] / degrees
     const u64 staged = *(volatile u64*)&ctl->stage[par];
@@ -324,7 +444,8 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
         __syncwarp();
     }
 
-    // (2) long rows: one warp per PUSH_CHUNK-edge chunk, four independent edges per lane in flight
+    // (2) long rows: one warp per PUSH_CHUNK-edge chunk; SCAN mode keeps the whole chunk's ids in flight (PUSH_CHUNK / 32 = 8
+    // loads per lane, then 8 reductions), LIST mode four (the crossing test needs the ids, degrees and flags live)
     for (i64 c = gwarp; c < nch; c += nwarps) {
         uint2 desc = A.chunks[c];
         u64 pk = A.l_pack[desc.x];
@@ -333,6 +454,16 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
         u32 off = desc.y * PUSH_CHUNK;
         u32 len = min((u32)PUSH_CHUNK, d - off);
         const u32* row = A.push_idx + vtx_begin(pk) + off;
+        if (!LIST) {
+            u32 u[PUSH_CHUNK / 32];
+#pragma unroll
+            for (int k = 0; k < PUSH_CHUNK / 32; k++) { u32 e = 32 * k + lane; u[k] = e < len ? ld_hint_u32(&row[e], pol_stream) : 0xffffffffu; }
+#pragma unroll
+            for (int k = 0; k < PUSH_CHUNK / 32; k++) {
+                if (u[k] != 0xffffffffu) { if (u[k] & HOT_BIT) hot_add(sm_hot, u[k] & HOT_MASK, q); else red_add_u64(&A.r[u[k]], q); }
+            }
+            continue;
+        }
         for (u32 eb = 0; eb < len; eb += 128) {
             u32 u[4], dg[4];
             bool cr[4];
@@ -347,8 +478,8 @@ __device__ void push_phase_b(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, 
     if (!LIST && A.n_hot) {  // flush the CTA's hub accumulators (uniform: every thread of the CTA gets here)
         __syncthreads();
         for (u32 sl = threadIdx.x; sl < A.n_hot; sl += blockDim.x) {
-            u64 x = sm_hot[sl];
-            if (x) { atomicAdd((ull*)&A.r[__ldg(&A.hot_id[sl])], (ull)x); sm_hot[sl] = 0; }
+            const u64 x = ((u64)sm_hot[HOT_SLOTS + sl] << 32) | (u64)sm_hot[sl];
+            if (x) { red_add_u64(&A.r[__ldg(&A.hot_id[sl])], x); sm_hot[sl] = 0; sm_hot[HOT_SLOTS + sl] = 0; }
         }
         __syncthreads();
     }
@@ -469,7 +600,7 @@ __device__ __noinline__ void push_mini(const PushArgs& A, int par, u64 rmax_fx, 
                 if (e < t_d) {
                     int o = 0;
 #pragma unroll
-                    for (int s = PUSH_MINI_MAX / 2; s > 0; s >>= 1) { int p = o + s; if (m_excl[p] <= e) o = p; }
+                    for (int s = PUSH_MINI_POW2 / 2; s > 0; s >>= 1) { int p = o + s; if (p < PUSH_MINI_MAX && m_excl[p] <= e) o = p; }
                     u[k] = __ldg(&A.push_idx[m_beg[o] + e]);
                     qq[k] = m_q[o];
                 }
@@ -512,6 +643,47 @@ __device__ __noinline__ void push_mini(const PushArgs& A, int par, u64 rmax_fx, 
         ctl->iters += acc[0]; ctl->pushes += acc[1]; ctl->edges = acc[2]; ctl->reserve_total += acc[3];
         ctl->mini_par = (u32)par;
     }
+}
+
+// --------------------------------------------------------------------------------- the small regime
+// Frontiers between the single-CTA limit and (midi_v vertices, midi_e edges) are too big for one CTA and far too small
+// for 296: a grid-wide iteration costs ~30 us there, nearly all of it barrier and dependent-round-trip latency.  The
+// first K CTAs (one per SM) iterate them with a barrier among themselves (sub_sync, ~1.5 us) and hand frontiers that
+// shrink further to CTA 0's push_mini without leaving the regime; the other CTAs wait at the next grid barrier.  Same
+// phase functions, same schedule, same bits as the grid-wide iteration.
+__device__ void push_small(const PushArgs& A, int par, u64 rmax_fx, u32 K, u32& bar_target, u64* sm_excl, u64* sm_beg, u64* sm_q, u32* sm_hot,
+                           u64* sm_scan, u32* sm_mf, u32* sm_mctr, u32* sm_cnt) {
+    PushCtl* ctl = A.ctl;
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)K * blockDim.x;
+    for (;;) {
+        const u32 c = *(volatile u32*)&ctl->cnt[par];
+        const u64 ne = *(volatile u64*)&ctl->nedge[par];
+        if (c == 0) break;
+        if (A.mini && c <= PUSH_MINI_MAX && ne <= PUSH_MINI_EDGES) {
+            if (blockIdx.x == 0) push_mini(A, par, rmax_fx, sm_excl, sm_beg, sm_q, sm_scan, sm_mf, sm_mctr);
+            if (K > 1) sub_sync(&ctl->sub_bar, K, bar_target); else __syncthreads();
+            par = (int)*(volatile u32*)&ctl->mini_par;
+            continue;
+        }
+        if (K <= 1 || c > A.midi_v || ne > A.midi_e) break;
+        u64 t0 = 0, t1 = 0;
+        if (gtid == 0) t0 = globaltimer_ns();
+        push_phase_a_list(A, par, rmax_fx, gtid, gsize, sm_cnt);
+        sub_sync(&ctl->sub_bar, K, bar_target);
+        if (gtid == 0) t1 = globaltimer_ns();
+        push_phase_b<true>(A, par, rmax_fx, gtid, gsize, sm_excl, sm_beg, sm_q, sm_hot);
+        sub_sync(&ctl->sub_bar, K, bar_target);
+        if (gtid == 0) {
+            u32 k = ctl->dbg_count;
+            if (k < DBG_ITERS) {
+                u64* d = A.dbg + (size_t)k * DBG_FIELDS;
+                d[0] = t0; d[1] = t1; d[2] = globaltimer_ns(); d[3] = c; d[4] = ctl->edges; d[5] = 8;
+                ctl->dbg_count = k + 1;
+            }
+        }
+        par ^= 1;
+    }
+    if (gtid == 0) ctl->mini_par = (u32)par;
 }
 
 // --------------------------------------------------------------------------------- walk preparation (inside the cooperative kernel)
@@ -622,14 +794,16 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(c
     __shared__ u64 sm_beg[(PUSH_THREADS / 32) * 32];
     __shared__ u64 sm_q[(PUSH_THREADS / 32) * 32];
     __shared__ __align__(8) u32 sm_cnt[16];
-    __shared__ u64 sm_hot[HOT_SLOTS];
     __shared__ u64 sm_scan[64];
     __shared__ u32 sm_mf[PUSH_MINI_MAX];
     __shared__ u32 sm_mctr[2];
+    extern __shared__ __align__(16) u32 sm_hot[];   // [2][HOT_SLOTS]: low and high words of the per-CTA hub accumulators
     PushCtl* ctl = A.ctl;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 gsize = (i64)gridDim.x * blockDim.x;
-    for (u32 sl = threadIdx.x; sl < HOT_SLOTS; sl += blockDim.x) sm_hot[sl] = 0;
+    for (u32 sl = threadIdx.x; sl < 2 * HOT_SLOTS; sl += blockDim.x) sm_hot[sl] = 0;
+    u32 bar_target = 0;  // sub-grid barrier: arrivals expected at this thread's next sub_sync
+    const u32 K = (A.midi_ctas > 1 && (u32)A.midi_ctas <= gridDim.x) ? (u32)A.midi_ctas : 1u;
     __syncthreads();
 
     if (A.init) {
@@ -643,7 +817,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(c
         grid.sync();
     }
     if (gtid == 0) {
-        ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0;
+        ctl->rsum_fx = 0; ctl->N = 0; ctl->total_walks = 0; ctl->n_sources = 0; ctl->sub_bar = 0;
         if (!A.init) {  // top-k round: host supplied the round's rmax; counters of both parities must be clean
             ctl->cnt[0] = ctl->cnt[1] = 0; ctl->stage[0] = ctl->stage[1] = 0; ctl->dang[0] = ctl->dang[1] = 0; ctl->fcnt[0] = ctl->fcnt[1] = 0; ctl->fedges[0] = ctl->fedges[1] = 0; ctl->nedge[0] = ctl->nedge[1] = 0;
             ctl->rmax = A.rmax0; ctl->rmax_fx = rmax_to_fx_dev(A.rmax0, A.alpha_q64);
@@ -682,15 +856,17 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(c
             if (have_list) {
                 const u32 c = *(volatile u32*)&ctl->cnt[par];
                 if (c == 0) break;
-                if (A.mini && c <= PUSH_MINI_MAX && *(volatile u64*)&ctl->nedge[par] <= PUSH_MINI_EDGES) {
-                    if (blockIdx.x == 0) push_mini(A, par, rmax_fx, sm_excl, sm_beg, sm_q, sm_scan, sm_mf, sm_mctr);
+                const u64 ne = *(volatile u64*)&ctl->nedge[par];
+                const bool mini_ok = A.mini && c <= PUSH_MINI_MAX && ne <= PUSH_MINI_EDGES;
+                if (mini_ok || (K > 1 && c <= A.midi_v && ne <= A.midi_e)) {
+                    if (blockIdx.x < K) push_small(A, par, rmax_fx, K, bar_target, sm_excl, sm_beg, sm_q, sm_hot, sm_scan, sm_mf, sm_mctr, sm_cnt);
                     grid.sync();
                     par = (int)*(volatile u32*)&ctl->mini_par;
                     continue;
                 }
-                push_phase_a<false>(A, par, rmax_fx, gtid, gsize, sm_cnt);
+                push_phase_a_list(A, par, rmax_fx, gtid, gsize, sm_cnt);
             } else {
-                push_phase_a<true>(A, par, rmax_fx, gtid, gsize, sm_cnt);
+                push_sweep_warp(A, par, rmax_fx, gtid, gsize, sm_cnt);
             }
             grid.sync();
             const u32 fcnt = *(volatile u32*)&ctl->fcnt[par];
@@ -767,7 +943,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_step_scan(PushArgs A, int par)
 __global__ void __launch_bounds__(PUSH_THREADS) k_step_a(PushArgs A, int par) {
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
     __shared__ __align__(8) u32 sm_cnt[16];
-    push_phase_a<false>(A, par, A.ctl->rmax_fx, gtid, gsize, sm_cnt);
+    push_phase_a_list(A, par, A.ctl->rmax_fx, gtid, gsize, sm_cnt);
 }
 __global__ void __launch_bounds__(PUSH_THREADS) k_step_b(PushArgs A, int par) {
     __shared__ u64 sm_excl[(PUSH_THREADS / 32) * 32];

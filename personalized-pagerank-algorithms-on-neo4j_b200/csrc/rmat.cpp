@@ -7,7 +7,12 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/pprb200.h"
+#include "../../include/pprgen.h"
+
+// status codes of this small library (same values as pprb200.h)
+#define PPR_OK 0
+#define PPR_E_INVALID (-1)
+#define PPR_E_NOMEM (-3)
 
 typedef uint64_t u64;
 typedef int64_t i64;

@@ -67,9 +67,15 @@ __device__ __forceinline__ bool walk_step(WalkState& w, const u64* __restrict__ 
     return false;
 }
 
-__device__ __forceinline__ u64 mul_div_u64(u64 a, u64 b, u64 c) {  // floor(a*b/c) for a*b < 2^64 * c, c < 2^32
-    // a = walk total (< 2^40), b <= nshards or warp index (< 2^24): the product fits in 64 bits
-    return (a * b) / c;
+__device__ __forceinline__ u64 mul_div_u64(u64 a, u64 b, u64 c) {  // floor(a*b/c) for b <= c (the result fits in 64 bits), 128-bit product
+    const u64 hi = __umul64hi(a, b), lo = a * b;
+    if (hi == 0) return lo / c;
+    // long division of (hi:lo) by c, c < 2^32 in every caller (shard and warp counts): two 64/32 steps
+    u64 r = hi % c;                       // hi < c because a*b/c < 2^64
+    u64 q_hi = ((r << 32) | (lo >> 32)) / c;
+    r = ((r << 32) | (lo >> 32)) % c;
+    u64 q_lo = ((r << 32) | (lo & 0xffffffffull)) / c;
+    return (q_hi << 32) | q_lo;
 }
 
 // HINT: L2 eviction-priority hints (vertex records evict-last, neighbour sectors evict-first).  Worth 6 % of the
@@ -234,7 +240,7 @@ __global__ void k_mc_setup(u64* counts, i64 n, u32* ws_v, u64* ws_begin, u64* ws
 }
 __global__ void k_mc_dangling(u64* counts, PushCtl* ctl, i32 src, u64 W, u64 shard, u64 nshards) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && ctl->src_dangling) {
-        u64 lo = (W * shard) / nshards, hi = (W * (shard + 1)) / nshards;
+        u64 lo = mul_div_u64(W, shard, nshards), hi = mul_div_u64(W, shard + 1, nshards);
         counts[src] = hi - lo;
         ctl->walks_done = hi - lo;
     }

@@ -1,4 +1,4 @@
-"""A handful of FORA queries on one R-MAT graph (ncu target: short, one GPU)."""
+"""A handful of FORA queries from non-dangling sources on one R-MAT graph (ncu target: short, one GPU)."""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -9,19 +9,33 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_symbols():
-    text = open(os.path.join(ROOT, "include", "pprb200.h")).read()
+def header_symbols(name):
+    text = open(os.path.join(ROOT, "include", name)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ppr_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_every_declared_symbol_is_exported(pkg):
     L = pkg.load()
-    syms = header_symbols()
-    assert len(syms) >= 30
-    for s in syms:
+    syms, dbg = header_symbols("pprb200.h"), header_symbols("pprb200_debug.h")
+    assert len(syms) >= 40 and len(dbg) >= 8
+    for s in syms + dbg:
         assert hasattr(L, s), "libpprb200.so does not export " + s
-    assert sorted(pkg._native.EXPORTS) == syms
+    assert sorted(pkg._native.EXPORTS) == syms and sorted(pkg._native.DEBUG_EXPORTS) == dbg
+    # measurement / test hooks and the synthetic-input generator are not part of the product header
+    assert not set(syms) & set(dbg) and "ppr_rmat_generate" not in syms + dbg and not hasattr(L, "ppr_rmat_generate")
+    G = pkg._native.load_gen()
+    assert header_symbols("pprgen.h") == pkg._native.GEN_EXPORTS and hasattr(G, "ppr_rmat_generate")
+
+
+def test_library_does_not_link_nccl_or_the_oracle(pkg):
+    """NCCL is bound at run time (csrc/comm.hpp): single-GPU use must not need it, and a host process that already carries
+    an NCCL (PyTorch) must not get a second one."""
+    import subprocess
+    out = subprocess.run(["ldd", pkg._native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in out and "oracle" not in out
+    out = subprocess.run(["ldd", pkg._native.GEN_PATH], capture_output=True, text=True).stdout
+    assert "cuda" not in out and "pprb200" not in out
 
 
 def test_library_is_sm100a_cuda(pkg):
