@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--scale", type=int, default=22, help="R-MAT scale (BASELINE.json's metric is quoted on scale 22)")
     ap.add_argument("--edge-factor", type=int, default=16)
     ap.add_argument("--queries-per-step", type=int, default=50, help="GPU arm: sources per step (20 steps x 50 = 1000 timed queries)")
-    ap.add_argument("--ref-queries-per-step", type=int, default=0, help="reference arm: sources per step (0 = 3/8 of the host threads)")
+    ap.add_argument("--ref-queries-per-step", type=int, default=0, help="reference arm: sources per step (0 = host threads / 8)")
     ap.add_argument("--eps", type=float, default=EPS)
     ap.add_argument("--walk-cost", type=float, default=WALK_COST, help="push/walk balance constant (both arms)")
     ap.add_argument("--cpu-baseline", type=int, default=1)
@@ -146,8 +146,14 @@ def workload_config(args):
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path = oracle mode A (C++ port of the Java loops), all
-    host threads busy for the whole timed window.  Maps libpprgen.so (graph generator) and the oracle only."""
+    """--impl reference: the reference's CPU implementation of the path = oracle mode A (C++ port of the Java loops) on all
+    host threads.  Maps libpprgen.so (graph generator) and the oracle only.
+
+    One step = `q` sources of the GPU arm's source list (same seed, same order).  The (W + K) * q sources are drained in order
+    by a pool of host threads (one query per thread at a time, as many threads as cores).  `value` is the throughput of the
+    saturated pool: threads / (mean wall seconds of a timed query, measured on its thread while the other threads are busy
+    with their own queries).  Completion ORDER is not used: ~half of the sources have no out-edges and return at once, so
+    counting completions (the previous version of this arm) ended the window while the heavy queries were still running."""
     if rank != 0:
         return
     pkg = importlib.import_module(PKG)
@@ -157,56 +163,55 @@ def run_reference(args, rank, world):
     og = O.OGraph(rp, ci)
     n = 1 << args.scale
     threads = args.ref_threads or max(1, min(os.cpu_count() or 1, 64))
-    q = args.ref_queries_per_step or max(1, (3 * threads) // 8)
+    q = args.ref_queries_per_step or max(1, threads // 8)
     K, W = args.steps, args.warmup
     need = (K + W) * q
-    srcs = pick_sources(n, need + 4 * threads)   # same list as the GPU arm (a prefix of it) + spare work that keeps the pool busy
+    srcs = pick_sources(n, need)   # a prefix of the GPU arm's source list
     lock = threading.Lock()
-    state = {"next": 0, "done": 0, "t_start": None, "t_end": None, "edges": 0, "walks": 0, "pushes": 0, "nd": 0}
+    state = {"next": 0}
+    rec = [None] * need            # (seconds, stats, t_begin, t_end) per query
 
     def worker():
         while True:
             with lock:
                 i = state["next"]
-                if i >= len(srcs) or state["t_end"] is not None:
+                if i >= need:
                     return
                 state["next"] = i + 1
+            t0 = time.perf_counter()
             _, st = O.a_fora(og, int(srcs[i]), ALPHA, args.eps, 1000 + i, walk_cost=args.walk_cost)
-            now = time.perf_counter()
-            with lock:
-                state["done"] += 1
-                d = state["done"]
-                if state["t_start"] is not None and state["t_end"] is None:
-                    state["edges"] += st["edges"]; state["walks"] += st["walks"]; state["pushes"] += st["pushes"]
-                    state["nd"] += 1 if st["edges"] else 0
-                if d == W * q and state["t_start"] is None:
-                    state["t_start"] = now
-                if d == need:
-                    state["t_end"] = now
+            t1 = time.perf_counter()
+            rec[i] = (t1 - t0, st, t0, t1)
 
     t_all = time.perf_counter()
-    if W == 0:
-        state["t_start"] = t_all
     ths = [threading.Thread(target=worker) for _ in range(threads)]
     for th in ths:
         th.start()
     for th in ths:
         th.join()
-    el = (state["t_end"] or time.perf_counter()) - state["t_start"]
+    timed = rec[W * q:]
     nq = K * q
-    qps = nq / el
+    busy = sum(r[0] for r in timed)
+    qps = threads * nq / busy if busy > 0 else 0.0
+    window = max(r[3] for r in timed) - min(r[2] for r in timed)
+    nd = sum(1 for r in timed if r[1]["edges"])
+    heavy = [r[0] for r in timed if r[1]["edges"]]
     line = {
         "impl": "reference", "metric": "FORA SSPPR queries/s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": K, "warmup": W, "ms_per_step": el / K * 1e3, "higher_is_better": True,
+        "steps": K, "warmup": W, "ms_per_step": q / qps * 1e3 if qps else None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args), "queries_per_step": q, "oracle_pinned": False,
-        "work_per_query": {"edges": state["edges"] / nq, "walks": state["walks"] / nq, "pushes": state["pushes"] / nq,
-                           "non_dangling_fraction": state["nd"] / nq},
+        "config": workload_config(args), "queries_per_step": q, "timed_queries": nq, "oracle_pinned": False,
+        "work_per_query": {"edges": sum(r[1]["edges"] for r in timed) / nq, "walks": sum(r[1]["walks"] for r in timed) / nq,
+                           "pushes": sum(r[1]["pushes"] for r in timed) / nq, "non_dangling_fraction": nd / nq},
+        "seconds_per_query_with_out_edges": {"mean": float(np.mean(heavy)) if heavy else None, "max": float(np.max(heavy)) if heavy else None, "count": len(heavy)},
+        "wall_window": {"seconds": window, "queries_per_s": nq / window if window > 0 else None,
+                        "note": "first timed query started -> last timed query finished; threads idle towards the end of the list, so this is a lower bound"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": "%d sources per step (the first %d of the GPU arm's source list), drained by a pool of %d host threads that "
-                                   "stays busy across step boundaries; window = from the %d-th to the %d-th completed query. oracle mode A = C++ "
-                                   "restatement of the Java loops (array state instead of boxed HashMaps: faster than the Java); the Java/Neo4j "
-                                   "reference cannot run in this image (no JDK, J/Fora_Topk.java:136 does not compile)" % (q, need, threads, W * q, need)},
+                         "sample": "%d sources per step = sources %d..%d of the GPU arm's list, drained in order by a pool of %d host threads; value = threads / "
+                                   "mean wall seconds per timed query (saturated-pool throughput; sources without out-edges return at once and count as "
+                                   "queries on both arms). oracle mode A = C++ restatement of the Java loops (array state instead of boxed HashMaps: "
+                                   "faster than the Java); the Java/Neo4j reference cannot run in this image (no JDK, J/Fora_Topk.java:136 does not compile)"
+                                   % (q, W * q, need - 1, threads)},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
     }

@@ -1,0 +1,329 @@
+// bwdcta.cuh -- All-Pair-Backward-Search: one CTA per target, targets handed out by a ticket counter (sm_100a).
+//
+// Replaces the loop of Base_Whole_Graph.preprocessing (J/Base_Whole_Graph.java:76-92: one
+// Backward_Search.backward_search_whole_graph per target, J/Backward_Search.java:38-100) and the grouping of the
+// stored pairs by source (J/Base_Whole_Graph.java:83-87,112-163).
+//
+// Why not the grid-synchronous batch kernel of backward.cuh (kept for the single-target ppr_backward_search): with T
+// targets advancing in lock step every iteration pays two grid barriers, and the dense T x n residue matrix is far
+// larger than the L2, so every relaxed edge was a returning atomic into HBM (1.3-1.5e10 edges/s, 1.4-4.9 % of the HBM
+// roofline in round 1).  The n searches are independent, so here a CTA owns one search from seed to convergence:
+//   * iterations are synchronised with __syncthreads (a few us for the small frontiers that dominate at large
+//     thresholds), hundreds of searches are in flight, nothing waits for the slowest target of a batch;
+//   * the state of a search is sparse: dense rows r[n], reserve[n] exist per CTA *slot*, but only the entries a search
+//     touches are ever read, written or cleaned (touched / pushed lists), so the L2 holds the live sectors of all slots;
+//   * same synchronous schedule and the same 2^-62 fixed-point arithmetic as oracle mode B: iteration k pushes
+//     {v : r[v] > rmax} (strict, absolute: J/Backward_Search.java:89) simultaneously; integer adds commute, so the
+//     bits do not depend on which thread relaxes which edge.
+// Pairs (v, t, reserve >= threshold) are appended to one device array in arrival order with key = v << B | t and then
+// put into (source, target) order by an LSD radix sort written here (k_rs_*); row pointers come from the sorted keys.
+#pragma once
+#include "common.cuh"
+#include "push.cuh"
+
+struct BwdCtaArgs {
+    i64 n;
+    const u64* in_vtx; const i32* row_idx; const u64* invdeg;
+    // per-slot state (slot = blockIdx.x), all rows n entries long
+    u64* r; u64* reserve;       // dense rows, zero outside a search
+    u32* front;                 // [slots][2][n] frontier lists
+    u32* pushed;                // [slots][n] distinct vertices that were pushed (the only ones holding reserve)
+    u32* touched;               // [slots][n] vertices whose residue left zero (duplicates possible; overflow -> dense clean)
+    u64* st_pk; u64* st_y;      // [slots][n] staged (vertex record, y) of frontiers larger than one tile
+    u32* ticket;                // next target offset
+    i32 t_lo, t_hi;
+    u64 alpha_q64, rmax_fx, thr_fx;
+    int key_bits;               // B: key = v << B | t
+    u64* out_key; u64* out_val; i64 out_cap;
+    ull* counters;              // [0] pair cursor, [1] pushes, [2] edges, [3] iterations (summed over targets)
+};
+
+// append to a per-CTA list whose cursor lives in shared memory; the first `mirror_cap` entries are mirrored in shared memory
+__device__ __forceinline__ void cta_append(u32* list, u32* sm_cursor, bool pred, u32 value, u32* mirror, u32 mirror_cap, u32 cap, u32* sm_overflow) {
+    const u32 mask = __ballot_sync(0xffffffffu, pred);
+    if (mask) {
+        const u32 leader = __ffs(mask) - 1;
+        u32 base = 0;
+        if (lane_id() == leader) base = atomicAdd(sm_cursor, (u32)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pred) {
+            const u32 idx = base + __popc(mask & lanemask_lt());
+            if (idx < cap) list[idx] = value; else *sm_overflow = 1;
+            if (mirror && idx < mirror_cap) mirror[idx] = value;
+        }
+    }
+}
+
+template <int BD>
+__global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaArgs A) {
+    constexpr int LOG_BD = BD == 1024 ? 10 : BD == 512 ? 9 : BD == 256 ? 8 : BD == 128 ? 7 : 6;
+    __shared__ u64 m_excl[BD];
+    __shared__ u64 m_beg[BD];
+    __shared__ u64 m_y[BD];
+    __shared__ u32 mf[2][BD];          // mirrors of the first BD entries of the two frontier lists
+    __shared__ u64 scratch[64];
+    __shared__ u32 s_ticket, s_next, s_npushed, s_ntouched, s_overflow, s_outoff;
+    __shared__ ull s_outbase;
+    const u32 tid = threadIdx.x;
+    const i64 n = A.n;
+    const size_t slot = blockIdx.x;
+    u64* R = A.r + slot * (size_t)n;
+    u64* RES = A.reserve + slot * (size_t)n;
+    u32* F[2] = {A.front + slot * 2 * (size_t)n, A.front + (slot * 2 + 1) * (size_t)n};
+    u32* PUSHED = A.pushed + slot * (size_t)n;
+    u32* TOUCHED = A.touched + slot * (size_t)n;
+    u64* ST_PK = A.st_pk + slot * (size_t)n;
+    u64* ST_Y = A.st_y + slot * (size_t)n;
+    const u32 cap = (u32)n;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(A.ticket, 1u);
+        __syncthreads();
+        const i64 t = (i64)A.t_lo + (i64)s_ticket;
+        if (t >= (i64)A.t_hi) break;
+        const u64 pk_t = __ldg(&A.in_vtx[t]);
+        if (vtx_deg(pk_t) == 0) {   // J/Backward_Search.java:46-49: a target without in-edges answers {t: 1}
+            if (tid == 0 && FX_ONE >= A.thr_fx) {
+                const ull at = atomicAdd(&A.counters[0], 1ull);
+                if ((i64)at < A.out_cap) { A.out_key[at] = ((u64)t << A.key_bits) | (u64)t; A.out_val[at] = FX_ONE; }
+            }
+            continue;
+        }
+        if (tid == 0) {
+            R[t] = FX_ONE; mf[0][0] = (u32)t; F[0][0] = (u32)t; TOUCHED[0] = (u32)t;
+            s_ntouched = 1; s_npushed = 0; s_overflow = 0;
+        }
+        u32 cnt = 1;
+        int par = 0;
+        u64 acc_pushes = 0, acc_edges = 0, acc_iters = 0;   // thread 0
+        __syncthreads();
+        while (cnt) {
+            if (tid == 0) s_next = 0;
+            u32* next = F[par ^ 1];
+            u32* next_m = mf[par ^ 1];
+            // ---- phase A (J/Backward_Search.java:58-68): capture and zero the residue, move the alpha part to the reserve
+            const bool single = cnt <= (u32)BD;
+            u64 pk = 0, y = 0;
+            if (single) {
+                bool fresh = false;
+                u32 v = 0;
+                if (tid < cnt) {
+                    v = mf[par][tid];
+                    const u64 x = __ldcg(&R[v]);       // residues are updated by L2 atomics: never through L1
+                    R[v] = 0;
+                    const u64 a = mulhi64(x, A.alpha_q64);
+                    const u64 old = RES[v];
+                    RES[v] = old + a;
+                    fresh = old == 0;
+                    y = x - a;
+                    pk = __ldg(&A.in_vtx[v]);
+                }
+                cta_append(PUSHED, &s_npushed, fresh, v, nullptr, 0u, cap, &s_overflow);
+            } else {
+                for (u32 base = 0; base < cnt; base += BD) {
+                    const u32 i = base + tid;
+                    bool fresh = false;
+                    u32 v = 0;
+                    if (i < cnt) {
+                        v = F[par][i];
+                        const u64 x = __ldcg(&R[v]);
+                        R[v] = 0;
+                        const u64 a = mulhi64(x, A.alpha_q64);
+                        const u64 old = RES[v];
+                        RES[v] = old + a;
+                        fresh = old == 0;
+                        ST_PK[i] = __ldg(&A.in_vtx[v]);
+                        ST_Y[i] = x - a;
+                    }
+                    cta_append(PUSHED, &s_npushed, fresh, v, nullptr, 0u, cap, &s_overflow);
+                }
+            }
+            __syncthreads();   // every capture precedes every add of this iteration
+            // ---- phase B (J/Backward_Search.java:77-94): tiles of BD frontier vertices, threads sweep the concatenated in-edge lists
+            u64 it_edges = 0;
+            for (u32 base = 0; base < cnt; base += BD) {
+                if (!single) {
+                    const u32 i = base + tid;
+                    pk = i < cnt ? ST_PK[i] : 0;
+                    y = i < cnt ? ST_Y[i] : 0;
+                }
+                const u32 d = vtx_deg(pk);
+                u64 e_d, e_x, t_d, t_x;
+                block_excl_scan2((u64)d, 0ull, scratch, e_d, e_x, t_d, t_x);
+                m_excl[tid] = (base + tid < cnt) ? e_d : ~0ull;
+                m_beg[tid] = vtx_begin(pk) - e_d;   // edge address of concatenated position e is m_beg[owner] + e
+                m_y[tid] = y;
+                __syncthreads();
+                it_edges += t_d;
+                for (u64 eb = 0; eb < t_d; eb += 4 * BD) {
+                    u32 u[4];
+                    u64 inc[4], old[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const u64 e = eb + (u64)k * BD + tid;
+                        u[k] = 0xffffffffu; inc[k] = 0;
+                        if (e < t_d) {
+                            int o = 0;
+#pragma unroll
+                            for (int s = BD / 2; s > 0; s >>= 1) { const int p = o + s; if (m_excl[p] <= e) o = p; }
+                            u[k] = (u32)__ldg(&A.row_idx[m_beg[o] + e]);
+                            inc[k] = m_y[o];
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (u[k] != 0xffffffffu) inc[k] = mulhi64(inc[k], __ldg(&A.invdeg[u[k]]));   // (1-alpha) r(v) / d_out(u)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) old[k] = (u[k] != 0xffffffffu && inc[k]) ? atomicAdd((ull*)&R[u[k]], (ull)inc[k]) : 1ull;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const bool live = u[k] != 0xffffffffu && inc[k] != 0;
+                        cta_append(TOUCHED, &s_ntouched, live && old[k] == 0, u[k], nullptr, 0u, cap, &s_overflow);
+                        const bool cross = live && old[k] <= A.rmax_fx && old[k] + inc[k] > A.rmax_fx;   // strict r > rmax, exactly one add crosses
+                        cta_append(next, &s_next, cross, u[k], next_m, (u32)BD, cap, &s_overflow);
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) { acc_pushes += cnt; acc_edges += it_edges; acc_iters += 1; }
+            cnt = s_next;
+            par ^= 1;
+            __syncthreads();
+        }
+        // ---- output: pushed vertices with reserve >= threshold (J/Base_Whole_Graph.java:80-88); clean the slot
+        const u32 np = s_npushed;
+        u32 mine = 0;
+        for (u32 i = tid; i < np; i += BD) { const u64 x = RES[PUSHED[i]]; mine += (x != 0 && x >= A.thr_fx) ? 1u : 0u; }
+        const u64 total = block_sum_u64((u64)mine, scratch);
+        if (tid == 0) {
+            s_outbase = total ? atomicAdd(&A.counters[0], (ull)total) : 0ull;
+            s_outoff = 0;
+            atomicAdd(&A.counters[1], (ull)acc_pushes); atomicAdd(&A.counters[2], (ull)acc_edges); atomicAdd(&A.counters[3], (ull)acc_iters);
+        }
+        __syncthreads();
+        const ull obase = s_outbase;
+        const bool fits = (i64)(obase + total) <= A.out_cap;
+        for (u32 base = 0; base < np; base += BD) {
+            const u32 i = base + tid;
+            u32 v = 0; u64 x = 0;
+            if (i < np) { v = PUSHED[i]; x = RES[v]; RES[v] = 0; }
+            const bool has = x != 0 && x >= A.thr_fx;
+            const u32 mask = __ballot_sync(0xffffffffu, has);
+            if (mask) {
+                const u32 leader = __ffs(mask) - 1;
+                u32 off = 0;
+                if (lane_id() == leader) off = atomicAdd(&s_outoff, (u32)__popc(mask));
+                off = __shfl_sync(0xffffffffu, off, leader);
+                if (has && fits) {
+                    const ull at = obase + off + __popc(mask & lanemask_lt());
+                    A.out_key[at] = ((u64)v << A.key_bits) | (u64)t;
+                    A.out_val[at] = x;
+                }
+            }
+        }
+        if (s_overflow) { for (i64 v = tid; v < n; v += BD) R[v] = 0; }
+        else { const u32 nt = s_ntouched; for (u32 i = tid; i < nt; i += BD) R[TOUCHED[i]] = 0; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ LSD radix sort of (key, value) pairs
+// 8-bit digits; three kernels per pass: per-block digit histograms, one exclusive scan over (digit, block), stable
+// scatter (ranks inside a 256-item round from __match_any_sync + per-warp counts).
+#define RS_THREADS 256
+#define RS_ROUNDS 32
+#define RS_TILE (RS_THREADS * RS_ROUNDS)
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ keys, i64 count, int shift, u32* __restrict__ hist /*[256][nb]*/, u32 nb) {
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const i64 lo = (i64)blockIdx.x * RS_TILE, hi = min(count, lo + RS_TILE);
+    for (i64 i = lo + threadIdx.x; i < hi; i += RS_THREADS) atomicAdd(&h[(u32)(keys[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of `len` u32 counters in place (one CTA of 1024 threads, 4 per thread per step, running carry)
+__global__ void __launch_bounds__(1024) k_rs_scan(u32* __restrict__ a, i64 len) {
+    __shared__ u32 wsum[32];
+    __shared__ u32 carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (i64 base = 0; base < len; base += 4096) {
+        const i64 i0 = base + (i64)threadIdx.x * 4;
+        u32 x[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) x[k] = i0 + k < len ? a[i0 + k] : 0;
+        const u32 mine = x[0] + x[1] + x[2] + x[3];
+        u32 incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            u32 s = wsum[lane], si = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += t; }
+            wsum[lane] = si - s;   // exclusive over warps
+        }
+        __syncthreads();
+        u32 run = carry_s + wsum[w] + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { if (i0 + k < len) a[i0 + k] = run; run += x[k]; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = run;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64* __restrict__ keys, const u64* __restrict__ vals, i64 count, int shift,
+                                                           const u32* __restrict__ offs /*[256][nb] exclusive*/, u32 nb,
+                                                           u64* __restrict__ keys_out, u64* __restrict__ vals_out) {
+    __shared__ u32 run[256];                          // next output position of every digit for this block
+    __shared__ u32 wc[RS_THREADS / 32][256];          // per-warp digit counts of the current round
+    const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    run[tid] = offs[(size_t)tid * nb + blockIdx.x];
+    const i64 lo = (i64)blockIdx.x * RS_TILE, hi = min(count, lo + RS_TILE);
+    for (i64 base = lo; base < hi; base += RS_THREADS) {
+#pragma unroll
+        for (int k = 0; k < RS_THREADS / 32; k++) wc[k][tid] = 0;
+        __syncthreads();
+        const i64 i = base + tid;
+        const bool ok = i < hi;
+        u64 key = 0, val = 0;
+        if (ok) { key = keys[i]; val = vals[i]; }
+        const u32 dg = ok ? ((u32)(key >> shift) & 255u) : 256u + lane;   // idle lanes never match each other or a digit
+        const u32 peers = __match_any_sync(0xffffffffu, dg);
+        const u32 rank = __popc(peers & lanemask_lt());
+        if (ok && rank == 0) wc[w][dg] = __popc(peers);
+        __syncthreads();
+        if (ok) {
+            u32 pos = run[dg] + rank;
+            for (u32 k = 0; k < w; k++) pos += wc[k][dg];
+            keys_out[pos] = key; vals_out[pos] = val;
+        }
+        __syncthreads();
+        {
+            u32 s = 0;
+#pragma unroll
+            for (int k = 0; k < RS_THREADS / 32; k++) s += wc[k][tid];
+            run[tid] += s;
+        }
+        __syncthreads();
+    }
+}
+
+// sorted keys -> targets and the row pointers of the index grouped by source (J/Base_Whole_Graph.java:83-87)
+__global__ void k_rs_rows(const u64* __restrict__ keys, i64 count, int key_bits, i64 n, i32* __restrict__ tgt, i64* __restrict__ src_ptr) {
+    const i64 gsize = (i64)gridDim.x * blockDim.x;
+    const u64 mask = (1ull << key_bits) - 1;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gsize) {
+        const u64 k = keys[i];
+        const i64 v = (i64)(k >> key_bits);
+        tgt[i] = (i32)(k & mask);
+        const i64 vp = i ? (i64)(keys[i - 1] >> key_bits) : -1;
+        for (i64 x = vp + 1; x <= v; x++) src_ptr[x] = i;
+        if (i == count - 1) for (i64 x = v + 1; x <= n; x++) src_ptr[x] = count;
+    }
+}

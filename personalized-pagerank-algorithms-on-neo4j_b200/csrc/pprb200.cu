@@ -21,6 +21,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "backward.cuh"
+#include "bwdcta.cuh"
 #include "comm.hpp"
 #include "common.cuh"
 #include "../../include/pprb200_debug.h"
@@ -313,19 +314,64 @@ static void bws_free(BwdWorkspace& b) {
     cudaFree(b.chunks); cudaFree(b.out_v); cudaFree(b.out_t); cudaFree(b.out_val);
     memset(&b, 0, sizeof b);
 }
-static int32_t bws_alloc(ppr_ctx* ctx, BwdWorkspace& b, i32 T, i64 n) {
+static int32_t bws_alloc(ppr_ctx* ctx, BwdWorkspace& b, i32 T, i64 n, i64 chunks_per_target) {
     memset(&b, 0, sizeof b);
     b.T = T; b.n = n;
     size_t tn = (size_t)T * (size_t)n;
     b.front_cap = (i64)std::min<size_t>(tn, (size_t)1 << 24);
-    b.chunk_cap = (i64)std::min<size_t>(tn, (size_t)1 << 24);
+    // one iteration of one target can stage ceil(indeg / PUSH_CHUNK) descriptors for every long row of the graph
+    // (chunks_per_target, from the in-degree histogram at export): dense graphs need more than T * n of them
+    b.chunk_cap = (i64)std::max<size_t>(std::min<size_t>((size_t)T * (size_t)std::max<i64>(chunks_per_target, 1), (size_t)1 << 26), (size_t)std::max<i64>(chunks_per_target, 1));
+    b.chunk_cap = std::max<i64>(b.chunk_cap, (i64)std::min<size_t>(tn, (size_t)1 << 24));
     b.out_cap = (i64)std::min<size_t>(tn, (size_t)1 << 25);
     CUDA_TRY(dalloc(&b.r, tn)); CUDA_TRY(dalloc(&b.reserve, tn));
     CUDA_TRY(dalloc(&b.front[0], (size_t)b.front_cap)); CUDA_TRY(dalloc(&b.front[1], (size_t)b.front_cap));
     CUDA_TRY(dalloc(&b.s_pack, (size_t)b.front_cap)); CUDA_TRY(dalloc(&b.s_y, (size_t)b.front_cap)); CUDA_TRY(dalloc(&b.s_t, (size_t)b.front_cap));
-    CUDA_TRY(dalloc(&b.l_pack, (size_t)b.front_cap)); CUDA_TRY(dalloc(&b.l_y, (size_t)b.front_cap)); CUDA_TRY(dalloc(&b.l_t, (size_t)b.front_cap));
+    CUDA_TRY(dalloc(&b.l_pack, (size_t)b.chunk_cap)); CUDA_TRY(dalloc(&b.l_y, (size_t)b.chunk_cap)); CUDA_TRY(dalloc(&b.l_t, (size_t)b.chunk_cap));   // indexed by a long row's first chunk slot
     CUDA_TRY(dalloc(&b.chunks, (size_t)b.chunk_cap));
     CUDA_TRY(dalloc(&b.out_v, (size_t)b.out_cap)); CUDA_TRY(dalloc(&b.out_t, (size_t)b.out_cap)); CUDA_TRY(dalloc(&b.out_val, (size_t)b.out_cap));
+    return PPR_OK;
+}
+
+// workspace of the CTA-per-target reverse push (bwdcta.cuh): per-slot rows + the growing pair buffers
+struct BwdCtaWorkspace {
+    int slots, bd; i64 n;
+    u64* r; u64* reserve; u32* front; u32* pushed; u32* touched; u64* st_pk; u64* st_y;
+    u32* ticket; ull* counters;
+    u64* key[2]; u64* val[2]; i64 cap;     // pairs (double-buffered for the radix sort)
+    u32* hist; size_t hist_len;
+};
+static void bcw_free(BwdCtaWorkspace& b) {
+    cudaFree(b.r); cudaFree(b.reserve); cudaFree(b.front); cudaFree(b.pushed); cudaFree(b.touched); cudaFree(b.st_pk); cudaFree(b.st_y);
+    cudaFree(b.ticket); cudaFree(b.counters); cudaFree(b.key[0]); cudaFree(b.key[1]); cudaFree(b.val[0]); cudaFree(b.val[1]); cudaFree(b.hist);
+    memset(&b, 0, sizeof b);
+}
+static int32_t bcw_alloc(ppr_ctx* ctx, BwdCtaWorkspace& b, int slots, int bd, i64 n) {
+    memset(&b, 0, sizeof b);
+    b.slots = slots; b.bd = bd; b.n = n;
+    const size_t sn = (size_t)slots * (size_t)n;
+    CUDA_TRY(dalloc(&b.r, sn)); CUDA_TRY(dalloc(&b.reserve, sn)); CUDA_TRY(dalloc(&b.front, 2 * sn));
+    CUDA_TRY(dalloc(&b.pushed, sn)); CUDA_TRY(dalloc(&b.touched, sn)); CUDA_TRY(dalloc(&b.st_pk, sn)); CUDA_TRY(dalloc(&b.st_y, sn));
+    CUDA_TRY(dalloc(&b.ticket, 1)); CUDA_TRY(dalloc(&b.counters, 8));
+    CUDA_TRY(cudaMemsetAsync(b.r, 0, sn * 8, ctx->stream));          // rows are zero outside a search; every search cleans up after itself
+    CUDA_TRY(cudaMemsetAsync(b.reserve, 0, sn * 8, ctx->stream));
+    return PPR_OK;
+}
+static int32_t bcw_reserve_pairs(ppr_ctx* ctx, BwdCtaWorkspace& b, i64 need, i64 keep) {   // grow the pair buffers, keeping the first `keep` pairs of buffer 0
+    if (need <= b.cap) return PPR_OK;
+    const i64 cap = std::max<i64>(need, b.cap + b.cap / 2);
+    u64 *k0 = nullptr, *v0 = nullptr, *k1 = nullptr, *v1 = nullptr;
+    cudaFree(b.key[1]); cudaFree(b.val[1]); b.key[1] = nullptr; b.val[1] = nullptr;
+    CUDA_TRY(dalloc(&k0, (size_t)cap)); CUDA_TRY(dalloc(&v0, (size_t)cap));
+    if (keep > 0) {
+        CUDA_TRY(cudaMemcpyAsync(k0, b.key[0], (size_t)keep * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(v0, b.val[0], (size_t)keep * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(b.key[0]); cudaFree(b.val[0]);
+    b.key[0] = k0; b.val[0] = v0;
+    CUDA_TRY(dalloc(&k1, (size_t)cap)); CUDA_TRY(dalloc(&v1, (size_t)cap));
+    b.key[1] = k1; b.val[1] = v1; b.cap = cap;
     return PPR_OK;
 }
 
@@ -333,6 +379,7 @@ static int32_t bws_alloc(ppr_ctx* ctx, BwdWorkspace& b, i32 T, i64 n) {
 struct GraphExtra {  // host-side bookkeeping kept beside ppr_graph
     bool ws1_ready;
     BwdWorkspace bws; bool bws_ready;
+    BwdCtaWorkspace bcw; bool bcw_ready;
     int walk_blocks;
     double last_divisor;
     // ppr_fora_batch: events and the pinned control-block snapshots are created once and reused by every call
@@ -360,6 +407,7 @@ extern "C" int32_t ppr_graph_destroy(ppr_graph* g) {
     ws_free(g->ws[0]);
     if (x && x->ws1_ready) ws_free(g->ws[1]);
     if (x && x->bws_ready) bws_free(x->bws);
+    if (x && x->bcw_ready) bcw_free(x->bcw);
     if (x) {
         for (auto& e : x->batch_ev) cudaEventDestroy(e);
         if (x->batch_ev_ready) for (int i = 0; i < 2; i++) { cudaEventDestroy(x->done_ev[i]); cudaEventDestroy(x->copied_ev[i]); }
@@ -397,6 +445,7 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     memset(&g->d, 0, sizeof g->d); memset(g->ws, 0, sizeof g->ws);
     g->ctx = ctx; g->last_ws = 0; g->last_kind = 0; g->trace_active = false;
     x->ws1_ready = false; x->bws_ready = false; x->walk_blocks = 0; x->last_divisor = 0.0; memset(&x->bws, 0, sizeof x->bws);
+    x->bcw_ready = false; memset(&x->bcw, 0, sizeof x->bcw);
     x->batch_ev_ready = false; x->snaps = nullptr; x->snaps_cap = 0; x->bwd_chunks_per_target = 1;
     { std::lock_guard<std::mutex> lk(g_extras_mu); g_extras.push_back(std::make_pair(g, x)); }
     g->d.n = n; g->d.m = m;
@@ -463,6 +512,9 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
         std::vector<std::pair<i64, i32>> cand;
         const i64 min_in = std::max<i64>(1, ctx->hot_min_indeg);
         for (i64 v = 0; v < n; v++) { i64 d = (i64)h_indeg[(size_t)v]; if (d >= min_in) cand.push_back(std::make_pair(-d, (i32)v)); }
+        i64 bch = 1;
+        for (i64 v = 0; v < n; v++) { i64 d = (i64)h_indeg[(size_t)v]; if (d > PUSH_SMALL_MAX) bch += (d + PUSH_CHUNK - 1) / PUSH_CHUNK; }
+        x->bwd_chunks_per_target = bch;
         size_t keep = std::min<size_t>(cand.size(), HOT_SLOTS);
         std::partial_sort(cand.begin(), cand.begin() + keep, cand.end());
         for (size_t k = 0; k < keep; k++) hot_id.push_back((u32)cand[k].second);
@@ -1257,7 +1309,7 @@ static int32_t bwd_ensure(ppr_graph* g, i32 T) {
     GraphExtra* x = extra_of(g);
     if (x->bws_ready && x->bws.T >= T) return PPR_OK;
     if (x->bws_ready) { bws_free(x->bws); x->bws_ready = false; }
-    int32_t rc = bws_alloc(g->ctx, x->bws, T, g->d.n);
+    int32_t rc = bws_alloc(g->ctx, x->bws, T, g->d.n, x->bwd_chunks_per_target);
     if (rc) { bws_free(x->bws); return rc; }
     x->bws_ready = true;
     return PPR_OK;
@@ -1296,6 +1348,83 @@ extern "C" int32_t ppr_backward_search(ppr_graph* g, int32_t target, double alph
 
 static void apply_topk_rows(ppr_pairs* P, int32_t k);
 
+// Launch configuration of k_bwd_cta: CTA size and CTAs per SM.  Cheap searches (large thresholds: a few thousand relaxed
+// edges, frontiers of a few dozen vertices) are latency chains -- many small CTAs; expensive ones want wide CTAs.
+// The first launch of a call probes with 256 x 4; PPR_BWD_BD / PPR_BWD_CPS override (tuning).
+template <int BD>
+static cudaError_t launch_bwd_cta(const BwdCtaArgs& A, int slots, cudaStream_t st) {
+    k_bwd_cta<BD><<<slots, BD, 0, st>>>(A);
+    return cudaGetLastError();
+}
+static cudaError_t launch_bwd_cta_bd(int bd, const BwdCtaArgs& A, int slots, cudaStream_t st) {
+    switch (bd) {
+        case 64: return launch_bwd_cta<64>(A, slots, st);
+        case 128: return launch_bwd_cta<128>(A, slots, st);
+        case 256: return launch_bwd_cta<256>(A, slots, st);
+        case 512: return launch_bwd_cta<512>(A, slots, st);
+        default: return launch_bwd_cta<1024>(A, slots, st);
+    }
+}
+static void bwd_cta_config(ppr_ctx* ctx, double edges_per_target, int* bd, int* cps) {
+    if (edges_per_target < 0) { *bd = 256; *cps = 4; }                 // probe
+    else if (edges_per_target < 16384.0) { *bd = 128; *cps = 12; }
+    else if (edges_per_target < 131072.0) { *bd = 256; *cps = 6; }
+    else { *bd = 512; *cps = 3; }
+    const char* e;
+    if ((e = getenv("PPR_BWD_BD"))) { int v = atoi(e); if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) *bd = v; }
+    if ((e = getenv("PPR_BWD_CPS"))) { int v = atoi(e); if (v >= 1 && v <= 32) *cps = v; }
+    *cps = std::min(*cps, 2048 / *bd);
+    int occ = 0;   // CTAs beyond what is resident would only queue (and cost 48 n bytes of slot state each)
+    cudaError_t e2 = cudaSuccess;
+    switch (*bd) {
+        case 64: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<64>, 64, 0); break;
+        case 128: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<128>, 128, 0); break;
+        case 256: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<256>, 256, 0); break;
+        case 512: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<512>, 512, 0); break;
+        default: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<1024>, 1024, 0); break;
+    }
+    if (e2 == cudaSuccess && occ >= 1) *cps = std::min(*cps, occ);
+}
+static int32_t bcw_ensure(ppr_graph* g, int slots, int bd) {
+    GraphExtra* x = extra_of(g);
+    if (x->bcw_ready && x->bcw.slots >= slots) { x->bcw.bd = bd; return PPR_OK; }
+    u64* key[2] = {nullptr, nullptr}; u64* val[2] = {nullptr, nullptr}; i64 cap = 0; u32* hist = nullptr; size_t hist_len = 0;
+    if (x->bcw_ready) {   // keep the pair buffers: they may already hold the pairs of earlier launches of this call
+        for (int i = 0; i < 2; i++) { key[i] = x->bcw.key[i]; val[i] = x->bcw.val[i]; x->bcw.key[i] = nullptr; x->bcw.val[i] = nullptr; }
+        cap = x->bcw.cap; hist = x->bcw.hist; hist_len = x->bcw.hist_len; x->bcw.hist = nullptr;
+        bcw_free(x->bcw); x->bcw_ready = false;
+    }
+    int32_t rc = bcw_alloc(g->ctx, x->bcw, slots, bd, g->d.n);
+    for (int i = 0; i < 2; i++) { x->bcw.key[i] = key[i]; x->bcw.val[i] = val[i]; }
+    x->bcw.cap = cap; x->bcw.hist = hist; x->bcw.hist_len = hist_len;
+    if (rc) { bcw_free(x->bcw); return rc; }
+    x->bcw_ready = true;
+    return PPR_OK;
+}
+
+// (source, target) order of the pair buffer: LSD radix sort over the 2 * key_bits key bits, then targets + row pointers
+static int32_t sort_pairs(ppr_ctx* ctx, BwdCtaWorkspace& b, i64 count, int key_bits, i64 n, i32* d_tgt, i64* d_ptr, int* result_buf) {
+    int cur = 0;
+    if (count > 0) {
+        const u32 nb = (u32)((count + RS_TILE - 1) / RS_TILE);
+        const size_t need = (size_t)256 * nb;
+        if (b.hist_len < need) { cudaFree(b.hist); b.hist = nullptr; b.hist_len = 0; CUDA_TRY(dalloc(&b.hist, need)); b.hist_len = need; }
+        for (int shift = 0; shift < 2 * key_bits; shift += 8) {
+            k_rs_hist<<<nb, RS_THREADS, 0, ctx->stream>>>(b.key[cur], count, shift, b.hist, nb);
+            k_rs_scan<<<1, 1024, 0, ctx->stream>>>(b.hist, (i64)need);
+            k_rs_scatter<<<nb, RS_THREADS, 0, ctx->stream>>>(b.key[cur], b.val[cur], count, shift, b.hist, nb, b.key[cur ^ 1], b.val[cur ^ 1]);
+            CUDA_TRY(cudaGetLastError());
+            cur ^= 1;
+        }
+        k_rs_rows<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b.key[cur], count, key_bits, n, d_tgt, d_ptr);
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        CUDA_TRY(cudaMemsetAsync(d_ptr, 0, ((size_t)n + 1) * 8, ctx->stream));
+    }
+    *result_buf = cur;
+    return PPR_OK;
+}
+
 extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double threshold, int32_t k, int32_t t_lo, int32_t t_hi,
                                           ppr_pairs** out, ppr_stats* stats) {
     if (!g) return PPR_E_INVALID;
@@ -1307,115 +1436,105 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     if (t_lo < 0 || t_hi > n || t_lo > t_hi) return ctx_fail(ctx, PPR_E_INVALID, "ppr_backward_all_pairs: bad target range");
     cudaSetDevice(ctx->device);
     g->trace_active = false;
-    // batch size: dense per-target state is 16 n bytes; stay within a quarter of the free memory and 8 GB
     StageTimer tm;
+    GraphExtra* x = extra_of(g);
+    int key_bits = 1;
+    while (key_bits < 31 && ((i64)1 << key_bits) < n) key_bits++;
+
+    BwdCtaArgs A;
+    memset(&A, 0, sizeof A);
+    A.n = n; A.in_vtx = g->d.in_vtx; A.row_idx = g->d.row_idx; A.invdeg = g->d.invdeg;
+    A.alpha_q64 = h_alpha_q64(alpha);
+    // J/Backward_Search.java:89 (r > rmax) and J/Base_Whole_Graph.java:83 (pi >= threshold), in fixed point
+    {
+        const double fl = threshold > 0 ? std::floor(threshold * FX_SCALE) : 0.0, cl = threshold > 0 ? std::ceil(threshold * FX_SCALE) : 0.0;
+        A.rmax_fx = fl >= 18446744073709551615.0 ? ~0ull : (u64)fl;
+        A.rmax_fx = std::max<u64>(A.rmax_fx, ~0ull / A.alpha_q64 + 2);   // floor: a push must move >= 1 unit into the reserve
+        A.thr_fx = cl >= 18446744073709551615.0 ? ~0ull : (u64)cl;
+    }
+    A.key_bits = key_bits;
+
+    // per-slot state is 48 n bytes; stay within half of the free memory
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    tm.mark("cudaMemGetInfo");
-    size_t budget = std::min<size_t>(free_b / 4, (size_t)8 << 30);
-    i64 T = (i64)std::max<size_t>(1, budget / ((size_t)16 * (size_t)n));
-    T = std::min<i64>(T, 4096);
-    // Keep the batch's residue matrix (8 n bytes per target) around the size of the L2: the returning atomics of
-    // the reverse push run ~5x faster on an L2-resident vector (scripts/microbench), which outweighs the
-    // extra launches of smaller batches.
-    if (ctx->bwd_batch > 0) T = std::min<i64>(T, ctx->bwd_batch);
-    else T = std::min<i64>(T, std::max<i64>(32, ((i64)768 << 20) / (8 * n)));
-    T = std::min<i64>(T, std::max<i64>(1, t_hi - t_lo));
-    int32_t rc = bwd_ensure(g, (i32)T); if (rc) return rc;
-    tm.mark("workspace");
-    BwdWorkspace& b = extra_of(g)->bws;
-    T = std::min<i64>(T, b.T);
-    std::vector<u32> hv, ht; std::vector<u64> hval;
+    if (x->bcw_ready) free_b += (size_t)x->bcw.slots * (size_t)n * 48;
+    const i64 max_slots = (i64)std::max<size_t>(1, (free_b / 2) / ((size_t)48 * (size_t)n));
     i64 pushes = 0, edges = 0, iters = 0;
     int launches = 0;
+    i64 cursor = 0;                     // pairs accepted so far (device buffer 0)
+    double edges_per_target = -1.0;
     CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-    i64 curT = T;
-    bool adapted = false;
     for (i64 t0 = t_lo; t0 < t_hi;) {
-        i64 Tb = std::min<i64>(curT, t_hi - t0);
-        PushCtl h;
-        rc = bwd_run_batch(g, b, (i32)t0, (i32)Tb, alpha, threshold, &h); if (rc) return rc;
-        launches++;
-        tm.mark("batch kernel + sync");
-        if (h.err || h.err_a || h.pairs_needed > (u64)b.out_cap) {  // frontier or output overflow: rerun with fewer targets
-            if (Tb == 1) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_backward_all_pairs: a single target overflows the batch buffers");
-            curT = std::max<i64>(1, Tb / 2);
-            continue;
-        }
-        pushes += (i64)h.pushes; edges += (i64)h.edges; iters += (i64)h.iters;
-        size_t cnt = (size_t)h.pairs;
-        if (cnt) {   // download straight into the tail of the host arrays
-            size_t old = hv.size();
-            try {
-                if (hv.capacity() < old + cnt) { size_t cap = std::max(old + cnt, old * 2); hv.reserve(cap); ht.reserve(cap); hval.reserve(cap); }
-                hv.resize(old + cnt); ht.resize(old + cnt); hval.resize(old + cnt);
-            } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
-            CUDA_TRY(cudaMemcpyAsync(hv.data() + old, b.out_v, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaMemcpyAsync(ht.data() + old, b.out_t, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaMemcpyAsync(hval.data() + old, b.out_val, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        int bd, cps;
+        bwd_cta_config(ctx, edges_per_target, &bd, &cps);
+        const i64 remaining = t_hi - t0;
+        i64 Tb = remaining;
+        if (ctx->bwd_batch > 0) Tb = std::min<i64>(Tb, ctx->bwd_batch);
+        else if (edges_per_target < 0) Tb = std::min<i64>(Tb, std::max<i64>(1024, (i64)ctx->sm_count * 8));   // probe launch
+        const int slots = (int)std::max<i64>(1, std::min<i64>(std::min<i64>((i64)ctx->sm_count * cps, max_slots), Tb));
+        int32_t rc = bcw_ensure(g, slots, bd); if (rc) return rc;
+        BwdCtaWorkspace& b = x->bcw;
+        // room for this launch's pairs: estimate from what has been seen, retry with the exact need on overflow
+        i64 want = cursor + (launches ? (i64)((double)cursor / (double)(t0 - t_lo) * (double)Tb * 1.25) + 65536 : std::max<i64>((i64)1 << 22, Tb * 64));
+        rc = bcw_reserve_pairs(ctx, b, want, cursor); if (rc) return rc;
+        for (;;) {
+            ull h_cnt[4] = {(ull)cursor, (ull)pushes, (ull)edges, (ull)iters};
+            CUDA_TRY(cudaMemcpyAsync(b.counters, h_cnt, sizeof h_cnt, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(b.ticket, 0, 4, ctx->stream));
+            A.r = b.r; A.reserve = b.reserve; A.front = b.front; A.pushed = b.pushed; A.touched = b.touched; A.st_pk = b.st_pk; A.st_y = b.st_y;
+            A.ticket = b.ticket; A.counters = b.counters; A.t_lo = (i32)t0; A.t_hi = (i32)(t0 + Tb);
+            A.out_key = b.key[0]; A.out_val = b.val[0]; A.out_cap = b.cap;
+            CUDA_TRY(launch_bwd_cta_bd(bd, A, slots, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(h_cnt, b.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            tm.mark("download");
-        }
-        if (!adapted && ctx->bwd_batch <= 0 && Tb == curT) {
-            // (after the download: growing reallocates the batch buffers)
-            // cheap targets (large thresholds: a few thousand edges each) are bound by the per-iteration cost of a batch,
-            // not by its atomics: quadruple the batch for them (scripts/sweep_bwd.py: 3.6e9 -> 5.5e9 edges/s at 1e-3,
-            // but 1.5e10 -> 1.3e10 at 5e-5, hence the test on the work per target)
-            adapted = true;
-            const i64 Tmax = std::min<i64>(4096, (i64)std::max<size_t>(1, budget / ((size_t)16 * (size_t)n)));
-            if ((double)h.edges / (double)Tb < 65536.0 && Tmax > curT && t_hi - (t0 + Tb) > curT) {
-                rc = bwd_ensure(g, (i32)Tmax); if (rc) return rc;
-                curT = std::min<i64>(Tmax, b.T);
+            launches++;
+            if ((i64)h_cnt[0] > b.cap) {   // pair buffer too small: the searches are deterministic, run the launch again with room
+                rc = bcw_reserve_pairs(ctx, b, (i64)h_cnt[0] + 65536, cursor); if (rc) return rc;
+                continue;
             }
+            cursor = (i64)h_cnt[0]; pushes = (i64)h_cnt[1]; edges = (i64)h_cnt[2]; iters = (i64)h_cnt[3];
+            break;
         }
+        tm.mark("reverse-push launch");
         t0 += Tb;
+        edges_per_target = (double)edges / (double)(t0 - t_lo);
     }
     CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    tm.mark("final sync");
-    // inverted index grouped by source v (J/Base_Whole_Graph.java:83-87): stable counting sort keeps targets ascending
+    if (cursor > 0xffffffffll) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_backward_all_pairs: more than 2^32 pairs in one call; split the target range");
+    // inverted index grouped by source v, targets ascending (J/Base_Whole_Graph.java:83-87): device radix sort + row pointers
     ppr_pairs* P = new (std::nothrow) ppr_pairs();
     if (!P) return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed");
     P->n = n;
-    try {
-        // stable counting sort by source, parallel over contiguous chunks of the (target-ordered) pair list:
-        // per-chunk histograms -> per-(source, chunk) start offsets -> independent scatters
-        const size_t np = hv.size();
-        unsigned hw = std::thread::hardware_concurrency();
-        int nt = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
-        while (nt > 1 && ((size_t)n * nt > ((size_t)64 << 20) || np < ((size_t)1 << 18))) nt /= 2;
-        std::vector<u32> hist((size_t)n * nt, 0);
-        auto chunk = [&](int c, size_t& lo, size_t& hi) { lo = np * (size_t)c / nt; hi = np * (size_t)(c + 1) / nt; };
-        auto run = [&](auto fn) {
-            std::vector<std::thread> th;
-            for (int c = 1; c < nt; c++) th.emplace_back(fn, c);
-            fn(0);
-            for (auto& t : th) t.join();
-        };
-        run([&](int c) { size_t lo, hi; chunk(c, lo, hi); u32* h = hist.data() + (size_t)c * n; for (size_t i = lo; i < hi; i++) h[hv[i]]++; });
-        P->src_ptr.assign((size_t)n + 1, 0);
-        {
-            i64 acc = 0;
-            for (i64 v = 0; v < n; v++) {
-                P->src_ptr[(size_t)v] = acc;
-                for (int c = 0; c < nt; c++) { u32 cnt = hist[(size_t)c * n + v]; hist[(size_t)c * n + v] = (u32)(acc - P->src_ptr[(size_t)v]); acc += cnt; }
-            }
-            P->src_ptr[(size_t)n] = acc;
-        }
-        P->tgt.resize(np); P->val.resize(np);
-        run([&](int c) {
-            size_t lo, hi; chunk(c, lo, hi);
-            u32* h = hist.data() + (size_t)c * n;   // now: offset of this chunk's next entry inside row v
-            for (size_t i = lo; i < hi; i++) { u32 v = hv[i]; size_t p = (size_t)P->src_ptr[v] + h[v]++; P->tgt[p] = (i32)ht[i]; P->val[p] = hval[i]; }
-        });
-        if (k >= 0) apply_topk_rows(P, k);
-    } catch (...) { delete P; return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
-    tm.mark("group by source");
+    i32* d_tgt = nullptr; i64* d_ptr = nullptr;
+    auto fail = [&](int32_t code) { cudaFree(d_tgt); cudaFree(d_ptr); delete P; return code; };
+    try { P->src_ptr.assign((size_t)n + 1, 0); P->tgt.resize((size_t)cursor); P->val.resize((size_t)cursor); }
+    catch (...) { return fail(ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed")); }
+#define P_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail(ctx_fail_cuda(ctx, e__, #expr, __FILE__, __LINE__)); } while (0)
+    if (!x->bcw_ready) { int32_t rc = bcw_ensure(g, 1, 256); if (rc) return fail(rc); }   // empty target range: nothing was launched
+    BwdCtaWorkspace& b = x->bcw;
+    P_TRY(dalloc(&d_tgt, (size_t)cursor)); P_TRY(dalloc(&d_ptr, (size_t)n + 1));
+    int buf = 0;
+    { int32_t rc = sort_pairs(ctx, b, cursor, key_bits, n, d_tgt, d_ptr, &buf); if (rc) return fail(rc); }
+    P_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    P_TRY(cudaMemcpyAsync(P->src_ptr.data(), d_ptr, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cursor) {
+        P_TRY(cudaMemcpyAsync(P->tgt.data(), d_tgt, (size_t)cursor * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        P_TRY(cudaMemcpyAsync(P->val.data(), b.val[buf], (size_t)cursor * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    P_TRY(cudaStreamSynchronize(ctx->stream));
+#undef P_TRY
+    cudaFree(d_tgt); cudaFree(d_ptr);
+    tm.mark("sort + download");
+    if (k >= 0) {
+        try { apply_topk_rows(P, k); } catch (...) { delete P; return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
+    }
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->pushes = pushes; stats->edges = edges; stats->iters = iters;
         cudaEventElapsedTime(&stats->ms_push, ctx->ev[0], ctx->ev[1]);
-        stats->ms_total = stats->ms_push; stats->launches = launches; stats->rounds = launches;
+        float ms_sort = 0; cudaEventElapsedTime(&ms_sort, ctx->ev[1], ctx->ev[2]);
+        stats->ms_select = ms_sort;
+        stats->ms_total = stats->ms_push + ms_sort; stats->launches = launches; stats->rounds = launches;
     }
     *out = P;
     return PPR_OK;

@@ -353,6 +353,76 @@ __device__ void push_sweep_warp(const PushArgs& A, int par, u64 rmax_fx, i64 gti
     phase_a_publish(ctl, par, tot, sm_cnt);
 }
 
+// Plain dense sweep (the round-1 form): r[] and the vertex record of every vertex that holds residue are loaded for
+// SWEEP_ITEMS x 32 consecutive vertices per warp, nothing is prefetched across tiles.  Selected with -DSWEEP_PLAIN.
+#ifndef SWEEP_ITEMS
+#define SWEEP_ITEMS 4
+#endif
+__device__ void push_sweep_plain(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u32* sm_cnt) {
+    PushCtl* ctl = A.ctl;
+    if (gtid == 0) phase_a_recycle(ctl, par);
+    PhaseATotals tot = {0, 0, 0, 0};
+    const u32 lane = lane_id();
+    const i64 n = A.n, gwarp = gtid >> 5, nwarps = gsize >> 5;
+    constexpr int IT = SWEEP_ITEMS;
+    for (i64 tile = gwarp * (32 * IT); tile < n; tile += nwarps * (32 * IT)) {
+        u64 pk[IT], q[IT], x[IT];
+        u32 cls[IT];
+#pragma unroll
+        for (int k = 0; k < IT; k++) { const i64 v = tile + (i64)k * 32 + lane; x[k] = v < n ? A.r[v] : 0; }
+#pragma unroll
+        for (int k = 0; k < IT; k++) { const i64 v = tile + (i64)k * 32 + lane; pk[k] = x[k] ? A.out_vtx[v] : 0; }
+        u32 my_nch = 0;
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+            q[k] = 0; cls[k] = 0;
+            const u32 d = vtx_deg(pk[k]);
+            if (x[k] && x[k] >= thr_fwd(rmax_fx, d)) {
+                const i64 v = tile + (i64)k * 32 + lane;
+                const u64 a = mulhi64(x[k], A.alpha_q64);
+                const u64 y = x[k] - a;
+                u64 left;
+                if (d == 0) { left = 0; tot.dang += y; }
+                else { q[k] = y / (u64)d; left = y - q[k] * (u64)d; }
+                A.r[v] = left;
+                A.reserve[v] += a;
+                tot.resv += a; tot.edges += d; tot.pushed += 1;
+                cls[k] = d == 0 ? 0u : (d <= PUSH_SMALL_MAX ? 1u : 2u);
+                if (cls[k] == 2) my_nch += (d + PUSH_CHUNK - 1) / PUSH_CHUNK;
+            }
+        }
+        u32 ms[IT], small_total = 0;
+#pragma unroll
+        for (int k = 0; k < IT; k++) { ms[k] = __ballot_sync(0xffffffffu, cls[k] == 1); small_total += __popc(ms[k]); }
+        u32 chunk_incl = 0, chunk_total = 0;
+        if (__any_sync(0xffffffffu, my_nch != 0)) {
+            chunk_incl = my_nch;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, chunk_incl, o); if (lane >= o) chunk_incl += t; }
+            chunk_total = __shfl_sync(0xffffffffu, chunk_incl, 31);
+        }
+        if (small_total | chunk_total) {
+            u64 base = 0;
+            if (lane == 0) base = atomicAdd((ull*)&ctl->stage[par], ((ull)chunk_total << 32) | (ull)small_total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            u32 off = (u32)base;
+            u32 cb = (u32)(base >> 32) + chunk_incl - my_nch;
+#pragma unroll
+            for (int k = 0; k < IT; k++) {
+                if (cls[k] == 1) { u32 slot = off + __popc(ms[k] & lanemask_lt()); A.s_pack[slot] = pk[k]; A.s_q[slot] = q[k]; }
+                off += __popc(ms[k]);
+                if (cls[k] == 2) {
+                    u32 nch = (vtx_deg(pk[k]) + PUSH_CHUNK - 1) / PUSH_CHUNK;
+                    A.l_pack[cb] = pk[k]; A.l_q[cb] = q[k];
+                    for (u32 c = 0; c < nch; c++) A.chunks[cb + c] = make_uint2(cb, c);
+                    cb += nch;
+                }
+            }
+        }
+    }
+    phase_a_publish(ctl, par, tot, sm_cnt);
+}
+
 // --------------------------------------------------------------------------------- phase B
 // One relaxed edge.  LIST: returning atomic + crossing test; otherwise a fire-and-forget reduction.
 // Hub accumulator in shared memory: value = hi * 2^32 + lo.  Shared memory has no native 64-bit add (atomicAdd on u64
@@ -866,7 +936,11 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(c
                 }
                 push_phase_a_list(A, par, rmax_fx, gtid, gsize, sm_cnt);
             } else {
+#ifdef SWEEP_PLAIN
+                push_sweep_plain(A, par, rmax_fx, gtid, gsize, sm_cnt);
+#else
                 push_sweep_warp(A, par, rmax_fx, gtid, gsize, sm_cnt);
+#endif
             }
             grid.sync();
             const u32 fcnt = *(volatile u32*)&ctl->fcnt[par];

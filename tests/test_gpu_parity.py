@@ -449,16 +449,55 @@ def test_all_pairs(G, OG, R12, O):
     assert np.array_equal(mptr, optr) and np.array_equal(mtgt, otgt) and np.array_equal(mval, oval)
 
 
-def test_all_pairs_batch_growth(R16, O):
-    # n = 65536: the first batch holds 1464 targets (residue matrix ~ 768 MB); targets this cheap (threshold 1e-3)
-    # make the library quadruple the batch after it -- the index must not depend on how targets are batched
+def test_all_pairs_launch_split(R16, O, ctx):
+    # n = 65536, 12000 targets: a probe launch (1184 targets, 256-thread CTAs), then the rest in one launch with the CTA shape
+    # chosen from the work per target -- the index must not depend on how targets are split over launches, CTA shapes,
+    # or on the pair buffer being regrown (PPR_BWD_* overrides are exercised by the forced batch below)
     g, og = R16
     hi = 12000
     optr, otgt, oval, ost = O.b_base_all_pairs(og, ALPHA, 1e-3, 0, hi)
     ptr, tgt, val, st = g.backward_all_pairs(ALPHA, 1e-3, -1, 0, hi, raw=True)
     assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval)
     assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"])
-    assert st["launches"] <= 4, st["launches"]      # 1464 + 4096 + 4096 + rest instead of 9 batches of 1464
+    assert st["launches"] <= 3, st["launches"]
+    try:
+        ctx.set_bwd_batch(700)      # 18 launches of at most 700 targets
+        ptr, tgt, val, st = g.backward_all_pairs(ALPHA, 1e-3, -1, 0, hi, raw=True)
+        assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval)
+        assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"]) and st["launches"] >= 18
+    finally:
+        ctx.set_bwd_batch(0)
+
+
+def test_all_pairs_multi_tile_frontiers(R12, O):
+    # threshold 1e-6 on R-MAT 2^12: frontiers of thousands of vertices (several tiles per CTA, staged through the slot's
+    # global rows), residues re-touched after being pushed (duplicates in the touched list)
+    g, og = R12
+    optr, otgt, oval, ost = O.b_base_all_pairs(og, ALPHA, 1e-6, 0, 300)
+    ptr, tgt, val, st = g.backward_all_pairs(ALPHA, 1e-6, -1, 0, 300, raw=True)
+    assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval)
+    assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"])
+
+
+def test_backward_search_dense_graph(pkg, ctx, O):
+    # n = 2048 with ~600 in-edges per vertex: one iteration of ONE target stages ceil(indeg / 256) chunk descriptors for
+    # every vertex, far more than T * n -- the chunk buffer is sized from the in-degree histogram at export
+    rng = np.random.default_rng(5)
+    n, d = 2048, 600
+    ci = np.sort(rng.integers(0, n, (n, d)), axis=1).astype(np.int32).ravel()
+    rp = (np.arange(n + 1, dtype=np.int64) * d)
+    g, og = pkg.Graph(ctx, rp, ci), O.OGraph(rp, ci)
+    try:
+        res, st = g.backward_search(7, ALPHA, 1e-7)
+        raw, r = g.last_raw()
+        ores, orr, ost = O.b_backward_search(og, 7, ALPHA, 1e-7)
+        assert np.array_equal(raw, ores) and np.array_equal(r, orr)
+        assert (st["pushes"], st["edges"], st["iters"]) == (ost["pushes"], ost["edges"], ost["iters"])
+        optr, otgt, oval, ost = O.b_base_all_pairs(og, ALPHA, 1e-4, 0, 64)
+        ptr, tgt, val, st = g.backward_all_pairs(ALPHA, 1e-4, -1, 0, 64, raw=True)
+        assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval)
+    finally:
+        g.close()
 
 
 def test_all_pairs_topk_rows(G, OG, O):
