@@ -171,6 +171,15 @@ int32_t ppr_topk(ppr_ctx* ctx, const double* vec, int64_t n, int32_t k, int32_t*
  * reference uses 100).  Double arithmetic, deterministic pull over the CSC. */
 int32_t ppr_power_iteration(ppr_graph* g, int32_t src, double alpha, int32_t iters, double* out);
 
+/* Gen_Util.computeError(algo, pm, err_type, k), J/Gen_Util.java:259-326, evaluated on the device.
+ * ppr_metrics_keep snapshots the dense result of the LAST query of this graph (power iteration, FORA, forward push,
+ * Monte-Carlo, FORA top-k estimate) as doubles in HBM: slot 0 = ground truth (pm), slot 1 = estimate (algo).
+ * ppr_metrics_compute returns MAX_ERR (max |est - truth| over the vertices the ground truth reached, :306-321),
+ * PRECISION (:273-281: hits / size of the ground-truth top-k, ties included on both sides) and NDCG (:282-300) for k;
+ * any output pointer may be NULL; k = 0 computes MAX_ERR only. */
+int32_t ppr_metrics_keep(ppr_graph* g, int32_t slot);
+int32_t ppr_metrics_compute(ppr_graph* g, int32_t k, double* max_err, double* precision, double* ndcg);
+
 /* Throughput path: nq FORA queries back to back, results written to ppr_out[q*n .. (q+1)*n) while
  * the next query computes.  Query q uses seed + q.  stats_out (nullable) is an array of nq entries.
  * ppr_out == NULL leaves the results on the device (throughput measurements; ppr_last_raw reads the last one). */

@@ -23,6 +23,11 @@ int32_t ppr_flush_l2(ppr_ctx* ctx);
  * Results are identical; the parity tests force each variant on graphs of any size. */
 int32_t ppr_set_walk_variant(ppr_ctx* ctx, int32_t hint);
 
+/* Direction switch of the forward push: a dense iteration whose frontier owns at least enter_share * m edges is followed
+ * by pull-direction passes (every in-edge read once, no atomics) until the frontier owns less than exit_share * m.
+ * enter_share < 0 switches the pull direction off; 0 / 0 forces it after every dense iteration.  Results are identical. */
+int32_t ppr_set_pull(ppr_ctx* ctx, double enter_share, double exit_share);
+
 /* ---------------------------------------------------------------- raw state of the last query (parity tests)
  * Fixed-point vectors exactly as the kernels left them: reserve (or FORA estimate / Monte-Carlo
  * counts) and residue.  Either pointer may be NULL. */

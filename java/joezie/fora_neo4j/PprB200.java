@@ -42,6 +42,7 @@ public final class PprB200 implements AutoCloseable {
     private static final MethodHandle PAIRS_COUNT = fn("ppr_pairs_count", FunctionDescriptor.of(I64, PTR));
     private static final MethodHandle PAIRS_EXPORT = fn("ppr_pairs_export", FunctionDescriptor.of(I32, PTR, PTR, PTR, PTR, PTR));
     private static final MethodHandle PAIRS_DESTROY = fn("ppr_pairs_destroy", FunctionDescriptor.of(I32, PTR));
+    private static final MethodHandle WALK_TERMINALS = fn("ppr_walk_terminals", FunctionDescriptor.of(I32, PTR, I32, I32, I64, I64, I64, I64, F64, I32, PTR));
 
     private final Arena arena = Arena.ofShared();
     private final MemorySegment ctx;
@@ -132,6 +133,45 @@ public final class PprB200 implements AutoCloseable {
             java.util.Vector<Long> out = new java.util.Vector<>();
             for (int i = 0; i < cnt.get(I32, 0); i++) out.add(originalIds[ids.getAtIndex(I32, i)]);
             return out;
+        }
+    }
+
+    /** Fora_Topk as (node id, estimate) entries in result order (estimate descending, ties included). */
+    public java.util.List<java.util.Map.Entry<Long, Double>> foraTopkEntries(long nodeIdStart, double alpha, double eps, int k, double delta, double pfail, double minDelta, long seed) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            int cap = (int) Math.min((long) n, Math.max(4L * k, k + 4096L));
+            for (;;) {
+                MemorySegment ids = a.allocate(I32, cap), vals = a.allocate(F64, cap), cnt = a.allocate(I32), conf = a.allocate(F64, 3);
+                conf.setAtIndex(F64, 0, delta); conf.setAtIndex(F64, 1, pfail); conf.setAtIndex(F64, 2, minDelta);
+                int rc = (int) FORA_TOPK.invokeExact(graph, adjM.toMappedNodeId(nodeIdStart), alpha, eps, k, seed, 0, conf, ids, vals, cap, cnt, MemorySegment.NULL);
+                if (rc == -5 /* PPR_E_CAPACITY: more ties than room; *count_out holds the needed size */) { cap = cnt.get(I32, 0); continue; }
+                check(rc, ctx);
+                java.util.List<java.util.Map.Entry<Long, Double>> out = new java.util.ArrayList<>();
+                for (int i = 0; i < cnt.get(I32, 0); i++) out.add(new java.util.AbstractMap.SimpleEntry<>(originalIds[ids.getAtIndex(I32, i)], vals.getAtIndex(F64, i)));
+                return out;
+            }
+        }
+    }
+
+    /** Algo_Util.kth_ppr + retrieveTopK + getTopKNodeIds over a result map: entries >= the k-th largest value, sorted descending. */
+    public java.util.List<java.util.Map.Entry<Long, Double>> topk(java.util.HashMap<Long, Double> res, int k) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment dense = a.allocate(F64, n), ids = a.allocate(I32, n), vals = a.allocate(F64, n), cnt = a.allocate(I32);
+            for (java.util.Map.Entry<Long, Double> e : res.entrySet()) dense.setAtIndex(F64, adjM.toMappedNodeId(e.getKey()), e.getValue());
+            check((int) TOPK.invokeExact(ctx, dense, (long) n, k, ids, vals, n, cnt, MemorySegment.NULL), ctx);
+            java.util.List<java.util.Map.Entry<Long, Double>> out = new java.util.ArrayList<>();
+            for (int i = 0; i < cnt.get(I32, 0); i++) out.add(new java.util.AbstractMap.SimpleEntry<>(originalIds[ids.getAtIndex(I32, i)], vals.getAtIndex(F64, i)));
+            return out;
+        }
+    }
+
+    /** Monte_Carlo.random_walk / random_walk_no_zero_hop: terminal of walk `walkId` from nodeIdStart (restart at the start vertex, as the reference). */
+    public long walkTerminal(long nodeIdStart, long walkId, long seed, double alpha, boolean noZeroHop) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment out = a.allocate(I32);
+            int s = adjM.toMappedNodeId(nodeIdStart);
+            check((int) WALK_TERMINALS.invokeExact(graph, s, s, walkId, 1L, seed, 0L, alpha, noZeroHop ? 1 : 0, out), ctx);
+            return originalIds[out.get(I32, 0)];
         }
     }
 

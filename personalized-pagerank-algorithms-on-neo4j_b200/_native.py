@@ -30,9 +30,9 @@ EXPORTS = [
     "ppr_pairs_export", "ppr_pairs_destroy", "ppr_fora_shard", "ppr_monte_carlo_shard", "ppr_fora_topk_shard", "ppr_result_devptr",
     "ppr_result_export", "ppr_walk_terminals", "ppr_version",
     "ppr_comm_unique_id", "ppr_comm_init", "ppr_comm_destroy", "ppr_comm_info", "ppr_comm_max_f64", "ppr_fora_sharded", "ppr_monte_carlo_sharded",
-    "ppr_fora_topk_sharded", "ppr_backward_all_pairs_sharded",
+    "ppr_fora_topk_sharded", "ppr_backward_all_pairs_sharded", "ppr_metrics_keep", "ppr_metrics_compute",
 ]
-DEBUG_EXPORTS = ["ppr_timer_record", "ppr_timer_elapsed_ms", "ppr_flush_l2", "ppr_set_walk_variant", "ppr_last_raw", "ppr_push_trace_begin",
+DEBUG_EXPORTS = ["ppr_timer_record", "ppr_timer_elapsed_ms", "ppr_flush_l2", "ppr_set_walk_variant", "ppr_set_pull", "ppr_last_raw", "ppr_push_trace_begin",
                  "ppr_push_trace_step", "ppr_debug_timeline"]
 GEN_EXPORTS = ["ppr_rmat_generate"]   # include/pprgen.h, libpprgen.so (host only)
 GEN_PATH = os.path.join(_PKG, "libpprgen.so")
@@ -140,6 +140,9 @@ def load():
         "ppr_debug_timeline": (i32, [vp, vp, i64, C.POINTER(i64)]),
         "ppr_version": (C.c_char_p, []),
         "ppr_set_walk_variant": (i32, [vp, i32]),
+        "ppr_set_pull": (i32, [vp, f64, f64]),
+        "ppr_metrics_keep": (i32, [vp, i32]),
+        "ppr_metrics_compute": (i32, [vp, i32, C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)]),
         "ppr_comm_unique_id": (i32, [vp]),
         "ppr_comm_init": (i32, [vp, vp, i32, i32]),
         "ppr_comm_destroy": (i32, [vp]),
@@ -217,6 +220,10 @@ class Context:
 
     def set_walk_variant(self, hint=-1):
         self.check(self.L.ppr_set_walk_variant(self.h, hint))
+
+    def set_pull(self, enter_share=-1.0, exit_share=0.0):
+        """Direction switch of the forward push (pull-direction passes for fat iterations); enter_share < 0 = off, 0/0 = forced."""
+        self.check(self.L.ppr_set_pull(self.h, enter_share, exit_share))
 
     # ---- multi-GPU (NCCL inside the library)
     @staticmethod
@@ -457,6 +464,16 @@ class Graph:
         p, st = C.c_void_p(), Stats()
         self.ctx.check(self.L.ppr_backward_all_pairs(self.h, alpha, threshold, k, t_lo, t_hi, C.byref(p), C.byref(st)))
         return self._pairs_out(p, raw) + (st.as_dict(),)
+
+    # ---- Gen_Util.computeError on the device (J/Gen_Util.java:259-326)
+    def metrics_keep(self, slot):
+        """Snapshot the last query's dense result in HBM: slot 0 = ground truth (power iteration), 1 = estimate."""
+        self.ctx.check(self.L.ppr_metrics_keep(self.h, slot))
+
+    def metrics_compute(self, k):
+        me, pr, nd = C.c_double(), C.c_double(), C.c_double()
+        self.ctx.check(self.L.ppr_metrics_compute(self.h, k, C.byref(me), C.byref(pr), C.byref(nd)))
+        return {"max_err": me.value, "precision": pr.value, "ndcg": nd.value}
 
     # ---- raw state / replay hooks (parity tests, multi-GPU plumbing)
     def last_raw(self, want_residue=True):

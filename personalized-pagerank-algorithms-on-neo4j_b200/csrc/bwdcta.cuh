@@ -36,6 +36,8 @@ struct BwdCtaArgs {
     int key_bits;               // B: key = v << B | t
     u64* out_key; u64* out_val; i64 out_cap;
     ull* counters;              // [0] pair cursor, [1] pushes, [2] edges, [3] iterations (summed over targets)
+                                // timing != 0: [4] ticket+seed ns, [5] phase A ns, [6] phase B ns, [7] output+clean ns, [8] targets (thread 0's clock)
+    int timing;
 };
 
 // append to a per-CTA list whose cursor lives in shared memory; the first `mirror_cap` entries are mirrored in shared memory
@@ -54,10 +56,31 @@ __device__ __forceinline__ void cta_append(u32* list, u32* sm_cursor, bool pred,
     }
 }
 
+// four predicated values per lane, one shared-memory cursor update per warp
+__device__ __forceinline__ void cta_append4(u32* list, u32* sm_cursor, const bool (&pred)[4], const u32 (&value)[4], u32* mirror, u32 mirror_cap, u32 cap, u32* sm_overflow) {
+    u32 m[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { m[k] = __ballot_sync(0xffffffffu, pred[k]); tot += __popc(m[k]); }
+    if (tot) {
+        u32 base = 0;
+        if (lane_id() == 0) base = atomicAdd(sm_cursor, tot);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (pred[k]) {
+                const u32 idx = base + __popc(m[k] & lanemask_lt());
+                if (idx < cap) list[idx] = value[k]; else *sm_overflow = 1;
+                if (mirror && idx < mirror_cap) mirror[idx] = value[k];
+            }
+            base += __popc(m[k]);
+        }
+    }
+}
+
 template <int BD>
 __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaArgs A) {
     constexpr int LOG_BD = BD == 1024 ? 10 : BD == 512 ? 9 : BD == 256 ? 8 : BD == 128 ? 7 : 6;
-    __shared__ u64 m_excl[BD];
+    __shared__ u64 m_excl[BD + 1];      // exclusive in-degree prefix of the tile's frontier vertices; ~0 beyond them (and as the sentinel)
     __shared__ u64 m_beg[BD];
     __shared__ u64 m_y[BD];
     __shared__ u32 mf[2][BD];          // mirrors of the first BD entries of the two frontier lists
@@ -78,6 +101,8 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
 
     for (;;) {
         __syncthreads();
+        u64 tm0 = 0, tmA = 0, tmB = 0, tm1 = 0;
+        if (A.timing && tid == 0) tm0 = globaltimer_ns();
         if (tid == 0) s_ticket = atomicAdd(A.ticket, 1u);
         __syncthreads();
         const i64 t = (i64)A.t_lo + (i64)s_ticket;
@@ -98,6 +123,7 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
         int par = 0;
         u64 acc_pushes = 0, acc_edges = 0, acc_iters = 0;   // thread 0
         __syncthreads();
+        if (A.timing && tid == 0) { tm1 = globaltimer_ns(); tm0 = tm1 - tm0; }
         while (cnt) {
             if (tid == 0) s_next = 0;
             u32* next = F[par ^ 1];
@@ -140,6 +166,7 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                 }
             }
             __syncthreads();   // every capture precedes every add of this iteration
+            if (A.timing && tid == 0) { const u64 now = globaltimer_ns(); tmA += now - tm1; tm1 = now; }
             // ---- phase B (J/Backward_Search.java:77-94): tiles of BD frontier vertices, threads sweep the concatenated in-edge lists
             u64 it_edges = 0;
             for (u32 base = 0; base < cnt; base += BD) {
@@ -152,21 +179,27 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                 u64 e_d, e_x, t_d, t_x;
                 block_excl_scan2((u64)d, 0ull, scratch, e_d, e_x, t_d, t_x);
                 m_excl[tid] = (base + tid < cnt) ? e_d : ~0ull;
+                if (tid == 0) m_excl[BD] = ~0ull;
                 m_beg[tid] = vtx_begin(pk) - e_d;   // edge address of concatenated position e is m_beg[owner] + e
                 m_y[tid] = y;
                 __syncthreads();
                 it_edges += t_d;
                 for (u64 eb = 0; eb < t_d; eb += 4 * BD) {
+                    // four consecutive edges per thread: one binary search for the first, the others advance linearly
                     u32 u[4];
                     u64 inc[4], old[4];
+                    const u64 e0 = eb + 4ull * tid;
+                    int o = 0;
+                    if (e0 < t_d) {
+#pragma unroll
+                        for (int s = BD / 2; s > 0; s >>= 1) { const int p = o + s; if (m_excl[p] <= e0) o = p; }
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const u64 e = eb + (u64)k * BD + tid;
+                        const u64 e = e0 + k;
                         u[k] = 0xffffffffu; inc[k] = 0;
                         if (e < t_d) {
-                            int o = 0;
-#pragma unroll
-                            for (int s = BD / 2; s > 0; s >>= 1) { const int p = o + s; if (m_excl[p] <= e) o = p; }
+                            while (m_excl[o + 1] <= e) o++;
                             u[k] = (u32)__ldg(&A.row_idx[m_beg[o] + e]);
                             inc[k] = m_y[o];
                         }
@@ -175,13 +208,15 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                     for (int k = 0; k < 4; k++) if (u[k] != 0xffffffffu) inc[k] = mulhi64(inc[k], __ldg(&A.invdeg[u[k]]));   // (1-alpha) r(v) / d_out(u)
 #pragma unroll
                     for (int k = 0; k < 4; k++) old[k] = (u[k] != 0xffffffffu && inc[k]) ? atomicAdd((ull*)&R[u[k]], (ull)inc[k]) : 1ull;
+                    bool first[4], cross[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const bool live = u[k] != 0xffffffffu && inc[k] != 0;
-                        cta_append(TOUCHED, &s_ntouched, live && old[k] == 0, u[k], nullptr, 0u, cap, &s_overflow);
-                        const bool cross = live && old[k] <= A.rmax_fx && old[k] + inc[k] > A.rmax_fx;   // strict r > rmax, exactly one add crosses
-                        cta_append(next, &s_next, cross, u[k], next_m, (u32)BD, cap, &s_overflow);
+                        first[k] = live && old[k] == 0;
+                        cross[k] = live && old[k] <= A.rmax_fx && old[k] + inc[k] > A.rmax_fx;   // strict r > rmax, exactly one add crosses
                     }
+                    cta_append4(TOUCHED, &s_ntouched, first, u, nullptr, 0u, cap, &s_overflow);
+                    cta_append4(next, &s_next, cross, u, next_m, (u32)BD, cap, &s_overflow);
                 }
                 __syncthreads();
             }
@@ -189,6 +224,7 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
             cnt = s_next;
             par ^= 1;
             __syncthreads();
+            if (A.timing && tid == 0) { const u64 now = globaltimer_ns(); tmB += now - tm1; tm1 = now; }
         }
         // ---- output: pushed vertices with reserve >= threshold (J/Base_Whole_Graph.java:80-88); clean the slot
         const u32 np = s_npushed;
@@ -223,6 +259,14 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
         }
         if (s_overflow) { for (i64 v = tid; v < n; v += BD) R[v] = 0; }
         else { const u32 nt = s_ntouched; for (u32 i = tid; i < nt; i += BD) R[TOUCHED[i]] = 0; }
+        if (A.timing) {
+            __syncthreads();
+            if (tid == 0) {
+                const u64 now = globaltimer_ns();
+                atomicAdd(&A.counters[4], (ull)tm0); atomicAdd(&A.counters[5], (ull)tmA); atomicAdd(&A.counters[6], (ull)tmB);
+                atomicAdd(&A.counters[7], (ull)(now - tm1)); atomicAdd(&A.counters[8], 1ull);
+            }
+        }
     }
 }
 

@@ -55,7 +55,11 @@ typedef unsigned long long ull;
 #define PUSH_MIDI_V 4096
 #define PUSH_MIDI_E (1 << 16)
 #ifndef PUSH_CTAS_PER_SM
-#define PUSH_CTAS_PER_SM (1024 / PUSH_THREADS)   // 32 resident warps per SM at 64 registers per thread
+// One 512-thread CTA per SM: the push kernel then gets 126 registers per thread and does not spill (with two CTAs per
+// SM, 64 registers, it spilled 380 bytes and the prefetching dense sweep lost 25 %: 3.62 -> 3.22 ms per query at R-MAT
+// scale 22, 1.09 -> 1.01 ms at scale 20; profiles/r02_push_variants.txt).  16 warps per SM are enough for the dense
+// phase B (same 4.0 ms either way), and the barrier-bound small iterations get cheaper with half the CTAs.
+#define PUSH_CTAS_PER_SM 1
 #endif
 #define WALK_THREADS 256
 #ifndef WALK_PER_LANE
@@ -184,6 +188,7 @@ struct ppr_ctx {
     i32 midi_ctas;         // forward push, small regime: CTAs taking part (<= 1: off), vertex and edge limits
     i64 midi_v, midi_e;
     i32 walk_hint;         // walk kernel variant: -1 automatic (L2 eviction hints once the graph exceeds the L2), 0 plain, 1 hints
+    double pull_enter, pull_exit;   // forward push: pull-direction passes from / until this share of all edges in the frontier (enter < 0: off)
     // measurement helpers (pprb200_debug.h): per context, created on first use, destroyed by ppr_shutdown
     cudaEvent_t timer_ev[4]; bool timer_init;
     void* flush_buf;
@@ -204,6 +209,13 @@ struct DevGraph {
     u32* push_idx;  // [m] col_idx with hub targets encoded as HOT_BIT | slot
     u32* hot_id;    // [n_hot] slot -> vertex
     u32 n_hot;
+    // pull-direction iterations of the forward push (pull.cuh)
+    u32* pull_idx;      // [m] row_idx with the highest out-degree sources encoded as HOT_BIT | slot
+    u32* pull_hot_id;   // [n_pull_hot] slot -> vertex
+    u32 n_pull_hot;
+    u32* long_v; u32 n_long;             // vertices with more than PULL_LONG in-edges
+    uint2* long_chunk; u32 n_long_chunk; // (vertex, chunk number)
+    u32* pull_task; u32 n_pull_task;     // n_pull_task + 1 boundaries, in 32-vertex groups
 };
 
 struct Workspace {
@@ -211,6 +223,7 @@ struct Workspace {
     u64* r;         // residue
     u64* reserve;   // reserve / result
     u64* est;       // FORA top-k estimate (push reserve + walk contributions)
+    u64* q[2];      // pull-direction iterations: dense per-edge amounts of the current / next frontier
     u32* front[2];  // frontier lists
     u64* s_pack; u64* s_q;   // staged small items (packed vertex record, per-edge amount)
     u64* l_pack; u64* l_q;   // staged large items
@@ -238,9 +251,14 @@ struct ppr_graph {
     bool trace_active; int trace_parity; i32 trace_src; u64 trace_alpha_q64;
 };
 
-struct ppr_pairs {
+struct ppr_pairs {   // inverted index of Base_Whole_Graph: row v = (target, pi(v, target)) pairs, targets ascending (or the top-k rows)
     i64 n;
+    i64 count;
     std::vector<i64> src_ptr;
+    // device-resident result (the normal case): ppr_pairs_export copies straight into the caller's arrays
+    int device; i32* d_tgt; u64* d_val;
+    // host-resident result (top-k rows): on_host
+    bool on_host;
     std::vector<i32> tgt;
     std::vector<u64> val;
 };

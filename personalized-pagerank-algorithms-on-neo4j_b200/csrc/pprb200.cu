@@ -23,13 +23,14 @@
 #include "backward.cuh"
 #include "bwdcta.cuh"
 #include "comm.hpp"
+#include "metrics.cuh"
 #include "common.cuh"
 #include "../../include/pprb200_debug.h"
 #include "push.cuh"
 #include "select.cuh"
 #include "walk.cuh"
 
-#define PUSH_DYN_SMEM ((size_t)HOT_SLOTS * 8)   // dynamic shared memory of k_push_query: the per-CTA hub accumulators
+#define PUSH_DYN_SMEM ((size_t)(HOT_SLOTS > PULL_SLOTS ? HOT_SLOTS : PULL_SLOTS) * 8)   // dynamic shared memory of k_push_query: the per-CTA hub accumulators (push) / hub amounts (pull)
 static thread_local std::string g_init_err;
 
 int32_t ctx_fail(ppr_ctx* ctx, int32_t code, const std::string& msg) {
@@ -120,6 +121,10 @@ extern "C" int32_t ppr_init(int32_t device, ppr_ctx** out) {
     ctx->bwd_batch = 0;
     ctx->batch_streams = 0;
     ctx->walk_hint = -1;
+    // pull-direction passes are OFF by default: inside the 16-warp-per-SM persistent kernel a pass is a chain of dependent
+    // gathers and costs ~950 us at R-MAT scale 22 (profiles/r02_pull_direction.txt), more than the fattest push iteration
+    ctx->pull_enter = -1.0; ctx->pull_exit = 0.0;
+    { const char* e; if ((e = getenv("PPR_PULL_ENTER"))) ctx->pull_enter = atof(e); if ((e = getenv("PPR_PULL_EXIT"))) ctx->pull_exit = atof(e); }
     ctx->timer_init = false; ctx->flush_buf = nullptr; ctx->topk_buf = nullptr; ctx->topk_bytes = 0;
     ctx->comm = nullptr; ctx->rank = 0; ctx->world = 1;
     {   // small-regime knobs of the forward push (debug overrides: PPR_MIDI_CTAS / PPR_MIDI_V / PPR_MIDI_E)
@@ -228,6 +233,12 @@ extern "C" int32_t ppr_flush_l2(ppr_ctx* ctx) {
     CUDA_TRY(cudaMemsetAsync(ctx->flush_buf, 0x5a, bytes, ctx->stream));
     return PPR_OK;
 }
+extern "C" int32_t ppr_set_pull(ppr_ctx* ctx, double enter_share, double exit_share) {
+    if (!ctx) return PPR_E_INVALID;
+    ctx->pull_enter = enter_share; ctx->pull_exit = exit_share;
+    return PPR_OK;
+}
+
 extern "C" int32_t ppr_set_walk_variant(ppr_ctx* ctx, int32_t hint) {
     if (!ctx || hint < -1 || hint > 1) return PPR_E_INVALID;
     ctx->walk_hint = hint;
@@ -257,7 +268,7 @@ template <typename T>
 static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
 
 static void ws_free(Workspace& w) {
-    cudaFree(w.r); cudaFree(w.reserve); cudaFree(w.est); cudaFree(w.front[0]); cudaFree(w.front[1]);
+    cudaFree(w.r); cudaFree(w.reserve); cudaFree(w.est); cudaFree(w.front[0]); cudaFree(w.front[1]); cudaFree(w.q[0]); cudaFree(w.q[1]);
     cudaFree(w.s_pack); cudaFree(w.s_q); cudaFree(w.l_pack); cudaFree(w.l_q); cudaFree(w.chunks);
     cudaFree(w.ws_v); cudaFree(w.ws_begin); cudaFree(w.ws_inc); cudaFree(w.ws_rem);
     cudaFree(w.blk_a); cudaFree(w.blk_b); cudaFree(w.blk_c); cudaFree(w.out_f64); cudaFree(w.hist);
@@ -273,6 +284,7 @@ static int32_t ws_alloc(ppr_ctx* ctx, Workspace& w, i64 n, i64 chunk_cap) {
     size_t N = (size_t)n;
     CUDA_TRY(dalloc(&w.r, N)); CUDA_TRY(dalloc(&w.reserve, N)); CUDA_TRY(dalloc(&w.est, N));
     CUDA_TRY(dalloc(&w.front[0], N)); CUDA_TRY(dalloc(&w.front[1], N));
+    CUDA_TRY(dalloc(&w.q[0], N)); CUDA_TRY(dalloc(&w.q[1], N));
     CUDA_TRY(dalloc(&w.s_pack, N)); CUDA_TRY(dalloc(&w.s_q, N)); CUDA_TRY(dalloc(&w.l_pack, std::max(N, (size_t)chunk_cap))); CUDA_TRY(dalloc(&w.l_q, std::max(N, (size_t)chunk_cap)));
     CUDA_TRY(dalloc(&w.chunks, (size_t)chunk_cap));
     CUDA_TRY(dalloc(&w.ws_v, N)); CUDA_TRY(dalloc(&w.ws_begin, N + 64)); CUDA_TRY(dalloc(&w.ws_inc, N)); CUDA_TRY(dalloc(&w.ws_rem, N));
@@ -352,7 +364,7 @@ static int32_t bcw_alloc(ppr_ctx* ctx, BwdCtaWorkspace& b, int slots, int bd, i6
     const size_t sn = (size_t)slots * (size_t)n;
     CUDA_TRY(dalloc(&b.r, sn)); CUDA_TRY(dalloc(&b.reserve, sn)); CUDA_TRY(dalloc(&b.front, 2 * sn));
     CUDA_TRY(dalloc(&b.pushed, sn)); CUDA_TRY(dalloc(&b.touched, sn)); CUDA_TRY(dalloc(&b.st_pk, sn)); CUDA_TRY(dalloc(&b.st_y, sn));
-    CUDA_TRY(dalloc(&b.ticket, 1)); CUDA_TRY(dalloc(&b.counters, 8));
+    CUDA_TRY(dalloc(&b.ticket, 1)); CUDA_TRY(dalloc(&b.counters, 16));
     CUDA_TRY(cudaMemsetAsync(b.r, 0, sn * 8, ctx->stream));          // rows are zero outside a search; every search cleans up after itself
     CUDA_TRY(cudaMemsetAsync(b.reserve, 0, sn * 8, ctx->stream));
     return PPR_OK;
@@ -388,6 +400,10 @@ struct GraphExtra {  // host-side bookkeeping kept beside ppr_graph
     bool batch_ev_ready;
     PushCtl* snaps; size_t snaps_cap;       // pinned
     i64 bwd_chunks_per_target;              // chunk descriptors one reverse-push target can need in one iteration
+    // on-device error metrics (metrics.cuh): [0] ground truth, [1] estimate, as doubles; the last power-iteration result
+    double* metric_vec[2]; bool metric_set[2];
+    double* pm_result; bool last_is_pm;
+    i32* sort_ids; u64* sort_vals; i64 sort_cap;   // ordered top-k survivors (k_rank_sort)
 };
 static std::vector<std::pair<ppr_graph*, GraphExtra*>> g_extras;
 static std::mutex g_extras_mu;   // graphs of different contexts may be created / queried / destroyed from different threads
@@ -412,9 +428,11 @@ extern "C" int32_t ppr_graph_destroy(ppr_graph* g) {
         for (auto& e : x->batch_ev) cudaEventDestroy(e);
         if (x->batch_ev_ready) for (int i = 0; i < 2; i++) { cudaEventDestroy(x->done_ev[i]); cudaEventDestroy(x->copied_ev[i]); }
         if (x->snaps) cudaFreeHost(x->snaps);
+        cudaFree(x->metric_vec[0]); cudaFree(x->metric_vec[1]); cudaFree(x->pm_result); cudaFree(x->sort_ids); cudaFree(x->sort_vals);
     }
     cudaFree(g->d.out_vtx); cudaFree(g->d.col_idx); cudaFree(g->d.out_deg);
     cudaFree(g->d.in_vtx); cudaFree(g->d.row_idx); cudaFree(g->d.invdeg); cudaFree(g->d.push_idx); cudaFree(g->d.hot_id);
+    cudaFree(g->d.pull_idx); cudaFree(g->d.pull_hot_id); cudaFree(g->d.long_v); cudaFree(g->d.long_chunk); cudaFree(g->d.pull_task);
     {
         std::lock_guard<std::mutex> lk(g_extras_mu);
         for (size_t i = 0; i < g_extras.size(); i++) if (g_extras[i].first == g) { delete g_extras[i].second; g_extras.erase(g_extras.begin() + i); break; }
@@ -446,6 +464,7 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     g->ctx = ctx; g->last_ws = 0; g->last_kind = 0; g->trace_active = false;
     x->ws1_ready = false; x->bws_ready = false; x->walk_blocks = 0; x->last_divisor = 0.0; memset(&x->bws, 0, sizeof x->bws);
     x->bcw_ready = false; memset(&x->bcw, 0, sizeof x->bcw);
+    x->metric_vec[0] = x->metric_vec[1] = nullptr; x->metric_set[0] = x->metric_set[1] = false; x->pm_result = nullptr; x->last_is_pm = false; x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0;
     x->batch_ev_ready = false; x->snaps = nullptr; x->snaps_cap = 0; x->bwd_chunks_per_target = 1;
     { std::lock_guard<std::mutex> lk(g_extras_mu); g_extras.push_back(std::make_pair(g, x)); }
     g->d.n = n; g->d.m = m;
@@ -528,6 +547,52 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
         k_encode_push_idx<<<blocks, 256, 0, ctx->stream>>>(g->d.col_idx, d_slot, m, g->d.push_idx);
         B_TRY(cudaGetLastError());
     }
+    // pull-direction iterations (pull.cuh): hub SOURCES (highest out-degree) encoded in a copy of the CSC, the list of
+    // long rows cut into chunks, and a split of the 32-vertex groups into tasks with equal numbers of in-edges
+    {
+        std::vector<u32> phot, longv, task;
+        std::vector<uint2> lchunk;
+        try {
+            std::vector<std::pair<i64, i32>> cand;
+            for (i64 v = 0; v < n; v++) { i64 d = row_ptr[v + 1] - row_ptr[v]; if (d >= 64) cand.push_back(std::make_pair(-d, (i32)v)); }
+            size_t keep = std::min<size_t>(cand.size(), PULL_SLOTS);
+            std::partial_sort(cand.begin(), cand.begin() + keep, cand.end());
+            for (size_t k = 0; k < keep; k++) phot.push_back((u32)cand[k].second);
+            const i64 groups = (n + 31) / 32;
+            std::vector<i64> gw((size_t)groups, 0);
+            i64 total_w = 0;
+            for (i64 v = 0; v < n; v++) {
+                const i64 d = (i64)h_indeg[(size_t)v];
+                if (d > PULL_LONG) {
+                    longv.push_back((u32)v);
+                    for (i64 c = 0; c * PULL_LCHUNK < d; c++) lchunk.push_back(make_uint2((u32)v, (u32)c));
+                } else gw[(size_t)(v >> 5)] += d;
+            }
+            for (i64 gidx = 0; gidx < groups; gidx++) { gw[(size_t)gidx] += 96; total_w += gw[(size_t)gidx]; }   // + the fixed cost of a group
+            const i64 nt = std::max<i64>(1, std::min<i64>(groups, 65536));
+            task.assign((size_t)nt + 1, (u32)groups);
+            task[0] = 0;
+            i64 acc = 0, t = 1;
+            for (i64 gidx = 0; gidx < groups && t < nt; gidx++) {
+                acc += gw[(size_t)gidx];
+                while (t < nt && acc * nt >= total_w * t) { task[(size_t)t] = (u32)(gidx + 1); t++; }
+            }
+        } catch (...) { free_tmp(); return fail(ctx_fail(ctx, PPR_E_NOMEM, "ppr_graph_create: host allocation failed")); }
+        g->d.n_pull_hot = (u32)phot.size(); g->d.n_long = (u32)longv.size(); g->d.n_long_chunk = (u32)lchunk.size(); g->d.n_pull_task = (u32)task.size() - 1;
+        B_TRY(dalloc(&g->d.pull_hot_id, phot.size())); B_TRY(dalloc(&g->d.long_v, longv.size())); B_TRY(dalloc(&g->d.long_chunk, lchunk.size()));
+        B_TRY(dalloc(&g->d.pull_task, task.size())); B_TRY(dalloc(&g->d.pull_idx, (size_t)m));
+        if (!phot.empty()) B_TRY(cudaMemcpyAsync(g->d.pull_hot_id, phot.data(), phot.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!longv.empty()) B_TRY(cudaMemcpyAsync(g->d.long_v, longv.data(), longv.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!lchunk.empty()) B_TRY(cudaMemcpyAsync(g->d.long_chunk, lchunk.data(), lchunk.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+        B_TRY(cudaMemcpyAsync(g->d.pull_task, task.data(), task.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (m > 0) {
+            B_TRY(cudaMemsetAsync(d_slot, 0xff, (size_t)n * sizeof(i32), ctx->stream));
+            if (!phot.empty()) { k_set_slots<<<(unsigned)((phot.size() + 255) / 256), 256, 0, ctx->stream>>>(g->d.pull_hot_id, g->d.n_pull_hot, d_slot); B_TRY(cudaGetLastError()); }
+            k_encode_push_idx<<<blocks, 256, 0, ctx->stream>>>(g->d.row_idx, d_slot, m, g->d.pull_idx);
+            B_TRY(cudaGetLastError());
+        }
+        B_TRY(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
+    }
     B_TRY(cudaStreamSynchronize(ctx->stream));
     free_tmp();
 #undef B_TRY
@@ -577,6 +642,13 @@ static void fill_push_args(PushArgs& A, ppr_graph* g, Workspace& w) {
     A.prep_adds_push_part = 1;
     A.scan_threshold = g->ctx->scan_threshold < 0 ? std::max<i64>(1, g->d.n / 4) : g->ctx->scan_threshold;
     A.midi_ctas = g->ctx->midi_ctas; A.midi_v = (u32)g->ctx->midi_v; A.midi_e = (u64)g->ctx->midi_e;
+    A.in_vtx = g->d.in_vtx; A.pull_idx = g->d.pull_idx; A.pull_hot_id = g->d.pull_hot_id; A.n_pull_hot = g->d.n_pull_hot;
+    A.long_v = g->d.long_v; A.n_long = g->d.n_long; A.long_chunk = g->d.long_chunk; A.n_long_chunk = g->d.n_long_chunk;
+    A.pull_task = g->d.pull_task; A.n_pull_task = g->d.n_pull_task; A.q[0] = w.q[0]; A.q[1] = w.q[1];
+    // direction switch: a pull pass costs about as much as pushing a quarter of all edges
+    const double pe = g->ctx->pull_enter, px = std::min(g->ctx->pull_exit, g->ctx->pull_enter);
+    A.pull_enter = (pe < 0 || g->d.m == 0) ? -1 : (i64)(pe * (double)g->d.m);
+    A.pull_exit = (pe < 0 || g->d.m == 0) ? 0 : (i64)(px * (double)g->d.m);
 }
 
 static cudaError_t launch_push(ppr_ctx* ctx, Workspace& w, PushArgs& A, cudaStream_t st = nullptr, int blocks = 0) {
@@ -677,7 +749,7 @@ extern "C" int32_t ppr_forward_push(ppr_graph* g, int32_t src, double alpha, dou
         rc = export_vec(g, w, w.r, 0.0, residue_out, ctx->stream); if (rc) return rc; launches++;
     }
     rc = read_ctl(g, w); if (rc) return rc;
-    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0;
+    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0; extra_of(g)->last_is_pm = false;
     if (rsum_out) *rsum_out = (double)(FX_ONE - w.ctl_host->reserve_total) * FX_INV;
     if (stats) {
         stats_from_ctl(stats, w.ctl_host, 0.0);
@@ -731,7 +803,7 @@ extern "C" int32_t ppr_fora_shard(ppr_graph* g, int32_t src, double alpha, doubl
     rc = fora_launch(g, w, src, alpha, eps, seed, flags, conf, shard, nshards, ctx->ev[0], ctx->ev[1], ctx->ev[2], &omega);
     if (rc) return rc;
     rc = read_ctl(g, w); if (rc) return rc;
-    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0;
+    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0; extra_of(g)->last_is_pm = false;
     if (stats) {
         stats_from_ctl(stats, w.ctl_host, omega);
         cudaEventElapsedTime(&stats->ms_push, ctx->ev[0], ctx->ev[1]);
@@ -798,7 +870,8 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
     // automatic: two queries in flight only while both working sets fit in the L2 together (measured: +17 % at
     // R-MAT scale 20, -1.5 % at scale 22)
     const bool small_graph = 4.0 * (double)g->d.m + 8.0 * (double)g->d.n <= 96.0 * 1024 * 1024;
-    const bool dual = nq > 1 && (ctx->batch_streams == 2 || (ctx->batch_streams == 0 && small_graph));
+    // (two cooperative kernels are only resident together when an SM holds two of their CTAs)
+    const bool dual = nq > 1 && g->ws[0].coop_blocks >= 2 * ctx->sm_count && (ctx->batch_streams == 2 || (ctx->batch_streams == 0 && small_graph));
     auto issue_copy = [&](int q) {
         // download of query q on the copy stream, overlapping the kernels of query q+1
         Workspace& w = g->ws[q & 1];
@@ -839,7 +912,7 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
             cudaEventElapsedTime(&st->ms_total, e[0], e[2]);
             st->launches = resident ? 2 : 3;
         }
-        if (nq > 0) { g->last_ws = (nq - 1) & 1; g->last_kind = 1; x->last_divisor = 0.0; }
+        if (nq > 0) { g->last_ws = (nq - 1) & 1; g->last_kind = 1; x->last_divisor = 0.0; x->last_is_pm = false; }
     }
     return rc;
 }
@@ -872,7 +945,7 @@ extern "C" int32_t ppr_monte_carlo_shard(ppr_graph* g, int32_t src, double alpha
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
     rc = read_ctl(g, w); if (rc) return rc;
-    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = omega;
+    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = omega; extra_of(g)->last_is_pm = false;
     if (stats) {
         stats_from_ctl(stats, w.ctl_host, omega);
         stats->walks_total = (i64)W;
@@ -958,21 +1031,25 @@ static int32_t run_select(ppr_graph* g, Workspace& w, const u64* vals, i64 n, i6
 
 // survivors -> (value desc, id asc), the order of getTopKNodeIds (J/Fora_Topk.java:82-99; ties are unordered there)
 static int32_t fetch_survivors(ppr_graph* g, Workspace& w, std::vector<i32>& ids, std::vector<u64>& vals) {
+    // the <= k + ties survivors are put in order (value descending, id ascending) on the device (k_rank_sort) and downloaded once
     ppr_ctx* ctx = g->ctx;
     i64 cnt = w.ctl_host->sel_count;
     if (cnt > w.sel_cap) return ctx_fail(ctx, PPR_E_CAPACITY, "top-k: too many tied survivors for the selection buffer");
-    std::vector<i32> ti((size_t)cnt);
-    std::vector<u64> tv((size_t)cnt);
+    ids.resize((size_t)cnt); vals.resize((size_t)cnt);
     if (cnt) {
-        CUDA_TRY(cudaMemcpyAsync(ti.data(), w.sel_ids, (size_t)cnt * sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(tv.data(), w.sel_vals, (size_t)cnt * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        GraphExtra* x = extra_of(g);
+        if (x->sort_cap < cnt) {
+            cudaFree(x->sort_ids); cudaFree(x->sort_vals); x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0;
+            const i64 cap = std::max<i64>(cnt, 4096);
+            CUDA_TRY(dalloc(&x->sort_ids, (size_t)cap)); CUDA_TRY(dalloc(&x->sort_vals, (size_t)cap));
+            x->sort_cap = cap;
+        }
+        k_rank_sort<<<(unsigned)std::min<i64>((cnt + 127) / 128, 4096), 128, 0, ctx->stream>>>(w.sel_ids, w.sel_vals, cnt, x->sort_ids, x->sort_vals);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(ids.data(), x->sort_ids, (size_t)cnt * sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(vals.data(), x->sort_vals, (size_t)cnt * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
-    std::vector<i64> ord((size_t)cnt);
-    for (i64 i = 0; i < cnt; i++) ord[(size_t)i] = i;
-    std::sort(ord.begin(), ord.end(), [&](i64 a, i64 b) { return tv[a] != tv[b] ? tv[a] > tv[b] : ti[a] < ti[b]; });
-    ids.resize((size_t)cnt); vals.resize((size_t)cnt);
-    for (i64 i = 0; i < cnt; i++) { ids[(size_t)i] = ti[(size_t)ord[(size_t)i]]; vals[(size_t)i] = tv[(size_t)ord[(size_t)i]]; }
     return PPR_OK;
 }
 
@@ -1037,7 +1114,7 @@ static int32_t fora_topk_impl(ppr_graph* g, int32_t src, double alpha, double ep
         delta_local = std::max(min_delta, delta_local / 4.0);
     }
     CUDA_TRY(cudaEventRecord(ctx->ev[5], ctx->stream));
-    g->last_ws = 0; g->last_kind = 2; extra_of(g)->last_divisor = 0.0;
+    g->last_ws = 0; g->last_kind = 2; extra_of(g)->last_divisor = 0.0; extra_of(g)->last_is_pm = false;
     std::vector<i32> ids; std::vector<u64> vals;
     rc = fetch_survivors(g, w, ids, vals); if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1070,37 +1147,46 @@ extern "C" int32_t ppr_topk(ppr_ctx* ctx, const double* vec, int64_t n, int32_t 
     if (!ctx) return PPR_E_INVALID;
     if (!vec || n < 1 || !count_out || cap < 0 || (cap > 0 && (!ids_out || !vals_out))) return ctx_fail(ctx, PPR_E_INVALID, "ppr_topk: bad arguments");
     cudaSetDevice(ctx->device);
-    // a throw-away pseudo graph/workspace: only the selection buffers are needed
-    double* d_vec = nullptr; u64* d_bits = nullptr; u32* hist = nullptr; i32* sel_ids = nullptr; u64* sel_vals = nullptr; PushCtl* ctl = nullptr;
+    // grow-only device scratch kept by the context (getTopKNodeIds is called once per query by Forward_Push / Monte_Carlo /
+    // Power_Method): vector, bit image, survivors and ordered survivors, histograms, control block
+    const size_t N = (size_t)n, al = 256;
+    auto up = [&](size_t x) { return (x + al - 1) / al * al; };
+    const size_t o_vec = 0, o_bits = o_vec + up(N * 8), o_sv = o_bits + up(N * 8), o_ov = o_sv + up(N * 8), o_si = o_ov + up(N * 8),
+                 o_oi = o_si + up(N * 4), o_hist = o_oi + up(N * 4), o_ctl = o_hist + up(9 * 256 * 4), total = o_ctl + up(sizeof(PushCtl));
+    if (ctx->topk_bytes < total) {
+        cudaFree(ctx->topk_buf); ctx->topk_buf = nullptr; ctx->topk_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->topk_buf, total));
+        ctx->topk_bytes = total;
+    }
+    char* base = static_cast<char*>(ctx->topk_buf);
+    double* d_vec = reinterpret_cast<double*>(base + o_vec); u64* d_bits = reinterpret_cast<u64*>(base + o_bits);
+    u64* sel_vals = reinterpret_cast<u64*>(base + o_sv); u64* ord_vals = reinterpret_cast<u64*>(base + o_ov);
+    i32* sel_ids = reinterpret_cast<i32*>(base + o_si); i32* ord_ids = reinterpret_cast<i32*>(base + o_oi);
+    u32* hist = reinterpret_cast<u32*>(base + o_hist); PushCtl* ctl = reinterpret_cast<PushCtl*>(base + o_ctl);
     PushCtl hctl;
-    int32_t rc = PPR_OK;
-    cudaError_t e = cudaSuccess;
-    auto done = [&]() { cudaFree(d_vec); cudaFree(d_bits); cudaFree(hist); cudaFree(sel_ids); cudaFree(sel_vals); cudaFree(ctl); };
-#define T_TRY(expr) do { e = (expr); if (e != cudaSuccess) { done(); return ctx_fail_cuda(ctx, e, #expr, __FILE__, __LINE__); } } while (0)
-    T_TRY(dalloc(&d_vec, (size_t)n)); T_TRY(dalloc(&d_bits, (size_t)n)); T_TRY(dalloc(&hist, (size_t)9 * 256));
-    T_TRY(dalloc(&sel_ids, (size_t)n)); T_TRY(dalloc(&sel_vals, (size_t)n)); T_TRY(dalloc(&ctl, 1));
-    T_TRY(cudaMemcpyAsync(d_vec, vec, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_vec, vec, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     k_import_f64<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_vec, d_bits, n);
-    T_TRY(cudaGetLastError());
+    CUDA_TRY(cudaGetLastError());
     int occ = 0;
-    T_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_topk_select, SEL_THREADS, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_topk_select, SEL_THREADS, 0));
     SelArgs S;
     S.vals = d_bits; S.n = n; S.k = k; S.hist = hist; S.sel_ids = sel_ids; S.sel_vals = sel_vals; S.sel_cap = n; S.ctl = ctl;
     void* args[] = {&S};
-    T_TRY(cudaLaunchCooperativeKernel((const void*)k_topk_select, dim3(ctx->sm_count * std::max(1, std::min(occ, 4))), dim3(SEL_THREADS), args, 0, ctx->stream));
-    T_TRY(cudaMemcpyAsync(&hctl, ctl, sizeof hctl, cudaMemcpyDeviceToHost, ctx->stream));
-    T_TRY(cudaStreamSynchronize(ctx->stream));
-    i64 cnt = hctl.sel_count;
-    std::vector<i32> ti((size_t)cnt);
-    if (cnt) { T_TRY(cudaMemcpy(ti.data(), sel_ids, (size_t)cnt * sizeof(i32), cudaMemcpyDeviceToHost)); }
-#undef T_TRY
-    done();
-    std::sort(ti.begin(), ti.end(), [&](i32 a, i32 b) { return vec[a] != vec[b] ? vec[a] > vec[b] : a < b; });
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_topk_select, dim3(ctx->sm_count * std::max(1, std::min(occ, 4))), dim3(SEL_THREADS), args, 0, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&hctl, ctl, sizeof hctl, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const i64 cnt = hctl.sel_count;
     *count_out = (int32_t)cnt;
     if (kth_out) { double kd; u64 kb = hctl.sel_kth; memcpy(&kd, &kb, 8); *kth_out = kb ? kd : 0.0; }
     if (cnt > cap) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_topk: output buffers too small");
-    for (i64 i = 0; i < cnt; i++) { ids_out[i] = ti[(size_t)i]; vals_out[i] = vec[ti[(size_t)i]]; }
-    return rc;
+    if (cnt) {   // value descending, id ascending, ordered on the device; the bit images are the doubles themselves
+        k_rank_sort<<<(unsigned)std::min<i64>((cnt + 127) / 128, 4096), 128, 0, ctx->stream>>>(sel_ids, sel_vals, cnt, ord_ids, ord_vals);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(ids_out, ord_ids, (size_t)cnt * sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(vals_out, ord_vals, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return PPR_OK;
 }
 
 // ============================================================================================= multi-GPU (NCCL behind the ABI)
@@ -1257,9 +1343,95 @@ extern "C" int32_t ppr_power_iteration(ppr_graph* g, int32_t src, double alpha, 
     }
     P_TRY(cudaGetLastError());
     P_TRY(cudaMemcpyAsync(out, res, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    {   // the result also stays on the device for ppr_metrics_keep (on-device error metrics against this ground truth)
+        GraphExtra* x = extra_of(g);
+        if (!x->pm_result) P_TRY(dalloc(&x->pm_result, (size_t)n));
+        P_TRY(cudaMemcpyAsync(x->pm_result, res, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        x->last_is_pm = true;
+    }
     P_TRY(cudaStreamSynchronize(ctx->stream));
 #undef P_TRY
     done();
+    return PPR_OK;
+}
+
+// ============================================================================================= error metrics on the device
+// Gen_Util.computeError (J/Gen_Util.java:259-326).  ppr_metrics_keep snapshots the result of the last query (as doubles, on
+// the device) as ground truth (slot 0: normally the power iteration) or estimate (slot 1); ppr_metrics_compute evaluates
+// MAX_ERR, PRECISION and NDCG of slot 1 against slot 0 without moving either vector to the host.
+extern "C" int32_t ppr_metrics_keep(ppr_graph* g, int32_t slot) {
+    if (!g) return PPR_E_INVALID;
+    ppr_ctx* ctx = g->ctx;
+    if (slot < 0 || slot > 1) return ctx_fail(ctx, PPR_E_INVALID, "ppr_metrics_keep: slot must be 0 (ground truth) or 1 (estimate)");
+    GraphExtra* x = extra_of(g);
+    cudaSetDevice(ctx->device);
+    const i64 n = g->d.n;
+    if (!x->metric_vec[slot]) CUDA_TRY(dalloc(&x->metric_vec[slot], (size_t)n));
+    if (x->last_is_pm) {
+        CUDA_TRY(cudaMemcpyAsync(x->metric_vec[slot], x->pm_result, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        if (g->last_kind == 0) return ctx_fail(ctx, PPR_E_STATE, "ppr_metrics_keep: no query has run");
+        Workspace& w = g->ws[g->last_ws];
+        k_export_f64<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->last_kind == 2 ? w.est : w.reserve, x->metric_vec[slot], n, x->last_divisor);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    x->metric_set[slot] = true;
+    return PPR_OK;
+}
+
+// tie-inclusive top-k of a double vector resident on the device, ordered (value descending, id ascending), left on the device
+static int32_t device_topk_f64(ppr_graph* g, Workspace& w, const double* vec, i64 k, i32* ids_out, u64* vals_out, i64 cap, i64* count) {
+    ppr_ctx* ctx = g->ctx;
+    const i64 n = g->d.n;
+    k_import_f64<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(vec, w.q[0], n);   // order-preserving bit image; q[0] is free outside a push
+    CUDA_TRY(cudaGetLastError());
+    int32_t rc = run_select(g, w, w.q[0], n, k); if (rc) return rc;
+    rc = read_ctl(g, w); if (rc) return rc;
+    const i64 c = w.ctl_host->sel_count;
+    if (c > w.sel_cap || c > cap) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_metrics_compute: too many tied top-k entries");
+    if (c) { k_rank_sort<<<(unsigned)std::min<i64>((c + 127) / 128, 4096), 128, 0, ctx->stream>>>(w.sel_ids, w.sel_vals, c, ids_out, vals_out); CUDA_TRY(cudaGetLastError()); }
+    *count = c;
+    return PPR_OK;
+}
+
+extern "C" int32_t ppr_metrics_compute(ppr_graph* g, int32_t k, double* max_err, double* precision, double* ndcg) {
+    if (!g) return PPR_E_INVALID;
+    ppr_ctx* ctx = g->ctx;
+    GraphExtra* x = extra_of(g);
+    if (!x->metric_set[0] || !x->metric_set[1]) return ctx_fail(ctx, PPR_E_STATE, "ppr_metrics_compute: keep a ground truth (slot 0) and an estimate (slot 1) first");
+    if (k < 0) return ctx_fail(ctx, PPR_E_INVALID, "ppr_metrics_compute: k < 0");
+    cudaSetDevice(ctx->device);
+    const i64 n = g->d.n;
+    Workspace& w = g->ws[0];
+    ull* d_bits = nullptr; double* d_out = nullptr; double* d_gain = nullptr; i32* ids[2] = {nullptr, nullptr}; u64* vals[2] = {nullptr, nullptr};
+    const i64 cap = w.sel_cap;
+    auto done = [&]() { cudaFree(d_bits); cudaFree(d_out); cudaFree(d_gain); cudaFree(ids[0]); cudaFree(ids[1]); cudaFree(vals[0]); cudaFree(vals[1]); };
+#define M_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { done(); return ctx_fail_cuda(ctx, e__, #expr, __FILE__, __LINE__); } } while (0)
+    M_TRY(dalloc(&d_bits, 1)); M_TRY(dalloc(&d_out, 2));
+    M_TRY(cudaMemsetAsync(d_bits, 0, 8, ctx->stream)); M_TRY(cudaMemsetAsync(d_out, 0, 16, ctx->stream));
+    k_max_err<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(x->metric_vec[0], x->metric_vec[1], n, d_bits);
+    M_TRY(cudaGetLastError());
+    i64 cnt[2] = {0, 0};
+    if (k > 0 && (precision || ndcg)) {
+        for (int s = 0; s < 2; s++) {
+            M_TRY(dalloc(&ids[s], (size_t)cap)); M_TRY(dalloc(&vals[s], (size_t)cap));
+            int32_t rc = device_topk_f64(g, w, x->metric_vec[s], k, ids[s], vals[s], cap, &cnt[s]);
+            if (rc) { done(); return rc; }
+        }
+        M_TRY(dalloc(&d_gain, (size_t)std::max<i64>(cnt[1], 1)));
+        k_topk_metrics<<<1, 256, 0, ctx->stream>>>(ids[0], vals[0], cnt[0], ids[1], cnt[1], d_gain, d_out);
+        M_TRY(cudaGetLastError());
+    }
+    ull h_bits = 0; double h_out[2] = {0, 0};
+    M_TRY(cudaMemcpyAsync(&h_bits, d_bits, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    M_TRY(cudaMemcpyAsync(h_out, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    M_TRY(cudaStreamSynchronize(ctx->stream));
+#undef M_TRY
+    done();
+    if (max_err) memcpy(max_err, &h_bits, 8);
+    if (precision) *precision = h_out[0];
+    if (ndcg) *ndcg = h_out[1];
     return PPR_OK;
 }
 
@@ -1334,7 +1506,7 @@ extern "C" int32_t ppr_backward_search(ppr_graph* g, int32_t target, double alph
     Workspace& w = g->ws[0];
     CUDA_TRY(cudaMemcpyAsync(w.reserve, b.reserve, (size_t)g->d.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(w.r, b.r, (size_t)g->d.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0;
+    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0; extra_of(g)->last_is_pm = false;
     rc = export_vec(g, w, w.reserve, 0.0, reserve_out, ctx->stream); if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (stats) {
@@ -1347,10 +1519,9 @@ extern "C" int32_t ppr_backward_search(ppr_graph* g, int32_t target, double alph
 }
 
 static void apply_topk_rows(ppr_pairs* P, int32_t k);
+static int32_t pairs_to_host(ppr_ctx* ctx, ppr_pairs* P);
 
-// Launch configuration of k_bwd_cta: CTA size and CTAs per SM.  Cheap searches (large thresholds: a few thousand relaxed
-// edges, frontiers of a few dozen vertices) are latency chains -- many small CTAs; expensive ones want wide CTAs.
-// The first launch of a call probes with 256 x 4; PPR_BWD_BD / PPR_BWD_CPS override (tuning).
+// Launch configuration of k_bwd_cta: CTA size and CTAs per SM (PPR_BWD_BD / PPR_BWD_CPS / PPR_BWD_SLOTS override it for tuning runs).
 template <int BD>
 static cudaError_t launch_bwd_cta(const BwdCtaArgs& A, int slots, cudaStream_t st) {
     k_bwd_cta<BD><<<slots, BD, 0, st>>>(A);
@@ -1366,10 +1537,11 @@ static cudaError_t launch_bwd_cta_bd(int bd, const BwdCtaArgs& A, int slots, cud
     }
 }
 static void bwd_cta_config(ppr_ctx* ctx, double edges_per_target, int* bd, int* cps) {
-    if (edges_per_target < 0) { *bd = 256; *cps = 4; }                 // probe
-    else if (edges_per_target < 16384.0) { *bd = 128; *cps = 12; }
-    else if (edges_per_target < 131072.0) { *bd = 256; *cps = 6; }
-    else { *bd = 512; *cps = 3; }
+    // Measured on B200 (profiles/r02_bwd_cta_shapes.txt): one 1024-thread CTA per SM wins at every threshold of the reference
+    // grid -- the fewer searches are in flight, the more of their sparse state stays in the L2 (148 slots: 60 / 101 / 1111 ms
+    // at 1e-3 / 5e-4 / 5e-5; 1184 slots of 128 threads: 193 / 303 / 2555 ms).
+    (void)edges_per_target;
+    *bd = 1024; *cps = 1;
     const char* e;
     if ((e = getenv("PPR_BWD_BD"))) { int v = atoi(e); if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) *bd = v; }
     if ((e = getenv("PPR_BWD_CPS"))) { int v = atoi(e); if (v >= 1 && v <= 32) *cps = v; }
@@ -1464,26 +1636,30 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     i64 cursor = 0;                     // pairs accepted so far (device buffer 0)
     double edges_per_target = -1.0;
     CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    const bool timing = getenv("PPR_BWD_TIMING") != nullptr;
+    ull h_tim[5] = {0, 0, 0, 0, 0};
     for (i64 t0 = t_lo; t0 < t_hi;) {
         int bd, cps;
         bwd_cta_config(ctx, edges_per_target, &bd, &cps);
         const i64 remaining = t_hi - t0;
         i64 Tb = remaining;
         if (ctx->bwd_batch > 0) Tb = std::min<i64>(Tb, ctx->bwd_batch);
-        else if (edges_per_target < 0) Tb = std::min<i64>(Tb, std::max<i64>(1024, (i64)ctx->sm_count * 8));   // probe launch
-        const int slots = (int)std::max<i64>(1, std::min<i64>(std::min<i64>((i64)ctx->sm_count * cps, max_slots), Tb));
+        else if (launches == 0) Tb = std::min<i64>(Tb, std::max<i64>(2048, (i64)ctx->sm_count * 16));   // first launch: learn the pairs per target
+        i64 want_slots = (i64)ctx->sm_count * cps;
+        { const char* e = getenv("PPR_BWD_SLOTS"); if (e && atoll(e) > 0) want_slots = atoll(e); }
+        const int slots = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(want_slots, max_slots), Tb));
         int32_t rc = bcw_ensure(g, slots, bd); if (rc) return rc;
         BwdCtaWorkspace& b = x->bcw;
         // room for this launch's pairs: estimate from what has been seen, retry with the exact need on overflow
         i64 want = cursor + (launches ? (i64)((double)cursor / (double)(t0 - t_lo) * (double)Tb * 1.25) + 65536 : std::max<i64>((i64)1 << 22, Tb * 64));
         rc = bcw_reserve_pairs(ctx, b, want, cursor); if (rc) return rc;
         for (;;) {
-            ull h_cnt[4] = {(ull)cursor, (ull)pushes, (ull)edges, (ull)iters};
+            ull h_cnt[16] = {(ull)cursor, (ull)pushes, (ull)edges, (ull)iters, h_tim[0], h_tim[1], h_tim[2], h_tim[3], h_tim[4], 0, 0, 0, 0, 0, 0, 0};
             CUDA_TRY(cudaMemcpyAsync(b.counters, h_cnt, sizeof h_cnt, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(cudaMemsetAsync(b.ticket, 0, 4, ctx->stream));
             A.r = b.r; A.reserve = b.reserve; A.front = b.front; A.pushed = b.pushed; A.touched = b.touched; A.st_pk = b.st_pk; A.st_y = b.st_y;
             A.ticket = b.ticket; A.counters = b.counters; A.t_lo = (i32)t0; A.t_hi = (i32)(t0 + Tb);
-            A.out_key = b.key[0]; A.out_val = b.val[0]; A.out_cap = b.cap;
+            A.out_key = b.key[0]; A.out_val = b.val[0]; A.out_cap = b.cap; A.timing = timing ? 1 : 0;
             CUDA_TRY(launch_bwd_cta_bd(bd, A, slots, ctx->stream));
             CUDA_TRY(cudaMemcpyAsync(h_cnt, b.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1493,40 +1669,43 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
                 continue;
             }
             cursor = (i64)h_cnt[0]; pushes = (i64)h_cnt[1]; edges = (i64)h_cnt[2]; iters = (i64)h_cnt[3];
+            for (int i = 0; i < 5; i++) h_tim[i] = h_cnt[4 + i];
             break;
         }
         tm.mark("reverse-push launch");
         t0 += Tb;
         edges_per_target = (double)edges / (double)(t0 - t_lo);
     }
+    if (timing && h_tim[4])
+        fprintf(stderr, "[pprb200] k_bwd_cta per target (thread 0 clock, us): ticket+seed %.2f  phase A %.2f  phase B %.2f  output+clean %.2f  (%llu targets with in-edges, %.2f iterations each)\n",
+                h_tim[0] / 1e3 / h_tim[4], h_tim[1] / 1e3 / h_tim[4], h_tim[2] / 1e3 / h_tim[4], h_tim[3] / 1e3 / h_tim[4], h_tim[4], (double)iters / (double)h_tim[4]);
     CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (cursor > 0xffffffffll) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_backward_all_pairs: more than 2^32 pairs in one call; split the target range");
-    // inverted index grouped by source v, targets ascending (J/Base_Whole_Graph.java:83-87): device radix sort + row pointers
+    // inverted index grouped by source v, targets ascending (J/Base_Whole_Graph.java:83-87): device radix sort + row pointers.
+    // The index stays on the device; ppr_pairs_export copies it into the caller's arrays.
     ppr_pairs* P = new (std::nothrow) ppr_pairs();
     if (!P) return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed");
-    P->n = n;
-    i32* d_tgt = nullptr; i64* d_ptr = nullptr;
-    auto fail = [&](int32_t code) { cudaFree(d_tgt); cudaFree(d_ptr); delete P; return code; };
-    try { P->src_ptr.assign((size_t)n + 1, 0); P->tgt.resize((size_t)cursor); P->val.resize((size_t)cursor); }
+    P->n = n; P->count = cursor; P->device = ctx->device; P->d_tgt = nullptr; P->d_val = nullptr; P->on_host = false;
+    i64* d_ptr = nullptr;
+    auto fail = [&](int32_t code) { cudaFree(d_ptr); ppr_pairs_destroy(P); return code; };
+    try { P->src_ptr.assign((size_t)n + 1, 0); }
     catch (...) { return fail(ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed")); }
 #define P_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail(ctx_fail_cuda(ctx, e__, #expr, __FILE__, __LINE__)); } while (0)
-    if (!x->bcw_ready) { int32_t rc = bcw_ensure(g, 1, 256); if (rc) return fail(rc); }   // empty target range: nothing was launched
+    if (!x->bcw_ready) { int32_t rc = bcw_ensure(g, 1, 1024); if (rc) return fail(rc); }   // empty target range: nothing was launched
     BwdCtaWorkspace& b = x->bcw;
-    P_TRY(dalloc(&d_tgt, (size_t)cursor)); P_TRY(dalloc(&d_ptr, (size_t)n + 1));
+    P_TRY(dalloc(&P->d_tgt, (size_t)cursor)); P_TRY(dalloc(&P->d_val, (size_t)cursor)); P_TRY(dalloc(&d_ptr, (size_t)n + 1));
     int buf = 0;
-    { int32_t rc = sort_pairs(ctx, b, cursor, key_bits, n, d_tgt, d_ptr, &buf); if (rc) return fail(rc); }
+    { int32_t rc = sort_pairs(ctx, b, cursor, key_bits, n, P->d_tgt, d_ptr, &buf); if (rc) return fail(rc); }
+    if (cursor) P_TRY(cudaMemcpyAsync(P->d_val, b.val[buf], (size_t)cursor * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     P_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
     P_TRY(cudaMemcpyAsync(P->src_ptr.data(), d_ptr, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (cursor) {
-        P_TRY(cudaMemcpyAsync(P->tgt.data(), d_tgt, (size_t)cursor * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        P_TRY(cudaMemcpyAsync(P->val.data(), b.val[buf], (size_t)cursor * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    }
     P_TRY(cudaStreamSynchronize(ctx->stream));
 #undef P_TRY
-    cudaFree(d_tgt); cudaFree(d_ptr);
-    tm.mark("sort + download");
-    if (k >= 0) {
-        try { apply_topk_rows(P, k); } catch (...) { delete P; return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
+    cudaFree(d_ptr); d_ptr = nullptr;
+    tm.mark("sort + row pointers");
+    if (k >= 0) {   // J/Base_Whole_Graph.java:133-148 on the host (rows are short after the cut; not the throughput path)
+        int32_t rc = pairs_to_host(ctx, P); if (rc) { ppr_pairs_destroy(P); return rc; }
+        try { apply_topk_rows(P, k); } catch (...) { ppr_pairs_destroy(P); return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
     }
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -1562,6 +1741,22 @@ static void apply_topk_rows(ppr_pairs* P, int32_t k) {
         nptr[(size_t)v + 1] = (i64)ntgt.size();
     }
     P->src_ptr.swap(nptr); P->tgt.swap(ntgt); P->val.swap(nval);
+    P->count = (i64)P->tgt.size();
+}
+
+// move a device-resident index into the host vectors of the handle
+static int32_t pairs_to_host(ppr_ctx* ctx, ppr_pairs* P) {
+    if (P->on_host) return PPR_OK;
+    try { P->tgt.resize((size_t)P->count); P->val.resize((size_t)P->count); }
+    catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_pairs: host allocation failed"); }
+    cudaSetDevice(P->device);
+    if (P->count) {
+        CUDA_TRY(cudaMemcpy(P->tgt.data(), P->d_tgt, (size_t)P->count * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(P->val.data(), P->d_val, (size_t)P->count * 8, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(P->d_tgt); cudaFree(P->d_val); P->d_tgt = nullptr; P->d_val = nullptr;
+    P->on_host = true;
+    return PPR_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- all pairs over the ranks
@@ -1618,8 +1813,8 @@ extern "C" int32_t ppr_backward_all_pairs_sharded(ppr_graph* g, double alpha, do
     i64 *d_cnt = nullptr, *d_all = nullptr, *d_rows = nullptr, *d_base = nullptr, *d_mptr = nullptr;
     i32 *d_tin = nullptr, *d_tout = nullptr; u64 *d_vin = nullptr, *d_vout = nullptr;
     ppr_pairs* P = nullptr;
-    auto done = [&]() { cudaFree(d_cnt); cudaFree(d_all); cudaFree(d_rows); cudaFree(d_base); cudaFree(d_mptr); cudaFree(d_tin); cudaFree(d_tout); cudaFree(d_vin); cudaFree(d_vout); };
-    auto fail = [&](int32_t code) { done(); delete L; delete P; return code; };
+    auto done = [&]() { cudaFree(d_cnt); cudaFree(d_all); cudaFree(d_rows); cudaFree(d_base); cudaFree(d_mptr); cudaFree(d_tin); cudaFree(d_vin); };
+    auto fail = [&](int32_t code) { done(); cudaFree(d_tout); cudaFree(d_vout); ppr_pairs_destroy(L); if (P) { P->d_tgt = nullptr; P->d_val = nullptr; ppr_pairs_destroy(P); } return code; };
 #define S_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail(ctx_fail_cuda(ctx, e__, #expr, __FILE__, __LINE__)); } while (0)
 #define SN_TRY(expr) do { ncclResult_t r__ = (expr); if (r__ != ncclSuccess) return fail(ctx_fail(ctx, PPR_E_COMM, std::string("NCCL: ") + api->GetErrorString(r__) + " in " #expr)); } while (0)
     cudaEvent_t e0 = ctx->ev[3], e1 = ctx->ev[4];
@@ -1637,9 +1832,14 @@ extern "C" int32_t ppr_backward_all_pairs_sharded(ppr_graph* g, double alpha, do
     const i64 total = base[(size_t)world];
     S_TRY(dalloc(&d_tin, (size_t)total)); S_TRY(dalloc(&d_vin, (size_t)total)); S_TRY(dalloc(&d_tout, (size_t)total)); S_TRY(dalloc(&d_vout, (size_t)total));
     const i64 mine = base[(size_t)rank + 1] - base[(size_t)rank];
-    if (mine) {
-        S_TRY(cudaMemcpyAsync(d_tin + base[(size_t)rank], L->tgt.data(), (size_t)mine * 4, cudaMemcpyHostToDevice, ctx->stream));
-        S_TRY(cudaMemcpyAsync(d_vin + base[(size_t)rank], L->val.data(), (size_t)mine * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (mine) {   // the local index is device resident (k < 0): no host round trip
+        if (L->on_host) {
+            S_TRY(cudaMemcpyAsync(d_tin + base[(size_t)rank], L->tgt.data(), (size_t)mine * 4, cudaMemcpyHostToDevice, ctx->stream));
+            S_TRY(cudaMemcpyAsync(d_vin + base[(size_t)rank], L->val.data(), (size_t)mine * 8, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            S_TRY(cudaMemcpyAsync(d_tin + base[(size_t)rank], L->d_tgt, (size_t)mine * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            S_TRY(cudaMemcpyAsync(d_vin + base[(size_t)rank], L->d_val, (size_t)mine * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
     }
     SN_TRY(api->GroupStart());
     for (int r = 0; r < world; r++) {
@@ -1656,34 +1856,57 @@ extern "C" int32_t ppr_backward_all_pairs_sharded(ppr_graph* g, double alpha, do
     S_TRY(cudaGetLastError());
     P = new (std::nothrow) ppr_pairs();
     if (!P) return fail(ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs_sharded: host allocation failed"));
-    try { P->n = n; P->src_ptr = mptr; P->tgt.resize((size_t)total); P->val.resize((size_t)total); }
+    P->n = n; P->count = total; P->device = ctx->device; P->d_tgt = nullptr; P->d_val = nullptr; P->on_host = false;
+    try { P->src_ptr = mptr; }
     catch (...) { return fail(ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs_sharded: host allocation failed")); }
-    if (total) {
-        S_TRY(cudaMemcpyAsync(P->tgt.data(), d_tout, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        S_TRY(cudaMemcpyAsync(P->val.data(), d_vout, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    }
     S_TRY(cudaEventRecord(e1, ctx->stream));
     S_TRY(cudaStreamSynchronize(ctx->stream));
 #undef S_TRY
 #undef SN_TRY
+    P->d_tgt = d_tout; P->d_val = d_vout; d_tout = nullptr; d_vout = nullptr;   // the merged index stays on the device (ppr_pairs_export)
     if (stats) { cudaEventElapsedTime(&stats->ms_comm, e0, e1); stats->ms_total += stats->ms_comm; }
     done();
-    delete L;
-    if (k >= 0) apply_topk_rows(P, k);
+    ppr_pairs_destroy(L);
+    if (k >= 0) {   // re-select per source over the union of the ranks' rows (J/Base_Whole_Graph.java:133-148)
+        rc = pairs_to_host(ctx, P); if (rc) { ppr_pairs_destroy(P); return rc; }
+        try { apply_topk_rows(P, k); } catch (...) { ppr_pairs_destroy(P); return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs_sharded: host allocation failed"); }
+    }
     *out = P;
     return PPR_OK;
 }
 
-extern "C" int64_t ppr_pairs_count(const ppr_pairs* p) { return p ? (int64_t)p->tgt.size() : -1; }
+extern "C" int64_t ppr_pairs_count(const ppr_pairs* p) { return p ? (int64_t)p->count : -1; }
 extern "C" int32_t ppr_pairs_export(const ppr_pairs* p, int64_t* src_ptr, int32_t* tgt, double* val, uint64_t* val_fx) {
     if (!p || !src_ptr) return PPR_E_INVALID;
     memcpy(src_ptr, p->src_ptr.data(), p->src_ptr.size() * sizeof(i64));
-    if (tgt && !p->tgt.empty()) memcpy(tgt, p->tgt.data(), p->tgt.size() * sizeof(i32));
-    if (val) for (size_t i = 0; i < p->val.size(); i++) val[i] = (double)p->val[i] * FX_INV;
-    if (val_fx && !p->val.empty()) memcpy(val_fx, p->val.data(), p->val.size() * sizeof(u64));
+    if (p->count == 0) return PPR_OK;
+    if (p->on_host) {
+        if (tgt) memcpy(tgt, p->tgt.data(), p->tgt.size() * sizeof(i32));
+        if (val) for (size_t i = 0; i < p->val.size(); i++) val[i] = (double)p->val[i] * FX_INV;
+        if (val_fx) memcpy(val_fx, p->val.data(), p->val.size() * sizeof(u64));
+        return PPR_OK;
+    }
+    // device-resident index: straight into the caller's arrays (doubles are converted on the device: value * 2^-62 is exact)
+    if (cudaSetDevice(p->device) != cudaSuccess) return PPR_E_CUDA;
+    const size_t c = (size_t)p->count;
+    if (tgt && cudaMemcpy(tgt, p->d_tgt, c * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return PPR_E_CUDA;
+    if (val_fx && cudaMemcpy(val_fx, p->d_val, c * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return PPR_E_CUDA;
+    if (val) {
+        double* d = nullptr;
+        if (cudaMalloc((void**)&d, c * 8) != cudaSuccess) return PPR_E_NOMEM;
+        k_export_f64<<<(unsigned)std::min<size_t>((c + 255) / 256, 65535), 256>>>(p->d_val, d, (i64)c, 0.0);
+        cudaError_t e = cudaMemcpy(val, d, c * 8, cudaMemcpyDeviceToHost);
+        cudaFree(d);
+        if (e != cudaSuccess) return PPR_E_CUDA;
+    }
     return PPR_OK;
 }
-extern "C" int32_t ppr_pairs_destroy(ppr_pairs* p) { delete p; return PPR_OK; }
+extern "C" int32_t ppr_pairs_destroy(ppr_pairs* p) {
+    if (!p) return PPR_OK;
+    if (p->d_tgt || p->d_val) { cudaSetDevice(p->device); cudaFree(p->d_tgt); cudaFree(p->d_val); }
+    delete p;
+    return PPR_OK;
+}
 
 // ============================================================================================= stepped push (trace)
 extern "C" int32_t ppr_push_trace_begin(ppr_graph* g, int32_t src, double alpha, double rmax) {
@@ -1703,7 +1926,7 @@ extern "C" int32_t ppr_push_trace_begin(ppr_graph* g, int32_t src, double alpha,
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     g->trace_active = true; g->trace_parity = 0; g->trace_src = src; g->trace_alpha_q64 = A.alpha_q64;
-    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0;
+    g->last_ws = 0; g->last_kind = 1; extra_of(g)->last_divisor = 0.0; extra_of(g)->last_is_pm = false;
     return PPR_OK;
 }
 

@@ -67,6 +67,15 @@ struct PushArgs {
     int midi_ctas;                // > 1: frontiers of <= midi_v vertices / midi_e edges are iterated by this many CTAs (push_small)
     u32 midi_v;
     u64 midi_e;
+    // pull-direction iterations (pull.cuh): CSC with hub sources encoded, dense amount buffers, static work split
+    const u64* in_vtx;
+    const u32* pull_idx;          // row_idx with the PULL_SLOTS highest out-degree sources replaced by HOT_BIT | slot
+    const u32* pull_hot_id; u32 n_pull_hot;
+    const u32* long_v; u32 n_long;            // vertices with more than PULL_LONG in-edges
+    const uint2* long_chunk; u32 n_long_chunk; // (vertex, chunk number)
+    const u32* pull_task; u32 n_pull_task;     // boundaries (in 32-vertex groups) of runs with equal in-edge counts
+    u64* q[2];
+    i64 pull_enter, pull_exit;    // frontier edges: a dense iteration with >= pull_enter edges is followed by pull passes until the frontier has < pull_exit; pull_enter < 0: off
 };
 
 #define PMODE_PUSH 0
@@ -205,7 +214,10 @@ __device__ __forceinline__ void phase_a_recycle(PushCtl* ctl, int par) {  // the
     ctl->fcnt[par ^ 1] = 0; ctl->fedges[par ^ 1] = 0; ctl->nedge[par ^ 1] = 0;
 }
 
-constexpr int PA_ITEMS = 4;
+#ifndef PUSH_PA_ITEMS
+#define PUSH_PA_ITEMS 4
+#endif
+constexpr int PA_ITEMS = PUSH_PA_ITEMS;   // vertices per lane and tile in phase A (list and dense sweep)
 
 __device__ void push_phase_a_list(const PushArgs& A, int par, u64 rmax_fx, i64 gtid, i64 gsize, u32* sm_cnt) {
     PushCtl* ctl = A.ctl;
@@ -857,6 +869,8 @@ __device__ void walk_prep(const PushArgs& A, cg::grid_group& grid, u64* sm) {
     }
 }
 
+#include "pull.cuh"
+
 // --------------------------------------------------------------------------------- the persistent query kernel
 __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(const __grid_constant__ PushArgs A) {
     cg::grid_group grid = cg::this_grid();
@@ -914,16 +928,42 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(c
     }
     grid.sync();
 
-    int par = 0;
+    int par = 0, qb = 0;
     bool first_round = true;
+    u64* sm_hq = reinterpret_cast<u64*>(sm_hot);
     for (;;) {  // rounds (FORA: rmax halves between rounds)
         const u64 rmax_fx = *(volatile u64*)&ctl->rmax_fx;
         bool have_list = first_round && A.init;  // later rounds start with a dense sweep: rmax just changed
+        bool pull_mode = false;                  // true: the frontier of iteration `par` exists as dense amounts in q[qb] (pull.cuh)
         first_round = false;
         for (;;) {
             u64 t0 = 0, t1 = 0;
             if (gtid == 0) t0 = globaltimer_ns();
-            if (have_list) {
+            if (pull_mode) {
+                const u32 pf = *(volatile u32*)&ctl->fcnt[par];
+                const u64 pe = *(volatile u64*)&ctl->fedges[par];
+                const u64 pd = *(volatile u64*)&ctl->dang[par];
+                if (pf == 0) break;
+                if ((i64)pe >= A.pull_exit) {   // iteration `par` in pull form, fused with phase A of the next one
+                    pull_main(A, par, rmax_fx, A.q[qb], A.q[qb ^ 1], sm_hq, sm_cnt, pd);
+                    grid.sync();
+                    if (gtid == 0) t1 = globaltimer_ns();
+                    pull_long(A, par, rmax_fx, A.q[qb ^ 1], sm_cnt, pd, pf, pe);
+                    grid.sync();
+                    if (gtid == 0) {
+                        u32 k = ctl->dbg_count;
+                        if (k < DBG_ITERS) {
+                            u64* d = A.dbg + (size_t)k * DBG_FIELDS;
+                            d[0] = t0; d[1] = t1; d[2] = globaltimer_ns(); d[3] = pf; d[4] = ctl->edges; d[5] = 16;
+                            ctl->dbg_count = k + 1;
+                        }
+                    }
+                    par ^= 1; qb ^= 1;
+                    continue;
+                }
+                pull_unstage(A, par, A.q[qb]);   // frontier too small for a pull pass: back to the push direction
+                pull_mode = false;
+            } else if (have_list) {
                 const u32 c = *(volatile u32*)&ctl->cnt[par];
                 if (c == 0) break;
                 const u64 ne = *(volatile u64*)&ctl->nedge[par];
@@ -962,6 +1002,24 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_CTAS_PER_SM) k_push_query(c
             }
             have_list = !next_scan;
             par ^= 1;
+            if (next_scan && A.pull_enter >= 0 && (i64)fedges >= A.pull_enter) {
+                // a fat iteration is usually followed by another: capture the next frontier as dense amounts
+                // (instead of staging lists) and continue in the pull direction
+                u64 s0 = 0;
+                if (gtid == 0) s0 = globaltimer_ns();
+                pull_sweep_q(A, par, rmax_fx, A.q[qb], sm_cnt);
+                grid.sync();
+                pull_mode = true;
+                if (gtid == 0) {
+                    u32 k = ctl->dbg_count;
+                    if (k < DBG_ITERS) {
+                        u64* d = A.dbg + (size_t)k * DBG_FIELDS;
+                        const u64 now = globaltimer_ns();
+                        d[0] = s0; d[1] = now; d[2] = now; d[3] = 0; d[4] = ctl->edges; d[5] = 32;
+                        ctl->dbg_count = k + 1;
+                    }
+                }
+            }
         }
         if (gtid == 0) {
             // deterministic stand-in for the wall-clock balancer of J/Fora_Whole_Graph.java:93-103

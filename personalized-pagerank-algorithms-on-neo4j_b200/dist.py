@@ -81,8 +81,30 @@ def monte_carlo_sharded(graph, src, alpha, eps, seed, rank, world, out=None, gro
     return graph.result_export(st["omega"], out), st
 
 
-def merge_pairs(parts, n):
-    """Concatenate per-rank inverted indexes (src_ptr, tgt, val) whose target blocks ascend with rank."""
+def topk_rows(ptr, tgt, val, k):
+    """Base_Whole_Graph's per-source cut (J/Base_Whole_Graph.java:133-148): keep the entries >= the k-th largest value of a
+    row, sorted by value descending (stable: ties keep ascending targets).  Rows with fewer than k entries keep everything."""
+    n = ptr.shape[0] - 1
+    optr = np.zeros(n + 1, np.int64)
+    ot, ov = [], []
+    for v in range(n):
+        t, x = tgt[ptr[v]:ptr[v + 1]], val[ptr[v]:ptr[v + 1]]
+        if 1 <= k <= x.shape[0]:
+            kth = np.partition(x, x.shape[0] - k)[x.shape[0] - k]
+            keep = np.flatnonzero(x >= kth)
+        else:
+            keep = np.arange(x.shape[0])
+        keep = keep[np.argsort(-x[keep].astype(np.float64) if x.dtype.kind == "f" else (np.iinfo(np.uint64).max - x[keep].astype(np.uint64)), kind="stable")]
+        ot.append(t[keep]); ov.append(x[keep])
+        optr[v + 1] = optr[v] + keep.shape[0]
+    return optr, (np.concatenate(ot) if ot else tgt[:0]), (np.concatenate(ov) if ov else val[:0])
+
+
+def merge_pairs(parts, n, k=-1):
+    """Concatenate per-rank inverted indexes (src_ptr, tgt, val) whose target blocks ascend with rank.
+
+    The parts must be FULL rows (computed with k < 0): a rank's own top-k cut is not the cut of the merged row.  With
+    k >= 0 the cut is applied here, after the merge, over the union of the ranks' rows (as ppr_backward_all_pairs_sharded does)."""
     cnts = [np.diff(p[0]) for p in parts]
     ptr = np.zeros(n + 1, np.int64)
     np.cumsum(sum(cnts), out=ptr[1:])
@@ -97,11 +119,14 @@ def merge_pairs(parts, n):
             tgt[dst] = t
             val[dst] = v
         start += cnt
+    if k >= 0:
+        return topk_rows(ptr, tgt, val, k)
     return ptr, tgt, val
 
 
-def gather_pairs(local, n, group=None):
-    """All-gather the per-rank (src_ptr, tgt, val) results of a block-partitioned all-pair run.
+def gather_pairs(local, n, group=None, k=-1):
+    """All-gather the per-rank (src_ptr, tgt, val) results of a block-partitioned all-pair run (full rows, k < 0 on every
+    rank); k >= 0 applies the per-source top-k cut to the merged rows.
 
     With NCCL the three arrays travel as padded device tensors (one all_gather each, over NVLink); with gloo
     (CPU tests) as pickled objects.
@@ -112,7 +137,7 @@ def gather_pairs(local, n, group=None):
     if dist.get_backend(group) != "nccl":
         parts = [None] * world
         dist.all_gather_object(parts, local, group=group)
-        return merge_pairs(parts, n)
+        return merge_pairs(parts, n, k)
     dev = torch.device("cuda", torch.cuda.current_device())
     ptr, tgt, val = local
     cnt = torch.tensor([tgt.shape[0]], dtype=torch.int64, device=dev)
@@ -148,4 +173,5 @@ def gather_pairs(local, n, group=None):
             dst += torch.arange(cnts[r], dtype=torch.int64, device=dev)
             mt[dst] = T[r, :cnts[r]]
             mv[dst] = V[r, :cnts[r]]
-    return mptr.cpu().numpy(), mt.cpu().numpy(), mv.cpu().numpy().view(val.dtype)
+    out = (mptr.cpu().numpy(), mt.cpu().numpy(), mv.cpu().numpy().view(val.dtype))
+    return topk_rows(*out, k) if k >= 0 else out

@@ -135,3 +135,39 @@ def test_cpp_host_driver_on_got(pkg, tmp_path):
     assert min(prec[2:]) > 0.8
     sec = text.split("1.2 FWDPUSH\n")[1].split("\n\n")[0].splitlines()
     assert float(sec[-1].split(",")[2].replace("E", "e")) < 1e-6       # rmax 1e-8
+
+
+def test_error_metrics_on_the_device(pkg, ctx, G, O, got, rmat12):
+    """N4: Gen_Util.computeError (J/Gen_Util.java:259-326) evaluated in HBM (ppr_metrics_keep / ppr_metrics_compute) equals the
+    oracle's orc_max_err / orc_topk_metrics on the downloaded vectors: MAX_ERR exactly, PRECISION exactly, NDCG to 1e-12."""
+    for g, (rp, ci), srcs, k in ((G, got[:2], (63, 0, 71), 10), (None, rmat12, None, 50)):
+        own = g is None
+        if own:
+            g = pkg.Graph(ctx, rp, ci)
+            srcs = [int(x) for x in np.flatnonzero(np.diff(rp) > 0)[[3, 40, 400]]]
+        try:
+            for s in srcs:
+                truth = g.power_iteration(s, ALPHA, 100)
+                g.metrics_keep(0)
+                for run in ("fora", "fwdpush", "mc", "topk"):
+                    if run == "fora":
+                        est, _ = g.fora(s, ALPHA, EPS, 7)
+                    elif run == "fwdpush":
+                        est = g.forward_push(s, ALPHA, 1e-6, want_residue=False)[0]
+                    elif run == "mc":
+                        est, _ = g.monte_carlo(s, ALPHA, 1.0, 7)
+                    else:
+                        g.fora_topk(s, ALPHA, EPS, k, 7)
+                        est = g.last_raw(False)[0] * O.FX_INV
+                    g.metrics_keep(1)
+                    m = g.metrics_compute(k)
+                    assert m["max_err"] == O.max_err(truth, est), (run, s)
+                    ref = O.topk_metrics(truth, k, O.topk_select(est, k))
+                    assert m["precision"] == ref["precision"], (run, s, m, ref)
+                    assert abs(m["ndcg"] - ref["ndcg"]) < 1e-12, (run, s, m, ref)
+                    assert 0.0 <= m["precision"] <= 1.0 and m["max_err"] < 0.05
+            m0 = g.metrics_compute(0)
+            assert m0["precision"] == 0.0 and m0["max_err"] == m["max_err"]
+        finally:
+            if own:
+                g.close()

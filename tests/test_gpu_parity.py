@@ -221,6 +221,50 @@ def test_frontier_modes_give_identical_bits(ctx, G, OG, R12, O):
         ctx.set_tuning(-1)
 
 
+def test_pull_direction_gives_identical_bits(pkg, ctx, G, OG, R12, R16, O, got, rmat12):
+    # Fat iterations run in the pull direction (pull.cuh): every in-edge read once, amounts gathered from a dense array, no
+    # atomics, phase A of the next iteration fused in.  Forced after EVERY dense iteration here (enter = exit = 0, sweep
+    # threshold 0 so that every iteration is dense), then with the default switch points, then off: always the oracle's bits,
+    # work counters and iteration counts.
+    try:
+        for enter, exit_, scan in ((0.0, 0.0, 0), (0.0, 0.0, -1), (0.05, 0.02, -1), (0.30, 0.20, -1), (-1.0, 0.0, -1)):
+            ctx.set_pull(enter, exit_)
+            ctx.set_tuning(scan)
+            for g, og, srcs in ((G, OG, (0, 63, 100)), (R12[0], R12[1], sources(R12[1], 3)), (R16[0], R16[1], sources(R16[1], 1))):
+                for s in srcs:
+                    check_fora(g, og, O, s, EPS)
+                    _, _, _, st = g.forward_push(s, ALPHA, 1e-7, want_residue=False)
+                    raw_res, raw_r = g.last_raw()
+                    ores, orr, ost = O.b_forward_push(og, s, ALPHA, 1e-7)
+                    assert np.array_equal(raw_res, ores) and np.array_equal(raw_r, orr), (enter, scan, s)
+                    assert (st["pushes"], st["edges"], st["iters"]) == (ost["pushes"], ost["edges"], ost["iters"])
+                    g.fora_topk(s, ALPHA, EPS, K, SEED)
+                    assert np.array_equal(g.last_raw(False)[0], O.b_fora_topk(og, s, ALPHA, EPS, K, SEED)[0])
+        # long rows (more than 2048 in-edges, summed chunk-wise by several warps) and dangling mass returning to the source:
+        # a star-like graph: vertex 0 receives an edge from everybody, half of the vertices have no other out-edge target
+        ctx.set_pull(0.0, 0.0)
+        ctx.set_tuning(0)
+        n = 6000
+        rng = np.random.default_rng(11)
+        rows = [np.unique(np.concatenate(([0], rng.integers(0, n, rng.integers(0, 6))))) if v % 3 else np.zeros(0, np.int64) for v in range(n)]
+        rows[0] = np.unique(rng.integers(1, n, 3000))
+        rp = np.concatenate(([0], np.cumsum([len(r) for r in rows]))).astype(np.int64)
+        ci = np.concatenate(rows).astype(np.int32)
+        g, og = pkg.Graph(ctx, rp, ci), O.OGraph(rp, ci)
+        try:
+            for s in (0, 1, 2, 4):
+                check_fora(g, og, O, s, EPS)
+                g.forward_push(s, ALPHA, 1e-9, want_residue=False)
+                raw_res, raw_r = g.last_raw()
+                ores, orr, _ = O.b_forward_push(og, s, ALPHA, 1e-9)
+                assert np.array_equal(raw_res, ores) and np.array_equal(raw_r, orr), s
+        finally:
+            g.close()
+    finally:
+        ctx.set_pull(-1.0, 0.0)     # the library default: off
+        ctx.set_tuning(-1)
+
+
 def test_single_cta_iterations_give_identical_bits(G, OG, R12, R16, O, monkeypatch):
     # small frontiers are iterated by one CTA (push_mini); PPR_NO_MINI=1 keeps every iteration grid-wide.
     # Both must give the oracle's bits (the rest of this file runs with the default, i.e. mini enabled).

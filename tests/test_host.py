@@ -93,6 +93,12 @@ def _gloo_worker(rank, world, port, q):
     ptr, tgt, val = pkg.dist.gather_pairs(local, g.n)
     rptr, rtgt, rval, _ = O.b_base_all_pairs(g, 0.15, 1e-3)
     ok2 = np.array_equal(ptr, rptr) and np.array_equal(tgt, rtgt) and np.array_equal(val, rval)
+    # top-k rows (k = 3) are cut AFTER the merge, over the union of the ranks' full rows (a rank's own cut is not the merged row's)
+    kptr, ktgt, kval = pkg.dist.gather_pairs(local, g.n, k=3)
+    for v in range(g.n):
+        rt, rv = rtgt[rptr[v]:rptr[v + 1]], rval[rptr[v]:rptr[v + 1]]
+        keep = O.topk_select(rv, 3) if len(rv) else np.zeros(0, np.int32)
+        ok2 = ok2 and np.array_equal(ktgt[kptr[v]:kptr[v + 1]], rt[keep]) and np.array_equal(kval[kptr[v]:kptr[v + 1]], rv[keep])
     # FORA top-k with every round's walks sharded: one sum of the estimate vector per round, all ranks agree
     def reduce(est):
         t = torch.from_numpy(est.view(np.int64))       # shares memory with the oracle's vector
