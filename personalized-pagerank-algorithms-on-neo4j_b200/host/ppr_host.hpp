@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <ctime>
+#include <filesystem>
 #include <fstream>
 #include <map>
 #include <memory>
@@ -113,6 +114,50 @@ struct Algo_Util {
     }
 };
 
+// Preprocessing_Interface (J/Preprocessing_Interface.java) for the single-source algorithms: one text file per source,
+// "<ALGO>_ppr_results/<db>/<param>/<nodeId>.txt", lines "id \t Double.toString(value)" (J/Forward_Push.java:289-363, :432-443)
+struct Prep_Store {
+    std::string preprocessing_dirName;
+    explicit Prep_Store(const std::string& root) : preprocessing_dirName(root) {}
+    virtual ~Prep_Store() {}
+    virtual void prep_query(int64_t s, double param) = 0;            // computeWholeGraphPPR
+    virtual const std::vector<double>& prep_result() = 0;            // its dense result
+    virtual void prep_load(const std::vector<double>& dense) = 0;    // readPreprocessedPPR target
+    void preprocessing(double /*threshold, unused as in the reference*/, double param, int64_t node_amount) {
+        namespace fs = std::filesystem;
+        preprocessing_dirName += "/" + java_double(param);
+        std::error_code ec;
+        fs::remove_all(preprocessing_dirName, ec);
+        fs::create_directories(preprocessing_dirName, ec);
+        for (int64_t v = 0; v < node_amount; v++) {
+            prep_query(v, param);
+            std::ofstream f(preprocessing_dirName + "/" + std::to_string(v) + ".txt");
+            const std::vector<double>& r = prep_result();
+            for (size_t t = 0; t < r.size(); t++) if (r[t] > 0) f << t << '\t' << java_double(r[t]) << '\n';
+        }
+    }
+    void readPreprocessedPPR(int64_t s, int64_t node_amount) {
+        std::vector<double> dense((size_t)node_amount, 0.0);
+        std::ifstream f(preprocessing_dirName + "/" + std::to_string(s) + ".txt");
+        std::string line;
+        while (std::getline(f, line)) {
+            size_t tab = line.find('\t');
+            if (tab == std::string::npos) continue;
+            dense[(size_t)std::stoll(line.substr(0, tab))] = std::stod(line.substr(tab + 1));
+        }
+        prep_load(dense);
+    }
+    int64_t getPrepSize() const {
+        namespace fs = std::filesystem;
+        int64_t bytes = 0;
+        std::error_code ec;
+        for (auto it = fs::recursive_directory_iterator(preprocessing_dirName, ec); !ec && it != fs::recursive_directory_iterator(); it.increment(ec))
+            if (it->is_regular_file(ec)) bytes += (int64_t)it->file_size(ec);
+        return bytes;
+    }
+    void deletePrepDir() { std::error_code ec; std::filesystem::remove_all(preprocessing_dirName, ec); }
+};
+
 // J/Power_Method.java
 struct Power_Method : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Interface {
     Graph& adjM; double alpha;
@@ -137,10 +182,14 @@ struct Power_Method : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Interface
 };
 
 // J/Forward_Push.java
-struct Forward_Push : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Interface {
+struct Forward_Push : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Interface, Prep_Store {
     Graph& adjM; double alpha, rsum;
     std::vector<double> reserve, residue; PprMap reserve_map; std::vector<int64_t> topk_nodeIds;
-    Forward_Push(double alpha_, double rsum_, Graph& g, const std::string& prop) : Algo_Util(prop), adjM(g), alpha(alpha_), rsum(rsum_) {}
+    Forward_Push(double alpha_, double rsum_, Graph& g, const std::string& prop, const std::string& dir_db = "got.db")
+        : Algo_Util(prop), Prep_Store("FWP_ppr_results/" + dir_db), adjM(g), alpha(alpha_), rsum(rsum_) {}
+    void prep_query(int64_t s, double p) override { computeWholeGraphPPR(s, p); }
+    const std::vector<double>& prep_result() override { return reserve; }
+    void prep_load(const std::vector<double>& d) override { reserve = d; reserve_map = to_map(reserve); topk_nodeIds.clear(); }
     void computeWholeGraphPPR(int64_t s, double rmax) override {
         reserve.assign((size_t)adjM.n, 0.0); residue.assign((size_t)adjM.n, 0.0); topk_nodeIds.clear();
         check(ppr_forward_push(adjM.g, (int32_t)s, alpha, rmax, reserve.data(), residue.data(), &rsum, nullptr), adjM.ctx);
@@ -159,10 +208,14 @@ struct Forward_Push : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Interface
 };
 
 // J/Monte_Carlo.java
-struct Monte_Carlo : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Interface {
+struct Monte_Carlo : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Interface, Prep_Store {
     Graph& adjM; double alpha, pfail, delta; uint64_t seed = 1, walk_counter = 0;
     std::vector<double> ppr; PprMap ppr_map; std::vector<int64_t> topk_nodeIds;
-    Monte_Carlo(double alpha_, double pfail_, double delta_, Graph& g, const std::string& prop) : Algo_Util(prop), adjM(g), alpha(alpha_), pfail(pfail_), delta(delta_) {}
+    Monte_Carlo(double alpha_, double pfail_, double delta_, Graph& g, const std::string& prop, const std::string& dir_db = "got.db")
+        : Algo_Util(prop), Prep_Store("MC_ppr_results/" + dir_db), adjM(g), alpha(alpha_), pfail(pfail_), delta(delta_) {}
+    void prep_query(int64_t s, double p) override { computeWholeGraphPPR(s, p); }
+    const std::vector<double>& prep_result() override { return ppr; }
+    void prep_load(const std::vector<double>& d) override { ppr = d; ppr_map = to_map(ppr); topk_nodeIds.clear(); }
     int64_t random_walk(int64_t start) { return one_walk(start, 0); }
     int64_t random_walk_no_zero_hop(int64_t start) { return one_walk(start, 1); }
     void computeWholeGraphPPR(int64_t s, double eps) override {
@@ -187,11 +240,14 @@ private:
 };
 
 // J/Fora_Whole_Graph.java
-struct Fora_Whole_Graph : Algo_Util, Whole_Graph_Util_Interface {
+struct Fora_Whole_Graph : Algo_Util, Whole_Graph_Util_Interface, Prep_Store {
     Graph& adjM; double alpha, rsum, pfail, delta; uint64_t seed = 1;
     std::vector<double> reserve; PprMap reserve_map;
-    Fora_Whole_Graph(double alpha_, double rsum_, double pfail_, double delta_, Graph& g, const std::string& prop)
-        : Algo_Util(prop), adjM(g), alpha(alpha_), rsum(rsum_), pfail(pfail_), delta(delta_) {}
+    Fora_Whole_Graph(double alpha_, double rsum_, double pfail_, double delta_, Graph& g, const std::string& prop, const std::string& dir_db = "got.db")
+        : Algo_Util(prop), Prep_Store("FORA_ppr_results/" + dir_db), adjM(g), alpha(alpha_), rsum(rsum_), pfail(pfail_), delta(delta_) {}
+    void prep_query(int64_t s, double p) override { computeWholeGraphPPR(s, p); }
+    const std::vector<double>& prep_result() override { return reserve; }
+    void prep_load(const std::vector<double>& d) override { reserve = d; reserve_map = to_map(reserve); }
     void computeWholeGraphPPR(int64_t s, double eps) override {
         reserve.assign((size_t)adjM.n, 0.0);
         ppr_conf c = {delta, pfail, 0.0};
@@ -268,10 +324,10 @@ struct Algo_Conf {
     double alpha; std::string node_property;
     Algo_Conf(double a, const std::string& p) : alpha(a), node_property(p) {}
     std::unique_ptr<Power_Method> set_conf_power_method(Graph& g) { return std::make_unique<Power_Method>(alpha, g, node_property); }
-    std::unique_ptr<Monte_Carlo> set_conf_mc(int64_t n, Graph& g) { double d = 1.0 / (double)n; return std::make_unique<Monte_Carlo>(alpha, d, d, g, node_property); }
+    std::unique_ptr<Monte_Carlo> set_conf_mc(int64_t n, Graph& g, const std::string& dir_db = "got.db") { double d = 1.0 / (double)n; return std::make_unique<Monte_Carlo>(alpha, d, d, g, node_property, dir_db); }
     std::unique_ptr<Base_Whole_Graph> set_conf_base_whole_graph(Graph& g, const std::string& dir_db) { return std::make_unique<Base_Whole_Graph>(alpha, g, node_property, dir_db); }
-    std::unique_ptr<Fora_Whole_Graph> set_conf_fora_whole_graph(int64_t n, Graph& g) { double d = 1.0 / (double)n; return std::make_unique<Fora_Whole_Graph>(alpha, 1.0, d, d, g, node_property); }
-    std::unique_ptr<Forward_Push> set_conf_fwdpush(Graph& g) { return std::make_unique<Forward_Push>(alpha, 1.0, g, node_property); }
+    std::unique_ptr<Fora_Whole_Graph> set_conf_fora_whole_graph(int64_t n, Graph& g, const std::string& dir_db = "got.db") { double d = 1.0 / (double)n; return std::make_unique<Fora_Whole_Graph>(alpha, 1.0, d, d, g, node_property, dir_db); }
+    std::unique_ptr<Forward_Push> set_conf_fwdpush(Graph& g, const std::string& dir_db = "got.db") { return std::make_unique<Forward_Push>(alpha, 1.0, g, node_property, dir_db); }
     std::unique_ptr<Fora_Topk> set_conf_fora_topk(int64_t n, int k, Graph& g) {
         double min_delta = 1.0 / (double)n, delta = 1.0 / (double)k;
         double pfail = 1.0 / (double)n / (double)n / std::log((double)(n / k));   // integer n / k, J/Algo_Conf.java:76
@@ -366,6 +422,33 @@ struct Gen_Util {
         fw << avg / 1000000 << "," << java_double(sp / query_num) << "," << java_double(sn / query_num) << "\n";
         rows.push_back({name(t), base ? threshold : param, avg / 1e6, 0, sp / query_num, sn / query_num});
     }
+    // Test 3 body for FORA / Forward Push / Monte-Carlo (J/Gen_Util.java:181-252 with to_be_preprocessed = true): preprocess every
+    // source into the result store, answer the queries by reading the files back, compare with the power method, delete the store
+    void prep_test(AlgoType t, int query_num, double param, double threshold) {
+        Algo_Conf ac(alpha, node_property);
+        std::unique_ptr<Whole_Graph_Util_Interface> algo;
+        Prep_Store* store = nullptr;
+        switch (t) {
+            case MC: { auto a = ac.set_conf_mc(node_amount, adjM, dir_db); store = a.get(); algo = std::move(a); break; }
+            case FWDPUSH: { auto a = ac.set_conf_fwdpush(adjM, dir_db); store = a.get(); algo = std::move(a); break; }
+            case FORA_WHOLE_GRAPH: { auto a = ac.set_conf_fora_whole_graph(node_amount, adjM, dir_db); store = a.get(); algo = std::move(a); break; }
+            default: return;
+        }
+        auto pm = ac.set_conf_power_method(adjM);
+        std::vector<int64_t> q = getQueryNodes(query_num);
+        fw << java_double(param) << ",";
+        int64_t t0 = now_ns(); store->preprocessing(threshold, param, node_amount); int64_t prep = now_ns() - t0;
+        fw << java_double(threshold) << "," << prep / 1000000 << "," << store->getPrepSize() << ",";
+        int64_t dur = 0; double sum_err = 0;
+        for (int64_t s : q) {
+            int64_t t1 = now_ns(); store->readPreprocessedPPR(s, node_amount); dur += now_ns() - t1;
+            pm->computeWholeGraphPPR(s, 0);
+            sum_err += max_err(*algo, *pm);
+        }
+        fw << java_double(sum_err / query_num) << "\n";    // no compute time for preprocessed algorithms (:239-243)
+        store->deletePrepDir();
+        rows.push_back({std::string(name(t)) + "(prep)", param, dur / 1e6 / query_num, sum_err / query_num, 0, 0});
+    }
     // J/Gen_Util.java:328-647, active (GOT) parameter grids :454-478; the Neo4j competitor is out of scope
     void algo_perf_batch_test(int query_num, int k, const std::string& out_dir) {
         static const std::map<AlgoType, std::vector<double>> grid = {
@@ -387,6 +470,13 @@ struct Gen_Util {
             fw << "\n2." << i + 1 << " " << name(topk[i]) << "\n";
             if (topk[i] == NEO4J_METHOD) continue;
             for (double p : grid.at(topk[i])) topk[i] == BASE_WHOLE_GRAPH ? topk_test(topk[i], query_num, k, -1, p) : topk_test(topk[i], query_num, k, p, -1.0);
+        }
+        fw << "\nTest 3. Preprocessing test\n";   // J/Gen_Util.java:602-645
+        AlgoType prep[] = {FORA_WHOLE_GRAPH, FWDPUSH, NEO4J_METHOD, MC, BASE_WHOLE_GRAPH};
+        for (int i = 0; i < 5; i++) {
+            fw << "\n3." << i + 1 << " " << name(prep[i]) << "\n";
+            if (prep[i] == NEO4J_METHOD) continue;
+            for (double p : grid.at(prep[i])) prep[i] == BASE_WHOLE_GRAPH ? whole_graph_test(prep[i], query_num, -1, p) : prep_test(prep[i], query_num, p, -1.0);
         }
         fw.close();
         printf("results appended to %s\n", path.c_str());

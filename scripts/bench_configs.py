@@ -3,6 +3,8 @@
   topk      config 3: LiveJournal-shape synthetic (n = 4.8 M, m = 69 M), FORA top-k = 500
   allpairs  config 4: all-pair backward search, symmetrised R-MAT with n = 100 000, m = 1.6 M
   walks     config 5 shape: Monte-Carlo / FORA walk phase on a large R-MAT (default scale 24; 25 needs ~40 GB of host RAM)
+  sharded   config 5 through the library's own collectives (ppr_comm_init, ppr_*_sharded): one query at a time over all GPUs against
+            the same query on one GPU (every rank also runs it alone), CUDA-event times, max over ranks
 
 Prints one JSON object per config.  N > 1: walks are sharded with one NCCL all-reduce per query; all-pair
 targets are block-partitioned with a gather at the end.
@@ -14,7 +16,7 @@ pkg = importlib.import_module("personalized-pagerank-algorithms-on-neo4j_b200")
 ALPHA = 0.15
 
 ap = argparse.ArgumentParser()
-ap.add_argument("what", choices=["topk", "allpairs", "walks"])
+ap.add_argument("what", choices=["topk", "allpairs", "walks", "sharded"])
 ap.add_argument("--queries", type=int, default=8)
 ap.add_argument("--scale", type=int, default=24)
 ap.add_argument("--edge-factor", type=int, default=16)
@@ -103,6 +105,55 @@ elif a.what == "allpairs":
             sptr, stgt, sval, _ = g.backward_all_pairs(ALPHA, thr, -1, 0, sample, raw=True)
             res["%g" % thr]["first_%d_targets_bit_exact" % sample] = bool(np.array_equal(optr, sptr) and np.array_equal(otgt, stgt) and np.array_equal(oval, sval))
     out.update(workload="symmetrised R-MAT n=100000 m=1.6M, all-pair backward search, targets block-partitioned", results=res)
+elif a.what == "sharded":
+    n = 1 << a.scale
+    t0 = time.perf_counter()
+    rp, ci = pkg.rmat(n, n * a.edge_factor, seed=42)
+    gen_s = time.perf_counter() - t0
+    g = pkg.Graph(ctx, rp, ci)
+    if world > 1:
+        box = [pkg.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], rank, world)
+    S = srcs_of(rp, a.queries + 1)
+    BAL = pkg._native.BALANCE_PER_SHARD
+
+    def run(fn):     # warm-up on S[0], then the mean over the other sources; CUDA events on the library stream, max over ranks
+        fn(S[0], 0)
+        sync()
+        acc = {}
+        ctx.timer_record(0)
+        for i, s in enumerate(S[1:]):
+            st = fn(s, 1 + i)
+            for k in ("ms_push", "ms_walk", "ms_comm", "walks_total", "walks", "steps", "edges", "rounds"):
+                acc[k] = acc.get(k, 0) + st[k]
+        ctx.timer_record(1)
+        ms = ctx.timer_elapsed_ms(0, 1)
+        sync()
+        if world > 1:
+            ms = float(ctx.comm_max([ms])[0])
+        q = len(S) - 1
+        r = {k: v / q for k, v in acc.items()}
+        r["ms_per_query"] = ms / q
+        return r
+
+    res = {}
+    res["monte_carlo_1gpu"] = run(lambda s, i: g.monte_carlo_shard(s, ALPHA, 0.5, 50 + i, 0, 1))
+    res["fora_1gpu"] = run(lambda s, i: g.fora_shard(s, ALPHA, 0.5, 50 + i, 0, 1))
+    if world > 1:
+        res["monte_carlo_sharded"] = run(lambda s, i: g.monte_carlo_sharded(s, ALPHA, 0.5, 50 + i, resident=True)[1])
+        res["fora_sharded"] = run(lambda s, i: g.fora_sharded(s, ALPHA, 0.5, 50 + i, resident=True)[1])
+        res["fora_sharded_balance_per_shard"] = run(lambda s, i: g.fora_sharded(s, ALPHA, 0.5, 50 + i, flags=BAL, resident=True)[1])
+        for k in ("monte_carlo", "fora"):
+            res[k + "_speedup"] = res[k + "_1gpu"]["ms_per_query"] / res[k + "_sharded"]["ms_per_query"]
+        res["fora_speedup_balance_per_shard"] = res["fora_1gpu"]["ms_per_query"] / res["fora_sharded_balance_per_shard"]["ms_per_query"]
+        res["walks_only_speedup"] = res["monte_carlo_1gpu"]["ms_walk"] / res["monte_carlo_sharded"]["ms_walk"]
+        res["comm"] = ctx.comm_info()
+    res["monte_carlo_walks_per_s"] = res["monte_carlo_1gpu"]["walks_total"] / (res["monte_carlo_sharded" if world > 1 else "monte_carlo_1gpu"]["ms_per_query"] / 1e3)
+    out.update(workload="R-MAT scale-%d edge factor %d (n=%d, m=%d), eps 0.5, %d non-dangling sources; sharded = one query at a time over %d GPU(s), ncclAllReduce inside the timed region"
+                        % (a.scale, a.edge_factor, n, n * a.edge_factor, a.queries, world), rmat_gen_s=gen_s, results=res)
+    if world > 1:
+        ctx.comm_destroy()
 else:
     n = 1 << a.scale
     rp, ci = pkg.rmat(n, n * a.edge_factor, seed=42)

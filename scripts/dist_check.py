@@ -61,6 +61,44 @@ for name, (rp, ci) in (("GOT", pkg.graphio.load_got()[:2]), ("rmat14", pkg.rmat(
         print("%s all-pair blocks over %d GPUs merge to the 1-GPU index: %s (%d pairs)" % (name, world, good, len(tgt)), flush=True)
     g.close()
 
+# ---- the library's own collectives (ppr_comm_init + ppr_*_sharded: ncclAllReduce / ncclAllGather / ncclBroadcast behind the C ABI)
+box = [pkg.Context.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(box, src=0)
+ctx.comm_init(box[0], rank, world)
+for name, (rp, ci) in (("GOT", pkg.graphio.load_got()[:2]), ("rmat14", pkg.rmat(1 << 14, 1 << 18, seed=42))):
+    g = pkg.Graph(ctx, rp, ci)
+    og = O.OGraph(rp, ci)
+    srcs = [int(x) for x in np.flatnonzero(np.diff(rp) > 0)[[5, 23]]]
+    good = True
+    for s in srcs:
+        out, st = g.fora_sharded(s, ALPHA, EPS, 7)
+        ref, _ = O.b_fora(og, s, ALPHA, EPS, 7)
+        good = good and bool(np.array_equal(g.last_raw(False)[0], ref)) and bool(np.array_equal(out, ref * O.FX_INV))
+        # balance per shard: walk_cost / world (more push, fewer walks per GPU); the oracle takes the same constant
+        out, st = g.fora_sharded(s, ALPHA, EPS, 7, flags=pkg._native.BALANCE_PER_SHARD)
+        ref, _ = O.b_fora(og, s, ALPHA, EPS, 7, walk_cost=6.0 / world)
+        good = good and bool(np.array_equal(g.last_raw(False)[0], ref))
+        out, st = g.monte_carlo_sharded(s, ALPHA, 1.0, 7)
+        refc, rst = O.b_monte_carlo(og, s, ALPHA, 1.0, 7)
+        good = good and bool(np.array_equal(g.last_raw(False)[0], refc)) and bool(np.array_equal(out, refc / rst["omega"]))
+        ids, vals, st = g.fora_topk_sharded(s, ALPHA, EPS, 10, 7)
+        ref, rst = O.b_fora_topk(og, s, ALPHA, EPS, 10, 7)
+        good = good and bool(np.array_equal(g.last_raw(False)[0], ref)) and set(ids.tolist()) == set(O.topk_select(ref, 10).tolist()) and st["rounds"] == rst["rounds"]
+    rptr, rtgt, rval, _ = O.b_base_all_pairs(og, ALPHA, 1e-3)
+    ptr, tgt, val, st = g.backward_all_pairs_sharded(ALPHA, 1e-3, -1, raw=True)
+    good = good and bool(np.array_equal(ptr, rptr) and np.array_equal(tgt, rtgt) and np.array_equal(val, rval))
+    kptr, ktgt, kval, _ = g.backward_all_pairs_sharded(ALPHA, 1e-3, 3, raw=True)      # top-3 rows: cut after the merge
+    for v in range(og.n):
+        rt, rv = rtgt[rptr[v]:rptr[v + 1]], rval[rptr[v]:rptr[v + 1]]
+        keep = O.topk_select(rv, 3) if len(rv) else np.zeros(0, np.int32)
+        good = good and bool(np.array_equal(ktgt[kptr[v]:kptr[v + 1]], rt[keep]) and np.array_equal(kval[kptr[v]:kptr[v + 1]], rv[keep]))
+    ok = ok and good
+    if rank == 0:
+        print("%s library collectives (FORA, FORA per-shard balance, MC, FORA top-k, all-pair gather, top-k rows) over %d GPUs bit-exact: %s" % (name, world, good), flush=True)
+    g.close()
+if rank == 0:
+    print("library communicator:", ctx.comm_info(), flush=True)
+
 # walk scaling at a size where walks dominate: Monte-Carlo on R-MAT scale 20 (eps 0.5: 1.8e8 walks)
 rp, ci = pkg.rmat(1 << 20, 1 << 24, seed=42)
 g = pkg.Graph(ctx, rp, ci)
@@ -81,6 +119,7 @@ if rank == 0:
           % (W, world, tt[0].item(), tt[1].item(), tt[2].item(), W / (tt[2].item() / 1e3)), flush=True)
     print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)
 g.close()
+ctx.comm_destroy()
 ctx.close()
 dist.barrier()
 dist.destroy_process_group()

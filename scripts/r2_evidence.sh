@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 single-GPU evidence: GPU tests, both bench arms, launch list and one full ncu capture (run under gpurun).
 set -x
-O=gpurun_out/r2
+O=gpurun_out/r2h
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem --format=csv > $O/gpu.txt
 timeout 1500 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "rc=$?" >> $O/pytest_gpu.log

@@ -122,7 +122,7 @@ def test_cpp_host_driver_on_got(pkg, tmp_path):
     exe = os.path.join(os.path.dirname(pkg.__file__), "PPR")
     got = os.path.join(os.path.dirname(__file__), "golden", "got")
     r = subprocess.run([exe, "-alpha", "0.15", "-eps", "0.5", "-query", "5", "-k", "10", "-db", got, "-out", str(tmp_path)],
-                       capture_output=True, text=True, timeout=300)
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path))      # the result stores of Test 3 are created under the cwd
     assert r.returncode == 0, r.stdout + r.stderr
     text = open(tmp_path / "got_AlgoPerfResults.txt").read()
     assert "Test 1. Whole-Graph test" in text and "1.1 FORA_WHOLE_GRAPH" in text and "2.1 FORA_TOPK" in text and "1.5 BASE_WHOLE_GRAPH" in text
@@ -135,6 +135,16 @@ def test_cpp_host_driver_on_got(pkg, tmp_path):
     assert min(prec[2:]) > 0.8
     sec = text.split("1.2 FWDPUSH\n")[1].split("\n\n")[0].splitlines()
     assert float(sec[-1].split(",")[2].replace("E", "e")) < 1e-6       # rmax 1e-8
+    # Test 3 (J/Gen_Util.java:602-645): every source preprocessed into "<ALGO>_ppr_results/<db>/<param>/<id>.txt", queries answered from
+    # the files, stores deleted afterwards (BASE keeps its index in memory).  Row: param, threshold, prep ms, store bytes, avg max error
+    assert "Test 3. Preprocessing test" in text and "3.1 FORA_WHOLE_GRAPH" in text and "3.5 BASE_WHOLE_GRAPH" in text
+    sec = text.split("3.2 FWDPUSH\n")[1].split("\n\n")[0].splitlines()
+    assert [l.split(",")[0] for l in sec] == ["1.0E-4", "1.0E-5", "1.0E-6", "1.0E-7", "1.0E-8"] and all(l.split(",")[1] == "-1.0" for l in sec)
+    assert all(int(l.split(",")[3]) > 107 * 4 for l in sec)            # bytes on disk: at least "s\t1.0\n" per source
+    assert float(sec[-1].split(",")[4].replace("E", "e")) < 1e-6       # values survive the Double.toString round trip
+    sec = text.split("3.1 FORA_WHOLE_GRAPH\n")[1].split("\n\n")[0].splitlines()
+    assert float(sec[2].split(",")[4].replace("E", "e")) < 0.05
+    assert not any(f.endswith(".txt") and f != "got_AlgoPerfResults.txt" for _, _, fs in os.walk(tmp_path) for f in fs)
 
 
 def test_error_metrics_on_the_device(pkg, ctx, G, O, got, rmat12):
