@@ -18,6 +18,8 @@
 // Pairs (v, t, reserve >= threshold) are appended to one device array in arrival order with key = v << B | t and then
 // put into (source, target) order by an LSD radix sort written here (k_rs_*); row pointers come from the sorted keys.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "push.cuh"
 
@@ -31,12 +33,14 @@ struct BwdCtaArgs {
     u32* touched;               // [slots][n] vertices whose residue left zero (duplicates possible; overflow -> dense clean)
     u64* st_pk; u64* st_y;      // [slots][n] staged (vertex record, y) of frontiers larger than one tile
     u32* ticket;                // next target offset
+    const i32* order;           // targets of this launch in processing order (heaviest first), n_order of them; NULL: t_lo + ticket
+    i32 n_order;
     i32 t_lo, t_hi;
     u64 alpha_q64, rmax_fx, thr_fx;
     int key_bits;               // B: key = v << B | t
     u64* out_key; u64* out_val; i64 out_cap;
     ull* counters;              // [0] pair cursor, [1] pushes, [2] edges, [3] iterations (summed over targets)
-                                // timing != 0: [4] ticket+seed ns, [5] phase A ns, [6] phase B ns, [7] output+clean ns, [8] targets (thread 0's clock)
+                                // timing != 0: [4] ticket+seed ns, [5] phase A ns, [6] phase B ns, [7] output+clean ns, [8] targets, [9] longest target ns (thread 0's clock)
     int timing;
 };
 
@@ -50,7 +54,7 @@ __device__ __forceinline__ void cta_append(u32* list, u32* sm_cursor, bool pred,
         base = __shfl_sync(0xffffffffu, base, leader);
         if (pred) {
             const u32 idx = base + __popc(mask & lanemask_lt());
-            if (idx < cap) list[idx] = value; else *sm_overflow = 1;
+            if (idx < cap) __stcg(&list[idx], value); else *sm_overflow = 1;
             if (mirror && idx < mirror_cap) mirror[idx] = value;
         }
     }
@@ -69,7 +73,7 @@ __device__ __forceinline__ void cta_append4(u32* list, u32* sm_cursor, const boo
         for (int k = 0; k < 4; k++) {
             if (pred[k]) {
                 const u32 idx = base + __popc(m[k] & lanemask_lt());
-                if (idx < cap) list[idx] = value[k]; else *sm_overflow = 1;
+                if (idx < cap) __stcg(&list[idx], value[k]); else *sm_overflow = 1;
                 if (mirror && idx < mirror_cap) mirror[idx] = value[k];
             }
             base += __popc(m[k]);
@@ -77,19 +81,41 @@ __device__ __forceinline__ void cta_append4(u32* list, u32* sm_cursor, const boo
     }
 }
 
-template <int BD>
+// Per-search cursors.  One copy per CTA in shared memory; a team (thread-block cluster) uses the copy of its rank-0 CTA through
+// distributed shared memory (cluster.map_shared_rank), so appends from all CTAs of the team land in one place.
+struct BwdCursors {
+    u32 ticket;
+    u32 ncount[2];      // frontier sizes by iteration parity
+    u32 npushed, ntouched, overflow;
+    u32 outoff, total;  // output compaction
+    ull outbase;
+};
+
+// TEAM == 1: one CTA per search.  TEAM > 1: a thread-block cluster of TEAM CTAs (TEAM SMs) per search -- for searches
+// that are too large for one SM (the hubs at large thresholds hold the launch's critical path: 35 ms for one target of
+// 70 ms at 1e-3; every search at small thresholds).  The CTAs of a team split phase A by frontier item and phase B by
+// EDGE range (every CTA scans the same tile of up to BD frontier vertices, then relaxes its share of the concatenated
+// in-edge list), share the cursors through DSMEM and separate phases with cluster.sync() (which also makes the other
+// CTAs' global writes visible).  Fewer searches in flight also keeps their residue rows L2-resident.
+template <int BD, int TEAM>
 __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaArgs A) {
-    constexpr int LOG_BD = BD == 1024 ? 10 : BD == 512 ? 9 : BD == 256 ? 8 : BD == 128 ? 7 : 6;
     __shared__ u64 m_excl[BD + 1];      // exclusive in-degree prefix of the tile's frontier vertices; ~0 beyond them (and as the sentinel)
     __shared__ u64 m_beg[BD];
     __shared__ u64 m_y[BD];
-    __shared__ u32 mf[2][BD];          // mirrors of the first BD entries of the two frontier lists
+    __shared__ u32 mf[2][TEAM == 1 ? BD : 1];   // TEAM == 1: mirrors of the first BD entries of the two frontier lists
     __shared__ u64 scratch[64];
-    __shared__ u32 s_ticket, s_next, s_npushed, s_ntouched, s_overflow, s_outoff;
-    __shared__ ull s_outbase;
+    __shared__ BwdCursors cur_local;
     const u32 tid = threadIdx.x;
     const i64 n = A.n;
-    const size_t slot = blockIdx.x;
+    u32 rank = 0;
+    BwdCursors* C = &cur_local;
+    if (TEAM > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        rank = cluster.block_rank();
+        C = cluster.map_shared_rank(&cur_local, 0);
+    }
+    auto team_sync = [&]() { if (TEAM > 1) cg::this_cluster().sync(); else __syncthreads(); };
+    const size_t slot = blockIdx.x / TEAM;
     u64* R = A.r + slot * (size_t)n;
     u64* RES = A.reserve + slot * (size_t)n;
     u32* F[2] = {A.front + slot * 2 * (size_t)n, A.front + (slot * 2 + 1) * (size_t)n};
@@ -98,38 +124,44 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
     u64* ST_PK = A.st_pk + slot * (size_t)n;
     u64* ST_Y = A.st_y + slot * (size_t)n;
     const u32 cap = (u32)n;
+    const u32 tstride = (u32)TEAM * BD, tfirst = rank * BD + tid;   // item distribution over the team's threads
 
     for (;;) {
-        __syncthreads();
+        team_sync();
         u64 tm0 = 0, tmA = 0, tmB = 0, tm1 = 0;
-        if (A.timing && tid == 0) tm0 = globaltimer_ns();
-        if (tid == 0) s_ticket = atomicAdd(A.ticket, 1u);
-        __syncthreads();
-        const i64 t = (i64)A.t_lo + (i64)s_ticket;
-        if (t >= (i64)A.t_hi) break;
+        const bool clock = A.timing && rank == 0 && tid == 0;
+        if (clock) tm0 = globaltimer_ns();
+        if (rank == 0 && tid == 0) C->ticket = atomicAdd(A.ticket, 1u);
+        team_sync();
+        const u32 ticket = C->ticket;
+        if (A.order ? (i64)ticket >= (i64)A.n_order : (i64)A.t_lo + (i64)ticket >= (i64)A.t_hi) break;
+        const i64 t = A.order ? (i64)__ldg(&A.order[ticket]) : (i64)A.t_lo + (i64)ticket;
         const u64 pk_t = __ldg(&A.in_vtx[t]);
         if (vtx_deg(pk_t) == 0) {   // J/Backward_Search.java:46-49: a target without in-edges answers {t: 1}
-            if (tid == 0 && FX_ONE >= A.thr_fx) {
+            if (rank == 0 && tid == 0 && FX_ONE >= A.thr_fx) {
                 const ull at = atomicAdd(&A.counters[0], 1ull);
                 if ((i64)at < A.out_cap) { A.out_key[at] = ((u64)t << A.key_bits) | (u64)t; A.out_val[at] = FX_ONE; }
             }
             continue;
         }
-        if (tid == 0) {
-            R[t] = FX_ONE; mf[0][0] = (u32)t; F[0][0] = (u32)t; TOUCHED[0] = (u32)t;
-            s_ntouched = 1; s_npushed = 0; s_overflow = 0;
+        if (rank == 0 && tid == 0) {
+            __stcg(reinterpret_cast<ull*>(&R[t]), (ull)FX_ONE);
+            if (TEAM == 1) mf[0][0] = (u32)t;
+            __stcg(&F[0][0], (u32)t); __stcg(&TOUCHED[0], (u32)t);
+            C->ncount[0] = 1; C->ncount[1] = 0; C->ntouched = 1; C->npushed = 0; C->overflow = 0; C->total = 0; C->outoff = 0;
         }
-        u32 cnt = 1;
         int par = 0;
-        u64 acc_pushes = 0, acc_edges = 0, acc_iters = 0;   // thread 0
-        __syncthreads();
-        if (A.timing && tid == 0) { tm1 = globaltimer_ns(); tm0 = tm1 - tm0; }
-        while (cnt) {
-            if (tid == 0) s_next = 0;
+        u64 acc_pushes = 0, acc_edges = 0, acc_iters = 0;   // rank 0, thread 0
+        team_sync();
+        if (clock) { tm1 = globaltimer_ns(); tm0 = tm1 - tm0; }
+        for (;;) {
+            const u32 cnt = C->ncount[par];
+            if (cnt == 0) break;
+            if (rank == 0 && tid == 0) C->ncount[par ^ 1] = 0;   // last read one iteration ago, behind two team barriers
             u32* next = F[par ^ 1];
-            u32* next_m = mf[par ^ 1];
+            u32* next_m = TEAM == 1 ? mf[par ^ 1] : nullptr;
             // ---- phase A (J/Backward_Search.java:58-68): capture and zero the residue, move the alpha part to the reserve
-            const bool single = cnt <= (u32)BD;
+            const bool single = TEAM == 1 && cnt <= (u32)BD;
             u64 pk = 0, y = 0;
             if (single) {
                 bool fresh = false;
@@ -145,35 +177,36 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                     y = x - a;
                     pk = __ldg(&A.in_vtx[v]);
                 }
-                cta_append(PUSHED, &s_npushed, fresh, v, nullptr, 0u, cap, &s_overflow);
+                cta_append(PUSHED, &C->npushed, fresh, v, nullptr, 0u, cap, &C->overflow);
             } else {
-                for (u32 base = 0; base < cnt; base += BD) {
-                    const u32 i = base + tid;
+                for (u32 base = 0; base < cnt; base += tstride) {
+                    const u32 i = base + tfirst;
                     bool fresh = false;
                     u32 v = 0;
                     if (i < cnt) {
-                        v = F[par][i];
+                        v = __ldcg(&F[par][i]);
                         const u64 x = __ldcg(&R[v]);
-                        R[v] = 0;
+                        __stcg(reinterpret_cast<ull*>(&R[v]), 0ull);
                         const u64 a = mulhi64(x, A.alpha_q64);
-                        const u64 old = RES[v];
-                        RES[v] = old + a;
+                        const u64 old = __ldcg(&RES[v]);
+                        __stcg(reinterpret_cast<ull*>(&RES[v]), (ull)(old + a));
                         fresh = old == 0;
-                        ST_PK[i] = __ldg(&A.in_vtx[v]);
-                        ST_Y[i] = x - a;
+                        __stcg(reinterpret_cast<ull*>(&ST_PK[i]), (ull)__ldg(&A.in_vtx[v]));
+                        __stcg(reinterpret_cast<ull*>(&ST_Y[i]), (ull)(x - a));
                     }
-                    cta_append(PUSHED, &s_npushed, fresh, v, nullptr, 0u, cap, &s_overflow);
+                    cta_append(PUSHED, &C->npushed, fresh, v, nullptr, 0u, cap, &C->overflow);
                 }
             }
-            __syncthreads();   // every capture precedes every add of this iteration
-            if (A.timing && tid == 0) { const u64 now = globaltimer_ns(); tmA += now - tm1; tm1 = now; }
-            // ---- phase B (J/Backward_Search.java:77-94): tiles of BD frontier vertices, threads sweep the concatenated in-edge lists
+            team_sync();   // every capture precedes every add of this iteration
+            if (clock) { const u64 now = globaltimer_ns(); tmA += now - tm1; tm1 = now; }
+            // ---- phase B (J/Backward_Search.java:77-94): tiles of BD frontier vertices; the team's CTAs take equal shares of a
+            // tile's concatenated in-edge list, four consecutive edges per thread
             u64 it_edges = 0;
             for (u32 base = 0; base < cnt; base += BD) {
                 if (!single) {
                     const u32 i = base + tid;
-                    pk = i < cnt ? ST_PK[i] : 0;
-                    y = i < cnt ? ST_Y[i] : 0;
+                    pk = i < cnt ? __ldcg(&ST_PK[i]) : 0;
+                    y = i < cnt ? __ldcg(&ST_Y[i]) : 0;
                 }
                 const u32 d = vtx_deg(pk);
                 u64 e_d, e_x, t_d, t_x;
@@ -184,13 +217,14 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                 m_y[tid] = y;
                 __syncthreads();
                 it_edges += t_d;
-                for (u64 eb = 0; eb < t_d; eb += 4 * BD) {
+                const u64 e_lo = TEAM == 1 ? 0 : t_d * rank / TEAM, e_hi = TEAM == 1 ? t_d : t_d * (rank + 1) / TEAM;
+                for (u64 eb = e_lo; eb < e_hi; eb += 4 * BD) {
                     // four consecutive edges per thread: one binary search for the first, the others advance linearly
                     u32 u[4];
                     u64 inc[4], old[4];
                     const u64 e0 = eb + 4ull * tid;
                     int o = 0;
-                    if (e0 < t_d) {
+                    if (e0 < e_hi) {
 #pragma unroll
                         for (int s = BD / 2; s > 0; s >>= 1) { const int p = o + s; if (m_excl[p] <= e0) o = p; }
                     }
@@ -198,7 +232,7 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                     for (int k = 0; k < 4; k++) {
                         const u64 e = e0 + k;
                         u[k] = 0xffffffffu; inc[k] = 0;
-                        if (e < t_d) {
+                        if (e < e_hi) {
                             while (m_excl[o + 1] <= e) o++;
                             u[k] = (u32)__ldg(&A.row_idx[m_beg[o] + e]);
                             inc[k] = m_y[o];
@@ -215,40 +249,41 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                         first[k] = live && old[k] == 0;
                         cross[k] = live && old[k] <= A.rmax_fx && old[k] + inc[k] > A.rmax_fx;   // strict r > rmax, exactly one add crosses
                     }
-                    cta_append4(TOUCHED, &s_ntouched, first, u, nullptr, 0u, cap, &s_overflow);
-                    cta_append4(next, &s_next, cross, u, next_m, (u32)BD, cap, &s_overflow);
+                    cta_append4(TOUCHED, &C->ntouched, first, u, nullptr, 0u, cap, &C->overflow);
+                    cta_append4(next, &C->ncount[par ^ 1], cross, u, next_m, (u32)BD, cap, &C->overflow);
                 }
                 __syncthreads();
             }
-            if (tid == 0) { acc_pushes += cnt; acc_edges += it_edges; acc_iters += 1; }
-            cnt = s_next;
+            if (rank == 0 && tid == 0) { acc_pushes += cnt; acc_edges += it_edges; acc_iters += 1; }
             par ^= 1;
-            __syncthreads();
-            if (A.timing && tid == 0) { const u64 now = globaltimer_ns(); tmB += now - tm1; tm1 = now; }
+            team_sync();
+            if (clock) { const u64 now = globaltimer_ns(); tmB += now - tm1; tm1 = now; }
         }
         // ---- output: pushed vertices with reserve >= threshold (J/Base_Whole_Graph.java:80-88); clean the slot
-        const u32 np = s_npushed;
+        const u32 np = C->npushed;
         u32 mine = 0;
-        for (u32 i = tid; i < np; i += BD) { const u64 x = RES[PUSHED[i]]; mine += (x != 0 && x >= A.thr_fx) ? 1u : 0u; }
-        const u64 total = block_sum_u64((u64)mine, scratch);
-        if (tid == 0) {
-            s_outbase = total ? atomicAdd(&A.counters[0], (ull)total) : 0ull;
-            s_outoff = 0;
+        for (u32 i = tfirst; i < np; i += tstride) { const u64 x = __ldcg(&RES[__ldcg(&PUSHED[i])]); mine += (x != 0 && x >= A.thr_fx) ? 1u : 0u; }
+        const u64 cta_total = block_sum_u64((u64)mine, scratch);
+        if (tid == 0 && cta_total) atomicAdd(&C->total, (u32)cta_total);
+        team_sync();
+        if (rank == 0 && tid == 0) {
+            const u32 total = C->total;
+            C->outbase = total ? atomicAdd(&A.counters[0], (ull)total) : 0ull;
             atomicAdd(&A.counters[1], (ull)acc_pushes); atomicAdd(&A.counters[2], (ull)acc_edges); atomicAdd(&A.counters[3], (ull)acc_iters);
         }
-        __syncthreads();
-        const ull obase = s_outbase;
-        const bool fits = (i64)(obase + total) <= A.out_cap;
-        for (u32 base = 0; base < np; base += BD) {
-            const u32 i = base + tid;
+        team_sync();
+        const ull obase = C->outbase;
+        const bool fits = (i64)(obase + C->total) <= A.out_cap;
+        for (u32 base = 0; base < np; base += tstride) {
+            const u32 i = base + tfirst;
             u32 v = 0; u64 x = 0;
-            if (i < np) { v = PUSHED[i]; x = RES[v]; RES[v] = 0; }
+            if (i < np) { v = __ldcg(&PUSHED[i]); x = __ldcg(&RES[v]); __stcg(reinterpret_cast<ull*>(&RES[v]), 0ull); }
             const bool has = x != 0 && x >= A.thr_fx;
             const u32 mask = __ballot_sync(0xffffffffu, has);
             if (mask) {
                 const u32 leader = __ffs(mask) - 1;
                 u32 off = 0;
-                if (lane_id() == leader) off = atomicAdd(&s_outoff, (u32)__popc(mask));
+                if (lane_id() == leader) off = atomicAdd(&C->outoff, (u32)__popc(mask));
                 off = __shfl_sync(0xffffffffu, off, leader);
                 if (has && fits) {
                     const ull at = obase + off + __popc(mask & lanemask_lt());
@@ -257,14 +292,15 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                 }
             }
         }
-        if (s_overflow) { for (i64 v = tid; v < n; v += BD) R[v] = 0; }
-        else { const u32 nt = s_ntouched; for (u32 i = tid; i < nt; i += BD) R[TOUCHED[i]] = 0; }
+        if (C->overflow) { for (i64 v = tfirst; v < n; v += tstride) __stcg(reinterpret_cast<ull*>(&R[v]), 0ull); }
+        else { const u32 nt = C->ntouched; for (u32 i = tfirst; i < nt; i += tstride) __stcg(reinterpret_cast<ull*>(&R[__ldcg(&TOUCHED[i])]), 0ull); }
         if (A.timing) {
-            __syncthreads();
-            if (tid == 0) {
+            team_sync();
+            if (clock) {
                 const u64 now = globaltimer_ns();
                 atomicAdd(&A.counters[4], (ull)tm0); atomicAdd(&A.counters[5], (ull)tmA); atomicAdd(&A.counters[6], (ull)tmB);
                 atomicAdd(&A.counters[7], (ull)(now - tm1)); atomicAdd(&A.counters[8], 1ull);
+                atomicMax(&A.counters[9], (ull)(tm0 + tmA + tmB + (now - tm1)));
             }
         }
     }

@@ -187,7 +187,7 @@ struct ppr_ctx {
     i32 hot_min_indeg;     // a vertex needs at least this in-degree to get a hub slot (graphs created afterwards)
     i32 midi_ctas;         // forward push, small regime: CTAs taking part (<= 1: off), vertex and edge limits
     i64 midi_v, midi_e;
-    i32 walk_hint;         // walk kernel variant: -1 automatic (L2 eviction hints once the graph exceeds the L2), 0 plain, 1 hints
+    i32 walk_hint;         // walk kernel variant: -1 automatic (beyond the L2: eviction hints + 32-bit row pointers), 0 plain, 1 hints, 2 hints + 32-bit row pointers
     double pull_enter, pull_exit;   // forward push: pull-direction passes from / until this share of all edges in the frontier (enter < 0: off)
     // measurement helpers (pprb200_debug.h): per context, created on first use, destroyed by ppr_shutdown
     cudaEvent_t timer_ev[4]; bool timer_init;
@@ -203,6 +203,7 @@ struct DevGraph {
     u64* out_vtx;   // [n] packed (begin<<24 | out-degree)
     i32* col_idx;   // [m]
     u32* out_deg;   // [n]
+    u32* row32;     // [n+1] 32-bit CSR row pointers (NULL when m >= 2^32): the walk kernel's vertex table beyond the L2
     u64* in_vtx;    // [n] packed over the CSC
     i32* row_idx;   // [m]
     u64* invdeg;    // [n] (2^64-1)/out_deg, 0 for dangling

@@ -45,6 +45,10 @@ int32_t ctx_fail_cuda(ppr_ctx* ctx, cudaError_t e, const char* expr, const char*
 }
 
 // ============================================================================================= graph build kernels
+__global__ void k_build_row32(const i64* __restrict__ ptr, u32* __restrict__ row32, i64 n) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    for (i64 v = gtid; v <= n; v += gsize) row32[v] = (u32)ptr[v];
+}
 __global__ void k_build_vtx(const i64* __restrict__ ptr, u64* __restrict__ vtx, u32* __restrict__ deg, u64* __restrict__ invdeg,
                             i64 n) {
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
@@ -121,6 +125,7 @@ extern "C" int32_t ppr_init(int32_t device, ppr_ctx** out) {
     ctx->bwd_batch = 0;
     ctx->batch_streams = 0;
     ctx->walk_hint = -1;
+    { const char* e = getenv("PPR_WALK_VARIANT"); if (e) ctx->walk_hint = atoi(e); }
     // pull-direction passes are OFF by default: inside the 16-warp-per-SM persistent kernel a pass is a chain of dependent
     // gathers and costs ~950 us at R-MAT scale 22 (profiles/r02_pull_direction.txt), more than the fattest push iteration
     ctx->pull_enter = -1.0; ctx->pull_exit = 0.0;
@@ -240,7 +245,7 @@ extern "C" int32_t ppr_set_pull(ppr_ctx* ctx, double enter_share, double exit_sh
 }
 
 extern "C" int32_t ppr_set_walk_variant(ppr_ctx* ctx, int32_t hint) {
-    if (!ctx || hint < -1 || hint > 1) return PPR_E_INVALID;
+    if (!ctx || hint < -1 || hint > 2) return PPR_E_INVALID;
     ctx->walk_hint = hint;
     return PPR_OK;
 }
@@ -404,6 +409,8 @@ struct GraphExtra {  // host-side bookkeeping kept beside ppr_graph
     double* metric_vec[2]; bool metric_set[2];
     double* pm_result; bool last_is_pm;
     i32* sort_ids; u64* sort_vals; i64 sort_cap;   // ordered top-k survivors (k_rank_sort)
+    std::vector<u32> h_indeg;                      // in-degrees (all-pair backward search: heaviest targets first)
+    i32* bwd_order; i64 bwd_order_cap;             // device copy of a call's target order
 };
 static std::vector<std::pair<ppr_graph*, GraphExtra*>> g_extras;
 static std::mutex g_extras_mu;   // graphs of different contexts may be created / queried / destroyed from different threads
@@ -428,9 +435,9 @@ extern "C" int32_t ppr_graph_destroy(ppr_graph* g) {
         for (auto& e : x->batch_ev) cudaEventDestroy(e);
         if (x->batch_ev_ready) for (int i = 0; i < 2; i++) { cudaEventDestroy(x->done_ev[i]); cudaEventDestroy(x->copied_ev[i]); }
         if (x->snaps) cudaFreeHost(x->snaps);
-        cudaFree(x->metric_vec[0]); cudaFree(x->metric_vec[1]); cudaFree(x->pm_result); cudaFree(x->sort_ids); cudaFree(x->sort_vals);
+        cudaFree(x->metric_vec[0]); cudaFree(x->metric_vec[1]); cudaFree(x->pm_result); cudaFree(x->sort_ids); cudaFree(x->sort_vals); cudaFree(x->bwd_order);
     }
-    cudaFree(g->d.out_vtx); cudaFree(g->d.col_idx); cudaFree(g->d.out_deg);
+    cudaFree(g->d.out_vtx); cudaFree(g->d.col_idx); cudaFree(g->d.out_deg); cudaFree(g->d.row32);
     cudaFree(g->d.in_vtx); cudaFree(g->d.row_idx); cudaFree(g->d.invdeg); cudaFree(g->d.push_idx); cudaFree(g->d.hot_id);
     cudaFree(g->d.pull_idx); cudaFree(g->d.pull_hot_id); cudaFree(g->d.long_v); cudaFree(g->d.long_chunk); cudaFree(g->d.pull_task);
     {
@@ -464,7 +471,7 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     g->ctx = ctx; g->last_ws = 0; g->last_kind = 0; g->trace_active = false;
     x->ws1_ready = false; x->bws_ready = false; x->walk_blocks = 0; x->last_divisor = 0.0; memset(&x->bws, 0, sizeof x->bws);
     x->bcw_ready = false; memset(&x->bcw, 0, sizeof x->bcw);
-    x->metric_vec[0] = x->metric_vec[1] = nullptr; x->metric_set[0] = x->metric_set[1] = false; x->pm_result = nullptr; x->last_is_pm = false; x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0;
+    x->metric_vec[0] = x->metric_vec[1] = nullptr; x->metric_set[0] = x->metric_set[1] = false; x->pm_result = nullptr; x->last_is_pm = false; x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0; x->bwd_order = nullptr; x->bwd_order_cap = 0;
     x->batch_ev_ready = false; x->snaps = nullptr; x->snaps_cap = 0; x->bwd_chunks_per_target = 1;
     { std::lock_guard<std::mutex> lk(g_extras_mu); g_extras.push_back(std::make_pair(g, x)); }
     g->d.n = n; g->d.m = m;
@@ -480,6 +487,11 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     G_TRY(cudaMemcpyAsync(d_ptr, row_ptr, ((size_t)n + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
     k_build_vtx<<<blocks, 256, 0, ctx->stream>>>(d_ptr, g->d.out_vtx, g->d.out_deg, g->d.invdeg, n);
     G_TRY(cudaGetLastError());
+    if (m < ((i64)1 << 32)) {
+        G_TRY(dalloc(&g->d.row32, (size_t)n + 1));
+        k_build_row32<<<blocks, 256, 0, ctx->stream>>>(d_ptr, g->d.row32, n);
+        G_TRY(cudaGetLastError());
+    }
     if (m > 0) G_TRY(cudaMemcpyAsync(g->d.col_idx, col_idx, (size_t)m * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
 
     // CSC on the device: histogram -> scan -> stable sort by target (temporaries freed at the end of this block)
@@ -534,6 +546,8 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
         i64 bch = 1;
         for (i64 v = 0; v < n; v++) { i64 d = (i64)h_indeg[(size_t)v]; if (d > PUSH_SMALL_MAX) bch += (d + PUSH_CHUNK - 1) / PUSH_CHUNK; }
         x->bwd_chunks_per_target = bch;
+        x->h_indeg.resize((size_t)n);
+        for (i64 v = 0; v < n; v++) x->h_indeg[(size_t)v] = (u32)std::min<ull>(h_indeg[(size_t)v], 0xffffffffull);
         size_t keep = std::min<size_t>(cand.size(), HOT_SLOTS);
         std::partial_sort(cand.begin(), cand.begin() + keep, cand.end());
         for (size_t k = 0; k < keep; k++) hot_id.push_back((u32)cand[k].second);
@@ -601,7 +615,7 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     rc = ws_alloc(ctx, g->ws[0], n, chunk_cap);
     if (rc != PPR_OK) { ppr_graph_destroy(g); return rc; }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<true, WALK_PER_LANE>, WALK_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<2, WALK_PER_LANE>, WALK_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
     x->walk_blocks = ctx->sm_count * occ;
     *out = g;
     return PPR_OK;
@@ -666,10 +680,13 @@ static cudaError_t launch_walk(ppr_ctx* ctx, ppr_graph* g, Workspace& w, u64* ta
     W.k0 = (u32)key; W.k1 = (u32)(key >> 32);
     W.tstop = h_stop_threshold(alpha);
     W.src = src; W.restart_at_source = restart_at_source; W.no_zero_hop = no_zero_hop;
-    const bool big = ctx->walk_hint >= 0 ? ctx->walk_hint == 1
-                                         : 4.0 * (double)g->d.m + 8.0 * (double)g->d.n > 96.0 * 1024 * 1024;   // graph beyond the L2: use eviction hints
-    if (big) k_walk<true, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
-    else k_walk<false, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
+    W.row32 = g->d.row32;
+    // graph beyond the L2: eviction hints, and the half-size 32-bit row pointers as the vertex table when they exist
+    int variant = ctx->walk_hint >= 0 ? ctx->walk_hint : (4.0 * (double)g->d.m + 8.0 * (double)g->d.n > 96.0 * 1024 * 1024 ? 2 : 0);
+    if (variant == 2 && !g->d.row32) variant = 1;
+    if (variant == 2) k_walk<2, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
+    else if (variant == 1) k_walk<1, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
+    else k_walk<0, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
     return cudaGetLastError();
 }
 
@@ -1039,7 +1056,7 @@ static int32_t fetch_survivors(ppr_graph* g, Workspace& w, std::vector<i32>& ids
     if (cnt) {
         GraphExtra* x = extra_of(g);
         if (x->sort_cap < cnt) {
-            cudaFree(x->sort_ids); cudaFree(x->sort_vals); x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0;
+            cudaFree(x->sort_ids); cudaFree(x->sort_vals); x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0; x->bwd_order = nullptr; x->bwd_order_cap = 0;
             const i64 cap = std::max<i64>(cnt, 4096);
             CUDA_TRY(dalloc(&x->sort_ids, (size_t)cap)); CUDA_TRY(dalloc(&x->sort_vals, (size_t)cap));
             x->sort_cap = cap;
@@ -1522,19 +1539,48 @@ static void apply_topk_rows(ppr_pairs* P, int32_t k);
 static int32_t pairs_to_host(ppr_ctx* ctx, ppr_pairs* P);
 
 // Launch configuration of k_bwd_cta: CTA size and CTAs per SM (PPR_BWD_BD / PPR_BWD_CPS / PPR_BWD_SLOTS override it for tuning runs).
-template <int BD>
+template <int BD, int TEAM>
 static cudaError_t launch_bwd_cta(const BwdCtaArgs& A, int slots, cudaStream_t st) {
-    k_bwd_cta<BD><<<slots, BD, 0, st>>>(A);
-    return cudaGetLastError();
-}
-static cudaError_t launch_bwd_cta_bd(int bd, const BwdCtaArgs& A, int slots, cudaStream_t st) {
-    switch (bd) {
-        case 64: return launch_bwd_cta<64>(A, slots, st);
-        case 128: return launch_bwd_cta<128>(A, slots, st);
-        case 256: return launch_bwd_cta<256>(A, slots, st);
-        case 512: return launch_bwd_cta<512>(A, slots, st);
-        default: return launch_bwd_cta<1024>(A, slots, st);
+    if (TEAM == 1) {
+        k_bwd_cta<BD, 1><<<slots, BD, 0, st>>>(A);
+        return cudaGetLastError();
     }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)slots * TEAM); cfg.blockDim = dim3(BD); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = TEAM; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_bwd_cta<BD, TEAM>, A);
+}
+static cudaError_t launch_bwd_cta_bd(int bd, int team, const BwdCtaArgs& A, int slots, cudaStream_t st) {
+    if (team == 8) return launch_bwd_cta<1024, 8>(A, slots, st);
+    if (team == 4) return launch_bwd_cta<1024, 4>(A, slots, st);
+    if (team == 2) return launch_bwd_cta<1024, 2>(A, slots, st);
+    switch (bd) {
+        case 64: return launch_bwd_cta<64, 1>(A, slots, st);
+        case 128: return launch_bwd_cta<128, 1>(A, slots, st);
+        case 256: return launch_bwd_cta<256, 1>(A, slots, st);
+        case 512: return launch_bwd_cta<512, 1>(A, slots, st);
+        default: return launch_bwd_cta<1024, 1>(A, slots, st);
+    }
+}
+// searches a team launch can keep in flight (clusters resident at once)
+static int bwd_team_slots(ppr_ctx* ctx, int team) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)ctx->sm_count / team * team); cfg.blockDim = dim3(1024);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = team; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = 0;
+    cudaError_t e = team == 8 ? cudaOccupancyMaxActiveClusters(&nc, k_bwd_cta<1024, 8>, &cfg)
+                  : team == 4 ? cudaOccupancyMaxActiveClusters(&nc, k_bwd_cta<1024, 4>, &cfg)
+                              : cudaOccupancyMaxActiveClusters(&nc, k_bwd_cta<1024, 2>, &cfg);
+    if (e != cudaSuccess || nc < 1) { cudaGetLastError(); nc = std::max(1, ctx->sm_count / team / 2); }
+    return nc;
 }
 static void bwd_cta_config(ppr_ctx* ctx, double edges_per_target, int* bd, int* cps) {
     // Measured on B200 (profiles/r02_bwd_cta_shapes.txt): one 1024-thread CTA per SM wins at every threshold of the reference
@@ -1549,11 +1595,11 @@ static void bwd_cta_config(ppr_ctx* ctx, double edges_per_target, int* bd, int* 
     int occ = 0;   // CTAs beyond what is resident would only queue (and cost 48 n bytes of slot state each)
     cudaError_t e2 = cudaSuccess;
     switch (*bd) {
-        case 64: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<64>, 64, 0); break;
-        case 128: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<128>, 128, 0); break;
-        case 256: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<256>, 256, 0); break;
-        case 512: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<512>, 512, 0); break;
-        default: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<1024>, 1024, 0); break;
+        case 64: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<64, 1>, 64, 0); break;
+        case 128: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<128, 1>, 128, 0); break;
+        case 256: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<256, 1>, 256, 0); break;
+        case 512: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<512, 1>, 512, 0); break;
+        default: e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_cta<1024, 1>, 1024, 0); break;
     }
     if (e2 == cudaSuccess && occ >= 1) *cps = std::min(*cps, occ);
 }
@@ -1637,30 +1683,75 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     double edges_per_target = -1.0;
     CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
     const bool timing = getenv("PPR_BWD_TIMING") != nullptr;
-    ull h_tim[5] = {0, 0, 0, 0, 0};
+    ull h_tim[6] = {0, 0, 0, 0, 0, 0};
+    // Processing order: a search costs roughly in proportion to what its target's in-neighbourhood reaches, and one CTA owns a
+    // search from start to end, so the heaviest targets (highest in-degree first) must start first or the launch ends with a few
+    // CTAs still working on hubs (longest-processing-time-first).  The first launch takes an evenly spaced sample of that order, so
+    // that its pairs-per-target estimate is representative.
+    const i64 R = t_hi - t_lo;
+    std::vector<i32> order;
+    i64 probe = 0;
+    if (R > 0 && !getenv("PPR_BWD_NO_ORDER")) {
+        try {
+            std::vector<i32> sorted((size_t)R);
+            for (i64 i = 0; i < R; i++) sorted[(size_t)i] = (i32)(t_lo + i);
+            const std::vector<u32>& deg = x->h_indeg;
+            std::stable_sort(sorted.begin(), sorted.end(), [&](i32 a, i32 b) { return deg[(size_t)a] > deg[(size_t)b]; });
+            probe = ctx->bwd_batch > 0 ? 0 : std::min<i64>(R, std::max<i64>(2048, (i64)ctx->sm_count * 16));
+            order.reserve((size_t)R);
+            if (probe > 0 && probe < R) {
+                const i64 stride = R / probe;
+                std::vector<char> taken((size_t)R, 0);
+                for (i64 i = 0; i < probe; i++) { order.push_back(sorted[(size_t)(i * stride)]); taken[(size_t)(i * stride)] = 1; }
+                for (i64 i = 0; i < R; i++) if (!taken[(size_t)i]) order.push_back(sorted[(size_t)i]);
+            } else order = sorted;
+        } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
+        if (x->bwd_order_cap < R) {
+            cudaFree(x->bwd_order); x->bwd_order = nullptr; x->bwd_order_cap = 0;
+            CUDA_TRY(dalloc(&x->bwd_order, (size_t)R));
+            x->bwd_order_cap = R;
+        }
+        CUDA_TRY(cudaMemcpyAsync(x->bwd_order, order.data(), (size_t)R * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // Launch plan.  (1) a probe launch, one CTA per search, over the evenly spaced sample: pairs and edges per target.
+    // (2) searches too large for one SM run as teams (thread-block clusters of `team` CTAs): every remaining target when the
+    // average search relaxes >= 64 K edges, otherwise the `heavy` targets of highest in-degree (they hold the critical path of the
+    // launch: one hub search takes 35 of 70 ms at threshold 1e-3 on one CTA).  (3) everything else, one CTA per search.
+    int team = 8;
+    i64 heavy = -1;     // < 0: decide after the probe
+    { const char* e; if ((e = getenv("PPR_BWD_TEAM"))) { int v = atoi(e); team = (v == 2 || v == 4 || v == 8) ? v : 1; }
+      if ((e = getenv("PPR_BWD_HEAVY"))) heavy = atoll(e); }
+    const bool force_team = getenv("PPR_BWD_FORCE_TEAM") != nullptr && team > 1;   // tests: every launch as teams
+    if (!force_team && (order.empty() || ctx->bwd_batch > 0)) team = 1;   // forced batches / unordered: plain launches only
     for (i64 t0 = t_lo; t0 < t_hi;) {
         int bd, cps;
         bwd_cta_config(ctx, edges_per_target, &bd, &cps);
         const i64 remaining = t_hi - t0;
         i64 Tb = remaining;
+        int lteam = force_team ? team : 1;
         if (ctx->bwd_batch > 0) Tb = std::min<i64>(Tb, ctx->bwd_batch);
         else if (launches == 0) Tb = std::min<i64>(Tb, std::max<i64>(2048, (i64)ctx->sm_count * 16));   // first launch: learn the pairs per target
-        i64 want_slots = (i64)ctx->sm_count * cps;
-        { const char* e = getenv("PPR_BWD_SLOTS"); if (e && atoll(e) > 0) want_slots = atoll(e); }
+        else if (team > 1 && t0 - t_lo == probe) {   // right after the probe: the team launch
+            const i64 nheavy = heavy >= 0 ? heavy : (edges_per_target >= 65536.0 ? remaining : std::min<i64>(remaining, (i64)8 * bwd_team_slots(ctx, team)));
+            if (nheavy > 0) { Tb = std::min<i64>(remaining, nheavy); lteam = team; }
+        }
+        i64 want_slots = lteam > 1 ? (i64)bwd_team_slots(ctx, lteam) : (i64)ctx->sm_count * cps;
+        { const char* e = getenv("PPR_BWD_SLOTS"); if (e && atoll(e) > 0 && lteam == 1) want_slots = atoll(e); }
         const int slots = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(want_slots, max_slots), Tb));
-        int32_t rc = bcw_ensure(g, slots, bd); if (rc) return rc;
+        int32_t rc = bcw_ensure(g, std::max(slots, x->bcw_ready ? x->bcw.slots : 0), bd); if (rc) return rc;
         BwdCtaWorkspace& b = x->bcw;
         // room for this launch's pairs: estimate from what has been seen, retry with the exact need on overflow
         i64 want = cursor + (launches ? (i64)((double)cursor / (double)(t0 - t_lo) * (double)Tb * 1.25) + 65536 : std::max<i64>((i64)1 << 22, Tb * 64));
         rc = bcw_reserve_pairs(ctx, b, want, cursor); if (rc) return rc;
         for (;;) {
-            ull h_cnt[16] = {(ull)cursor, (ull)pushes, (ull)edges, (ull)iters, h_tim[0], h_tim[1], h_tim[2], h_tim[3], h_tim[4], 0, 0, 0, 0, 0, 0, 0};
+            ull h_cnt[16] = {(ull)cursor, (ull)pushes, (ull)edges, (ull)iters, h_tim[0], h_tim[1], h_tim[2], h_tim[3], h_tim[4], h_tim[5], 0, 0, 0, 0, 0, 0};
             CUDA_TRY(cudaMemcpyAsync(b.counters, h_cnt, sizeof h_cnt, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(cudaMemsetAsync(b.ticket, 0, 4, ctx->stream));
             A.r = b.r; A.reserve = b.reserve; A.front = b.front; A.pushed = b.pushed; A.touched = b.touched; A.st_pk = b.st_pk; A.st_y = b.st_y;
             A.ticket = b.ticket; A.counters = b.counters; A.t_lo = (i32)t0; A.t_hi = (i32)(t0 + Tb);
+            A.order = order.empty() ? nullptr : x->bwd_order + (t0 - t_lo); A.n_order = (i32)Tb;   // launches walk through the order in slices of Tb
             A.out_key = b.key[0]; A.out_val = b.val[0]; A.out_cap = b.cap; A.timing = timing ? 1 : 0;
-            CUDA_TRY(launch_bwd_cta_bd(bd, A, slots, ctx->stream));
+            CUDA_TRY(launch_bwd_cta_bd(bd, lteam, A, slots, ctx->stream));
             CUDA_TRY(cudaMemcpyAsync(h_cnt, b.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             launches++;
@@ -1669,16 +1760,16 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
                 continue;
             }
             cursor = (i64)h_cnt[0]; pushes = (i64)h_cnt[1]; edges = (i64)h_cnt[2]; iters = (i64)h_cnt[3];
-            for (int i = 0; i < 5; i++) h_tim[i] = h_cnt[4 + i];
+            for (int i = 0; i < 6; i++) h_tim[i] = h_cnt[4 + i];
             break;
         }
-        tm.mark("reverse-push launch");
+        tm.mark(lteam > 1 ? "reverse-push launch (teams)" : "reverse-push launch");
         t0 += Tb;
         edges_per_target = (double)edges / (double)(t0 - t_lo);
     }
     if (timing && h_tim[4])
-        fprintf(stderr, "[pprb200] k_bwd_cta per target (thread 0 clock, us): ticket+seed %.2f  phase A %.2f  phase B %.2f  output+clean %.2f  (%llu targets with in-edges, %.2f iterations each)\n",
-                h_tim[0] / 1e3 / h_tim[4], h_tim[1] / 1e3 / h_tim[4], h_tim[2] / 1e3 / h_tim[4], h_tim[3] / 1e3 / h_tim[4], h_tim[4], (double)iters / (double)h_tim[4]);
+        fprintf(stderr, "[pprb200] k_bwd_cta per target (thread 0 clock, us): ticket+seed %.2f  phase A %.2f  phase B %.2f  output+clean %.2f  (%llu targets with in-edges, %.2f iterations each; longest target %.1f us)\n",
+                h_tim[0] / 1e3 / h_tim[4], h_tim[1] / 1e3 / h_tim[4], h_tim[2] / 1e3 / h_tim[4], h_tim[3] / 1e3 / h_tim[4], h_tim[4], (double)iters / (double)h_tim[4], h_tim[5] / 1e3);
     CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (cursor > 0xffffffffll) return ctx_fail(ctx, PPR_E_CAPACITY, "ppr_backward_all_pairs: more than 2^32 pairs in one call; split the target range");
     // inverted index grouped by source v, targets ascending (J/Base_Whole_Graph.java:83-87): device radix sort + row pointers.

@@ -19,6 +19,7 @@
 
 struct WalkArgs {
     const u64* out_vtx;
+    const u32* row32;    // [n+1] 32-bit row pointers (m < 2^32), half the footprint of out_vtx: used by the beyond-L2 variant (HINT == 2)
     const i32* col_idx;
     const u32* ws_v;
     const u64* ws_begin;
@@ -83,7 +84,10 @@ __device__ __forceinline__ u64 mul_div_u64(u64 a, u64 b, u64 c) {  // floor(a*b/
 // NW: walks in flight per lane.  A move is two dependent random loads (vertex record, neighbour), so a lane with one
 // walk spends most of its time waiting; with NW walks the loads of each stage are issued together (predicated, no
 // branches in between) and the latency is paid once per stage for all of them.
-template <bool HINT, int NW>
+// HINT == 2: as 1, and the vertex record is read as two adjacent 32-bit row pointers from a table half the size of out_vtx
+// (16 MB instead of 32 MB at R-MAT scale 22): the randomly accessed per-vertex data competes with the count / reserve vector and the
+// streamed edge array for the L2, and every record miss costs a 64-byte DRAM fetch.
+template <int HINT, int NW>
 __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_walk(WalkArgs A) {
     __shared__ u64 win[WALK_THREADS / 32][34];
     PushCtl* ctl = A.ctl;
@@ -182,20 +186,29 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_walk(WalkArg
             }
         }
         // stage 2: vertex records of all moving walks
-        u64 pk[NW];
+        u64 rb[NW];   // first edge of the row
+        u32 rd[NW];   // out-degree
 #pragma unroll
         for (int k = 0; k < NW; k++) {
-            pk[k] = 0;
-            if (go[k]) pk[k] = HINT ? ld_hint_u64(&A.out_vtx[w_cur[k]], pol_keep) : __ldg(&A.out_vtx[w_cur[k]]);
+            rb[k] = 0; rd[k] = 0;
+            if (go[k]) {
+                if (HINT == 2) {
+                    const u32 b = ld_hint_u32(&A.row32[w_cur[k]], pol_keep), e = ld_hint_u32(&A.row32[w_cur[k] + 1], pol_keep);
+                    rb[k] = b; rd[k] = e - b;
+                } else {
+                    const u64 pk = HINT ? ld_hint_u64(&A.out_vtx[w_cur[k]], pol_keep) : __ldg(&A.out_vtx[w_cur[k]]);
+                    rb[k] = vtx_begin(pk); rd[k] = vtx_deg(pk);
+                }
+            }
         }
         // stage 3: neighbours (a dangling vertex sends the walk to its restart vertex without a neighbour draw)
         u32 nb[NW];
 #pragma unroll
         for (int k = 0; k < NW; k++) {
-            const u32 d = vtx_deg(pk[k]);
+            const u32 d = rd[k];
             nb[k] = A.restart_at_source ? (u32)A.src : w_start[k];
             if (go[k] && d) {
-                const i32* p = &A.col_idx[vtx_begin(pk[k]) + mulhi64(rnd[k], (u64)d)];
+                const i32* p = &A.col_idx[rb[k] + mulhi64(rnd[k], (u64)d)];
                 nb[k] = HINT ? ld_hint_u32(p, pol_stream) : (u32)__ldg(p);
             }
         }

@@ -503,7 +503,7 @@ def test_all_pairs_launch_split(R16, O, ctx):
     ptr, tgt, val, st = g.backward_all_pairs(ALPHA, 1e-3, -1, 0, hi, raw=True)
     assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval)
     assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"])
-    assert st["launches"] <= 3, st["launches"]
+    assert st["launches"] <= 3, st["launches"]         # probe, the heaviest targets as cluster teams, the rest
     try:
         ctx.set_bwd_batch(700)      # 18 launches of at most 700 targets
         ptr, tgt, val, st = g.backward_all_pairs(ALPHA, 1e-3, -1, 0, hi, raw=True)
@@ -521,6 +521,29 @@ def test_all_pairs_multi_tile_frontiers(R12, O):
     ptr, tgt, val, st = g.backward_all_pairs(ALPHA, 1e-6, -1, 0, 300, raw=True)
     assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval)
     assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"])
+
+
+def test_all_pairs_cluster_teams(R12, R16, O, ctx, monkeypatch):
+    # searches too large for one SM run as thread-block clusters (teams of 2 / 4 / 8 CTAs splitting a tile's edges, cursors in
+    # distributed shared memory): forced for every launch here, on small frontiers (1e-3) and multi-tile ones (1e-6); then the
+    # automatic plan (probe, heaviest targets as teams, rest one CTA each) on R-MAT 2^16
+    g, og = R12
+    ref = {thr: O.b_base_all_pairs(og, ALPHA, thr, 0, 300) for thr in (1e-3, 1e-6)}
+    monkeypatch.setenv("PPR_BWD_FORCE_TEAM", "1")
+    for team in ("2", "4", "8"):
+        monkeypatch.setenv("PPR_BWD_TEAM", team)
+        for thr in (1e-3, 1e-6):
+            optr, otgt, oval, ost = ref[thr]
+            ptr, tgt, val, st = g.backward_all_pairs(ALPHA, thr, -1, 0, 300, raw=True)
+            assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval), (team, thr)
+            assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"])
+    monkeypatch.delenv("PPR_BWD_FORCE_TEAM")
+    monkeypatch.delenv("PPR_BWD_TEAM")
+    g, og = R16
+    optr, otgt, oval, ost = O.b_base_all_pairs(og, ALPHA, 1e-3, 0, 9000)
+    ptr, tgt, val, st = g.backward_all_pairs(ALPHA, 1e-3, -1, 0, 9000, raw=True)
+    assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval)
+    assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"]) and st["launches"] == 3   # probe, teams, rest
 
 
 def test_backward_search_dense_graph(pkg, ctx, O):
