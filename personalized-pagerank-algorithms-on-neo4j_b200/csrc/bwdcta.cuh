@@ -26,6 +26,7 @@
 struct BwdCtaArgs {
     i64 n;
     const u64* in_vtx; const i32* row_idx; const u64* invdeg;
+    const u64* edge_inv;        // [m] invdeg[row_idx[e]] per in-edge (nullable): the reciprocal degree arrives with the edge instead of a dependent gather
     // per-slot state (slot = blockIdx.x), all rows n entries long
     u64* r; u64* reserve;       // dense rows, zero outside a search
     u32* front;                 // [slots][2][n] frontier lists
@@ -42,6 +43,7 @@ struct BwdCtaArgs {
     ull* counters;              // [0] pair cursor, [1] pushes, [2] edges, [3] iterations (summed over targets)
                                 // timing != 0: [4] ticket+seed ns, [5] phase A ns, [6] phase B ns, [7] output+clean ns, [8] targets, [9] longest target ns (thread 0's clock)
     int timing;
+    int dbg;                    // bring-up aid: 1 = tickets only, 2 = seed only, 3 = search without output; 0 = normal
 };
 
 // append to a per-CTA list whose cursor lives in shared memory; the first `mirror_cap` entries are mirrored in shared memory
@@ -134,8 +136,12 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
         if (rank == 0 && tid == 0) C->ticket = atomicAdd(A.ticket, 1u);
         team_sync();
         const u32 ticket = C->ticket;
-        if (A.order ? (i64)ticket >= (i64)A.n_order : (i64)A.t_lo + (i64)ticket >= (i64)A.t_hi) break;
+        if (A.order ? (i64)ticket >= (i64)A.n_order : (i64)A.t_lo + (i64)ticket >= (i64)A.t_hi) {
+            team_sync();   // no CTA of a team may exit while another one still reads the cursors in its shared memory
+            break;
+        }
         const i64 t = A.order ? (i64)__ldg(&A.order[ticket]) : (i64)A.t_lo + (i64)ticket;
+        if (A.dbg == 1) continue;
         const u64 pk_t = __ldg(&A.in_vtx[t]);
         if (vtx_deg(pk_t) == 0) {   // J/Backward_Search.java:46-49: a target without in-edges answers {t: 1}
             if (rank == 0 && tid == 0 && FX_ONE >= A.thr_fx) {
@@ -153,6 +159,7 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
         int par = 0;
         u64 acc_pushes = 0, acc_edges = 0, acc_iters = 0;   // rank 0, thread 0
         team_sync();
+        if (A.dbg == 2) { if (rank == 0 && tid == 0) __stcg(reinterpret_cast<ull*>(&R[t]), 0ull); continue; }
         if (clock) { tm1 = globaltimer_ns(); tm0 = tm1 - tm0; }
         for (;;) {
             const u32 cnt = C->ncount[par];
@@ -236,10 +243,13 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                             while (m_excl[o + 1] <= e) o++;
                             u[k] = (u32)__ldg(&A.row_idx[m_beg[o] + e]);
                             inc[k] = m_y[o];
+                            if (A.edge_inv) inc[k] = mulhi64(inc[k], __ldg(&A.edge_inv[m_beg[o] + e]));   // (1-alpha) r(v) / d_out(u)
                         }
                     }
+                    if (!A.edge_inv) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) if (u[k] != 0xffffffffu) inc[k] = mulhi64(inc[k], __ldg(&A.invdeg[u[k]]));   // (1-alpha) r(v) / d_out(u)
+                        for (int k = 0; k < 4; k++) if (u[k] != 0xffffffffu) inc[k] = mulhi64(inc[k], __ldg(&A.invdeg[u[k]]));
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; k++) old[k] = (u[k] != 0xffffffffu && inc[k]) ? atomicAdd((ull*)&R[u[k]], (ull)inc[k]) : 1ull;
                     bool first[4], cross[4];
@@ -260,6 +270,12 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
             if (clock) { const u64 now = globaltimer_ns(); tmB += now - tm1; tm1 = now; }
         }
         // ---- output: pushed vertices with reserve >= threshold (J/Base_Whole_Graph.java:80-88); clean the slot
+        if (A.dbg == 3) {
+            const u32 np3 = C->npushed, nt3 = C->ntouched;
+            for (u32 i = tfirst; i < np3; i += tstride) __stcg(reinterpret_cast<ull*>(&RES[__ldcg(&PUSHED[i])]), 0ull);
+            for (u32 i = tfirst; i < nt3 && i < cap; i += tstride) __stcg(reinterpret_cast<ull*>(&R[__ldcg(&TOUCHED[i])]), 0ull);
+            continue;
+        }
         const u32 np = C->npushed;
         u32 mine = 0;
         for (u32 i = tfirst; i < np; i += tstride) { const u64 x = __ldcg(&RES[__ldcg(&PUSHED[i])]); mine += (x != 0 && x >= A.thr_fx) ? 1u : 0u; }

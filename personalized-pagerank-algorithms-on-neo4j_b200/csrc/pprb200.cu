@@ -45,6 +45,11 @@ int32_t ctx_fail_cuda(ppr_ctx* ctx, cudaError_t e, const char* expr, const char*
 }
 
 // ============================================================================================= graph build kernels
+// all-pair backward search: reciprocal out-degree of the SOURCE of every in-edge, laid out like row_idx (built on first use)
+__global__ void k_build_edge_inv(const i32* __restrict__ row_idx, const u64* __restrict__ invdeg, i64 m, u64* __restrict__ edge_inv) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
+    for (i64 e = gtid; e < m; e += gsize) edge_inv[e] = invdeg[row_idx[e]];
+}
 __global__ void k_build_row32(const i64* __restrict__ ptr, u32* __restrict__ row32, i64 n) {
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (i64)gridDim.x * blockDim.x;
     for (i64 v = gtid; v <= n; v += gsize) row32[v] = (u32)ptr[v];
@@ -411,6 +416,7 @@ struct GraphExtra {  // host-side bookkeeping kept beside ppr_graph
     i32* sort_ids; u64* sort_vals; i64 sort_cap;   // ordered top-k survivors (k_rank_sort)
     std::vector<u32> h_indeg;                      // in-degrees (all-pair backward search: heaviest targets first)
     i32* bwd_order; i64 bwd_order_cap;             // device copy of a call's target order
+    u64* edge_inv;                                 // [m] per in-edge reciprocal degree (lazily built by the all-pair search)
 };
 static std::vector<std::pair<ppr_graph*, GraphExtra*>> g_extras;
 static std::mutex g_extras_mu;   // graphs of different contexts may be created / queried / destroyed from different threads
@@ -435,7 +441,7 @@ extern "C" int32_t ppr_graph_destroy(ppr_graph* g) {
         for (auto& e : x->batch_ev) cudaEventDestroy(e);
         if (x->batch_ev_ready) for (int i = 0; i < 2; i++) { cudaEventDestroy(x->done_ev[i]); cudaEventDestroy(x->copied_ev[i]); }
         if (x->snaps) cudaFreeHost(x->snaps);
-        cudaFree(x->metric_vec[0]); cudaFree(x->metric_vec[1]); cudaFree(x->pm_result); cudaFree(x->sort_ids); cudaFree(x->sort_vals); cudaFree(x->bwd_order);
+        cudaFree(x->metric_vec[0]); cudaFree(x->metric_vec[1]); cudaFree(x->pm_result); cudaFree(x->sort_ids); cudaFree(x->sort_vals); cudaFree(x->bwd_order); cudaFree(x->edge_inv);
     }
     cudaFree(g->d.out_vtx); cudaFree(g->d.col_idx); cudaFree(g->d.out_deg); cudaFree(g->d.row32);
     cudaFree(g->d.in_vtx); cudaFree(g->d.row_idx); cudaFree(g->d.invdeg); cudaFree(g->d.push_idx); cudaFree(g->d.hot_id);
@@ -471,7 +477,7 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     g->ctx = ctx; g->last_ws = 0; g->last_kind = 0; g->trace_active = false;
     x->ws1_ready = false; x->bws_ready = false; x->walk_blocks = 0; x->last_divisor = 0.0; memset(&x->bws, 0, sizeof x->bws);
     x->bcw_ready = false; memset(&x->bcw, 0, sizeof x->bcw);
-    x->metric_vec[0] = x->metric_vec[1] = nullptr; x->metric_set[0] = x->metric_set[1] = false; x->pm_result = nullptr; x->last_is_pm = false; x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0; x->bwd_order = nullptr; x->bwd_order_cap = 0;
+    x->metric_vec[0] = x->metric_vec[1] = nullptr; x->metric_set[0] = x->metric_set[1] = false; x->pm_result = nullptr; x->last_is_pm = false; x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0; x->bwd_order = nullptr; x->bwd_order_cap = 0; x->edge_inv = nullptr;
     x->batch_ev_ready = false; x->snaps = nullptr; x->snaps_cap = 0; x->bwd_chunks_per_target = 1;
     { std::lock_guard<std::mutex> lk(g_extras_mu); g_extras.push_back(std::make_pair(g, x)); }
     g->d.n = n; g->d.m = m;
@@ -1056,7 +1062,7 @@ static int32_t fetch_survivors(ppr_graph* g, Workspace& w, std::vector<i32>& ids
     if (cnt) {
         GraphExtra* x = extra_of(g);
         if (x->sort_cap < cnt) {
-            cudaFree(x->sort_ids); cudaFree(x->sort_vals); x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0; x->bwd_order = nullptr; x->bwd_order_cap = 0;
+            cudaFree(x->sort_ids); cudaFree(x->sort_vals); x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0; x->bwd_order = nullptr; x->bwd_order_cap = 0; x->edge_inv = nullptr;
             const i64 cap = std::max<i64>(cnt, 4096);
             CUDA_TRY(dalloc(&x->sort_ids, (size_t)cap)); CUDA_TRY(dalloc(&x->sort_vals, (size_t)cap));
             x->sort_cap = cap;
@@ -1662,6 +1668,13 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     BwdCtaArgs A;
     memset(&A, 0, sizeof A);
     A.n = n; A.in_vtx = g->d.in_vtx; A.row_idx = g->d.row_idx; A.invdeg = g->d.invdeg;
+    if (!x->edge_inv && g->d.m > 0 && !getenv("PPR_BWD_NO_EDGE_INV")) {   // 8 bytes per edge, built once per graph: removes a dependent gather from every relaxed edge
+        if (cudaMalloc((void**)&x->edge_inv, (size_t)g->d.m * 8) == cudaSuccess) {
+            k_build_edge_inv<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d.row_idx, g->d.invdeg, g->d.m, x->edge_inv);
+            CUDA_TRY(cudaGetLastError());
+        } else { cudaGetLastError(); x->edge_inv = nullptr; }   // no room: keep the gather
+    }
+    A.edge_inv = getenv("PPR_BWD_NO_EDGE_INV") ? nullptr : x->edge_inv;
     A.alpha_q64 = h_alpha_q64(alpha);
     // J/Backward_Search.java:89 (r > rmax) and J/Base_Whole_Graph.java:83 (pi >= threshold), in fixed point
     {
@@ -1684,28 +1697,62 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
     const bool timing = getenv("PPR_BWD_TIMING") != nullptr;
     ull h_tim[6] = {0, 0, 0, 0, 0, 0};
-    // Processing order: a search costs roughly in proportion to what its target's in-neighbourhood reaches, and one CTA owns a
-    // search from start to end, so the heaviest targets (highest in-degree first) must start first or the launch ends with a few
-    // CTAs still working on hubs (longest-processing-time-first).  The first launch takes an evenly spaced sample of that order, so
-    // that its pairs-per-target estimate is representative.
+    // Launch plan.  One CTA owns a search from start to end, and search sizes are heavy-tailed (at threshold 1e-3 the mean search
+    // relaxes 12 K edges, the largest ~10 M: 35 ms on one CTA, half of the whole run), so:
+    //   (A) the `heavy` targets of highest in-degree run first, as teams: thread-block clusters of 8 CTAs per search;
+    //   (B) a probe launch, one CTA per search, over an evenly spaced sample of the remaining targets (in descending in-degree order):
+    //       pairs and relaxed edges per target;
+    //   (C) the rest, heaviest first (longest-processing-time-first); as teams of 2 CTAs when the probe's searches relax >= 64 K edges
+    //       on average (fewer searches in flight keep their residue rows in the L2: 836 against 1 090 ms at threshold 5e-5).
     const i64 R = t_hi - t_lo;
+    int team_heavy = 8, team_rest = 2;
+    i64 heavy = -1;
+    { const char* e;
+      if ((e = getenv("PPR_BWD_TEAM"))) { int v = atoi(e); team_heavy = (v == 2 || v == 4 || v == 8) ? v : 1; }
+      if ((e = getenv("PPR_BWD_TEAM_REST"))) { int v = atoi(e); team_rest = (v == 2 || v == 4 || v == 8) ? v : 1; }
+      if ((e = getenv("PPR_BWD_HEAVY"))) heavy = atoll(e); }
+    const bool force_team = getenv("PPR_BWD_FORCE_TEAM") != nullptr && team_heavy > 1;   // tests: every launch as teams of team_heavy
+    const bool ordered = R > 0 && !getenv("PPR_BWD_NO_ORDER");
+    struct Launch { i64 count; int team; bool probe; };
+    std::vector<Launch> plan;
     std::vector<i32> order;
-    i64 probe = 0;
-    if (R > 0 && !getenv("PPR_BWD_NO_ORDER")) {
-        try {
+    try {
+        if (ordered) {
             std::vector<i32> sorted((size_t)R);
             for (i64 i = 0; i < R; i++) sorted[(size_t)i] = (i32)(t_lo + i);
             const std::vector<u32>& deg = x->h_indeg;
-            std::stable_sort(sorted.begin(), sorted.end(), [&](i32 a, i32 b) { return deg[(size_t)a] > deg[(size_t)b]; });
-            probe = ctx->bwd_batch > 0 ? 0 : std::min<i64>(R, std::max<i64>(2048, (i64)ctx->sm_count * 16));
+            std::stable_sort(sorted.begin(), sorted.end(), [&](i32 a, i32 c) { return deg[(size_t)a] > deg[(size_t)c]; });
+            i64 H = 0, probe = 0;
+            if (ctx->bwd_batch <= 0 && !force_team) {
+                if (team_heavy > 1) H = std::min<i64>(R, heavy >= 0 ? heavy : (i64)8 * bwd_team_slots(ctx, team_heavy));
+                probe = std::min<i64>(R - H, std::max<i64>(2048, (i64)ctx->sm_count * 16));
+            }
             order.reserve((size_t)R);
-            if (probe > 0 && probe < R) {
-                const i64 stride = R / probe;
-                std::vector<char> taken((size_t)R, 0);
-                for (i64 i = 0; i < probe; i++) { order.push_back(sorted[(size_t)(i * stride)]); taken[(size_t)(i * stride)] = 1; }
-                for (i64 i = 0; i < R; i++) if (!taken[(size_t)i]) order.push_back(sorted[(size_t)i]);
-            } else order = sorted;
-        } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
+            for (i64 i = 0; i < H; i++) order.push_back(sorted[(size_t)i]);
+            const i64 rest = R - H;
+            if (probe > 0 && probe < rest) {
+                const i64 stride = rest / probe;
+                std::vector<char> taken((size_t)rest, 0);
+                for (i64 i = 0; i < probe; i++) { order.push_back(sorted[(size_t)(H + i * stride + stride / 2)]); taken[(size_t)(i * stride + stride / 2)] = 1; }
+                for (i64 i = 0; i < rest; i++) if (!taken[(size_t)i]) order.push_back(sorted[(size_t)(H + i)]);
+            } else {
+                for (i64 i = 0; i < rest; i++) order.push_back(sorted[(size_t)(H + i)]);
+                probe = rest;   // small ranges: the probe launch is the whole rest
+            }
+            if (ctx->bwd_batch > 0 || force_team) {
+                const i64 step = ctx->bwd_batch > 0 ? ctx->bwd_batch : R;
+                for (i64 i = 0; i < R; i += step) plan.push_back({std::min<i64>(step, R - i), force_team ? team_heavy : 1, false});
+            } else {
+                if (H > 0) plan.push_back({H, team_heavy, false});
+                if (probe > 0) plan.push_back({probe, 1, true});
+                if (rest - probe > 0) plan.push_back({rest - probe, 0 /* decided after the probe */, false});
+            }
+        } else if (R > 0) {
+            const i64 step = ctx->bwd_batch > 0 ? ctx->bwd_batch : R;
+            for (i64 i = 0; i < R; i += step) plan.push_back({std::min<i64>(step, R - i), 1, false});
+        }
+    } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_backward_all_pairs: host allocation failed"); }
+    if (!order.empty()) {
         if (x->bwd_order_cap < R) {
             cudaFree(x->bwd_order); x->bwd_order = nullptr; x->bwd_order_cap = 0;
             CUDA_TRY(dalloc(&x->bwd_order, (size_t)R));
@@ -1713,49 +1760,37 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
         }
         CUDA_TRY(cudaMemcpyAsync(x->bwd_order, order.data(), (size_t)R * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
     }
-    // Launch plan.  (1) a probe launch, one CTA per search, over the evenly spaced sample: pairs and edges per target.
-    // (2) searches too large for one SM run as teams (thread-block clusters of `team` CTAs): every remaining target when the
-    // average search relaxes >= 64 K edges, otherwise the `heavy` targets of highest in-degree (they hold the critical path of the
-    // launch: one hub search takes 35 of 70 ms at threshold 1e-3 on one CTA).  (3) everything else, one CTA per search.
-    int team = 8;
-    i64 heavy = -1;     // < 0: decide after the probe
-    { const char* e; if ((e = getenv("PPR_BWD_TEAM"))) { int v = atoi(e); team = (v == 2 || v == 4 || v == 8) ? v : 1; }
-      if ((e = getenv("PPR_BWD_HEAVY"))) heavy = atoll(e); }
-    const bool force_team = getenv("PPR_BWD_FORCE_TEAM") != nullptr && team > 1;   // tests: every launch as teams
-    if (!force_team && (order.empty() || ctx->bwd_batch > 0)) team = 1;   // forced batches / unordered: plain launches only
-    for (i64 t0 = t_lo; t0 < t_hi;) {
+    double pairs_per_target = 64.0;   // refined by the probe
+    i64 t0 = t_lo;
+    for (size_t li = 0; li < plan.size(); li++) {
         int bd, cps;
         bwd_cta_config(ctx, edges_per_target, &bd, &cps);
-        const i64 remaining = t_hi - t0;
-        i64 Tb = remaining;
-        int lteam = force_team ? team : 1;
-        if (ctx->bwd_batch > 0) Tb = std::min<i64>(Tb, ctx->bwd_batch);
-        else if (launches == 0) Tb = std::min<i64>(Tb, std::max<i64>(2048, (i64)ctx->sm_count * 16));   // first launch: learn the pairs per target
-        else if (team > 1 && t0 - t_lo == probe) {   // right after the probe: the team launch
-            const i64 nheavy = heavy >= 0 ? heavy : (edges_per_target >= 65536.0 ? remaining : std::min<i64>(remaining, (i64)8 * bwd_team_slots(ctx, team)));
-            if (nheavy > 0) { Tb = std::min<i64>(remaining, nheavy); lteam = team; }
-        }
+        const i64 Tb = plan[li].count;
+        int lteam = plan[li].team;
+        if (lteam == 0) lteam = edges_per_target >= 65536.0 ? team_rest : 1;
         i64 want_slots = lteam > 1 ? (i64)bwd_team_slots(ctx, lteam) : (i64)ctx->sm_count * cps;
         { const char* e = getenv("PPR_BWD_SLOTS"); if (e && atoll(e) > 0 && lteam == 1) want_slots = atoll(e); }
         const int slots = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(want_slots, max_slots), Tb));
         int32_t rc = bcw_ensure(g, std::max(slots, x->bcw_ready ? x->bcw.slots : 0), bd); if (rc) return rc;
         BwdCtaWorkspace& b = x->bcw;
-        // room for this launch's pairs: estimate from what has been seen, retry with the exact need on overflow
-        i64 want = cursor + (launches ? (i64)((double)cursor / (double)(t0 - t_lo) * (double)Tb * 1.25) + 65536 : std::max<i64>((i64)1 << 22, Tb * 64));
+        // room for this launch's pairs: estimate, retry with the exact need on overflow (the searches are deterministic)
+        const i64 want = cursor + std::max<i64>((i64)1 << 22, (i64)(pairs_per_target * (double)Tb * 1.25) + 65536);
         rc = bcw_reserve_pairs(ctx, b, want, cursor); if (rc) return rc;
+        const i64 edges_before = edges, cursor_before = cursor;
         for (;;) {
             ull h_cnt[16] = {(ull)cursor, (ull)pushes, (ull)edges, (ull)iters, h_tim[0], h_tim[1], h_tim[2], h_tim[3], h_tim[4], h_tim[5], 0, 0, 0, 0, 0, 0};
             CUDA_TRY(cudaMemcpyAsync(b.counters, h_cnt, sizeof h_cnt, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(cudaMemsetAsync(b.ticket, 0, 4, ctx->stream));
             A.r = b.r; A.reserve = b.reserve; A.front = b.front; A.pushed = b.pushed; A.touched = b.touched; A.st_pk = b.st_pk; A.st_y = b.st_y;
             A.ticket = b.ticket; A.counters = b.counters; A.t_lo = (i32)t0; A.t_hi = (i32)(t0 + Tb);
-            A.order = order.empty() ? nullptr : x->bwd_order + (t0 - t_lo); A.n_order = (i32)Tb;   // launches walk through the order in slices of Tb
+            A.order = order.empty() ? nullptr : x->bwd_order + (t0 - t_lo); A.n_order = (i32)Tb;   // launches walk through the order in slices
             A.out_key = b.key[0]; A.out_val = b.val[0]; A.out_cap = b.cap; A.timing = timing ? 1 : 0;
+            { const char* e = getenv("PPR_BWD_DBG"); A.dbg = e ? atoi(e) : 0; }
             CUDA_TRY(launch_bwd_cta_bd(bd, lteam, A, slots, ctx->stream));
             CUDA_TRY(cudaMemcpyAsync(h_cnt, b.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             launches++;
-            if ((i64)h_cnt[0] > b.cap) {   // pair buffer too small: the searches are deterministic, run the launch again with room
+            if ((i64)h_cnt[0] > b.cap) {   // pair buffer too small: run the launch again with room
                 rc = bcw_reserve_pairs(ctx, b, (i64)h_cnt[0] + 65536, cursor); if (rc) return rc;
                 continue;
             }
@@ -1765,7 +1800,10 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
         }
         tm.mark(lteam > 1 ? "reverse-push launch (teams)" : "reverse-push launch");
         t0 += Tb;
-        edges_per_target = (double)edges / (double)(t0 - t_lo);
+        if (plan[li].probe || edges_per_target < 0) {
+            edges_per_target = (double)(edges - edges_before) / (double)Tb;
+            pairs_per_target = std::max(1.0, (double)(cursor - cursor_before) / (double)Tb);
+        }
     }
     if (timing && h_tim[4])
         fprintf(stderr, "[pprb200] k_bwd_cta per target (thread 0 clock, us): ticket+seed %.2f  phase A %.2f  phase B %.2f  output+clean %.2f  (%llu targets with in-edges, %.2f iterations each; longest target %.1f us)\n",
