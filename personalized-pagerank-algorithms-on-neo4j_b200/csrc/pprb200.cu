@@ -1727,24 +1727,24 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
                 if (team_heavy > 1) H = std::min<i64>(R, heavy >= 0 ? heavy : (i64)8 * bwd_team_slots(ctx, team_heavy));
                 probe = std::min<i64>(R - H, std::max<i64>(2048, (i64)ctx->sm_count * 16));
             }
+            // layout of the order: [probe sample of the non-heavy targets][the H heaviest][the other targets, heaviest first]
             order.reserve((size_t)R);
-            for (i64 i = 0; i < H; i++) order.push_back(sorted[(size_t)i]);
             const i64 rest = R - H;
+            std::vector<char> taken((size_t)std::max<i64>(rest, 1), 0);
             if (probe > 0 && probe < rest) {
                 const i64 stride = rest / probe;
-                std::vector<char> taken((size_t)rest, 0);
                 for (i64 i = 0; i < probe; i++) { order.push_back(sorted[(size_t)(H + i * stride + stride / 2)]); taken[(size_t)(i * stride + stride / 2)] = 1; }
-                for (i64 i = 0; i < rest; i++) if (!taken[(size_t)i]) order.push_back(sorted[(size_t)(H + i)]);
-            } else {
-                for (i64 i = 0; i < rest; i++) order.push_back(sorted[(size_t)(H + i)]);
-                probe = rest;   // small ranges: the probe launch is the whole rest
+            } else if (ctx->bwd_batch <= 0 && !force_team) {
+                probe = 0;   // small ranges: no probe launch, the heavy block and the rest are everything
             }
+            for (i64 i = 0; i < H; i++) order.push_back(sorted[(size_t)i]);
+            for (i64 i = 0; i < rest; i++) if (!taken[(size_t)i]) order.push_back(sorted[(size_t)(H + i)]);
             if (ctx->bwd_batch > 0 || force_team) {
                 const i64 step = ctx->bwd_batch > 0 ? ctx->bwd_batch : R;
                 for (i64 i = 0; i < R; i += step) plan.push_back({std::min<i64>(step, R - i), force_team ? team_heavy : 1, false});
             } else {
-                if (H > 0) plan.push_back({H, team_heavy, false});
                 if (probe > 0) plan.push_back({probe, 1, true});
+                if (H > 0) plan.push_back({H, -1 /* heavy block: team_heavy, or merged into the rest when every search is large */, false});
                 if (rest - probe > 0) plan.push_back({rest - probe, 0 /* decided after the probe */, false});
             }
         } else if (R > 0) {
@@ -1765,9 +1765,13 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     for (size_t li = 0; li < plan.size(); li++) {
         int bd, cps;
         bwd_cta_config(ctx, edges_per_target, &bd, &cps);
-        const i64 Tb = plan[li].count;
+        i64 Tb = plan[li].count;
         int lteam = plan[li].team;
-        if (lteam == 0) lteam = edges_per_target >= 65536.0 ? team_rest : 1;
+        const bool all_large = edges_per_target >= 65536.0;   // (from the probe; -1 before any launch)
+        if (lteam == -1) {   // the heavy block
+            if (all_large && li + 1 < plan.size() && plan[li + 1].team == 0) { Tb += plan[li + 1].count; lteam = team_rest; li++; }   // one launch with the rest, heaviest first
+            else lteam = team_heavy;
+        } else if (lteam == 0) lteam = all_large ? team_rest : 1;
         i64 want_slots = lteam > 1 ? (i64)bwd_team_slots(ctx, lteam) : (i64)ctx->sm_count * cps;
         { const char* e = getenv("PPR_BWD_SLOTS"); if (e && atoll(e) > 0 && lteam == 1) want_slots = atoll(e); }
         const int slots = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(want_slots, max_slots), Tb));
@@ -1800,7 +1804,7 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
         }
         tm.mark(lteam > 1 ? "reverse-push launch (teams)" : "reverse-push launch");
         t0 += Tb;
-        if (plan[li].probe || edges_per_target < 0) {
+        if (plan[li].probe || (edges_per_target < 0 && lteam == 1)) {
             edges_per_target = (double)(edges - edges_before) / (double)Tb;
             pairs_per_target = std::max(1.0, (double)(cursor - cursor_before) / (double)Tb);
         }
