@@ -299,8 +299,8 @@ def headline(pkg, ctx, g, args, srcs, R, sample_clocks):
     clocks = sampler.stop() if sampler else None
     ms = R.max(ms)
 
-    # end to end: host source ids -> ppr_fora_batch -> dense doubles in pinned host memory (sub-batches of 10 sources)
-    sub = min(10, q)
+    # end to end: host source ids -> ppr_fora_batch -> dense doubles in pinned host memory (sub-batches of 25 sources)
+    sub = min(25, q)
     out = ctx.pinned((sub, n), np.float64)
 
     def e2e_step(i):
@@ -447,7 +447,7 @@ def main():
         "work_per_query": {"edges": acc["edges"] / nq_rank, "walks": acc["walks"] / nq_rank, "pushes": acc["pushes"] / nq_rank,
                            "non_dangling_fraction": acc["nd"] / nq_rank},
         "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": 4 * q, "d2h_bytes_per_step": 8 * n * q,
-                "api": "ppr_fora_batch (Fora_Whole_Graph.computeWholeGraphPPR per source), 10 sources per call, dense f64 result vectors to pinned host memory"},
+                "api": "ppr_fora_batch (Fora_Whole_Graph.computeWholeGraphPPR per source), 25 sources per call, dense f64 result vectors to pinned host memory"},
         "gpu_launches": int(acc["launches"]),
         "clocks": m["clocks"],
         "roofline": {"bound": "hbm", "kernel": "k_push_query", "achieved": push_gbs, "peak": peak, "unit": "GB/s",

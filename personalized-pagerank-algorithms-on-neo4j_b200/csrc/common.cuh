@@ -238,7 +238,8 @@ struct Workspace {
     u64* dbg;          // per-iteration timeline of the last push kernel: DBG_FIELDS u64 per iteration
     PushCtl* ctl;      // device
     PushCtl* ctl_host; // pinned mirror
-    int coop_blocks;   // grid size of the cooperative kernels
+    int coop_blocks;   // grid size of the cooperative push / reverse-push kernels
+    int sel_blocks;    // grid size of the cooperative radix select (its own occupancy: 256-thread CTAs, up to four per SM)
 };
 
 struct ppr_graph {

@@ -305,7 +305,9 @@ static int32_t ws_alloc(ppr_ctx* ctx, Workspace& w, i64 n, i64 chunk_cap) {
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_topk_select, SEL_THREADS, 0));
     int occ3 = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_bwd_batch, PUSH_THREADS, 0));
-    occ = std::min(occ, std::min(occ2, occ3));
+    if (occ2 < 1) return ctx_fail(ctx, PPR_E_CUDA, "cooperative kernels do not fit on an SM");
+    w.sel_blocks = ctx->sm_count * std::min(occ2, 4);
+    occ = std::min(occ, occ3);
     if (occ < 1) return ctx_fail(ctx, PPR_E_CUDA, "cooperative kernels do not fit on an SM");
     w.coop_blocks = ctx->sm_count * std::min(occ, 4);
     CUDA_TRY(dalloc(&w.blk_a, (size_t)w.coop_blocks)); CUDA_TRY(dalloc(&w.blk_b, (size_t)w.coop_blocks));
@@ -407,6 +409,9 @@ struct GraphExtra {  // host-side bookkeeping kept beside ppr_graph
     // ppr_fora_batch: events and the pinned control-block snapshots are created once and reused by every call
     std::vector<cudaEvent_t> batch_ev;      // 4 timing events per query (only when the caller asks for stats)
     cudaEvent_t done_ev[2], copied_ev[2];   // per workspace: result ready / result downloaded (no timing)
+    // ring of export buffers: a query's doubles leave its workspace at once, so the next queries compute while up to BATCH_RING
+    // downloads are queued (sources without out-edges finish in ~0.1 ms but still return a dense n-vector)
+    double* ring[8]; cudaEvent_t ring_done[8], ring_copied[8]; bool ring_ready;
     bool batch_ev_ready;
     PushCtl* snaps; size_t snaps_cap;       // pinned
     i64 bwd_chunks_per_target;              // chunk descriptors one reverse-push target can need in one iteration
@@ -441,6 +446,7 @@ extern "C" int32_t ppr_graph_destroy(ppr_graph* g) {
         for (auto& e : x->batch_ev) cudaEventDestroy(e);
         if (x->batch_ev_ready) for (int i = 0; i < 2; i++) { cudaEventDestroy(x->done_ev[i]); cudaEventDestroy(x->copied_ev[i]); }
         if (x->snaps) cudaFreeHost(x->snaps);
+        if (x->ring_ready) for (int i = 0; i < 8; i++) { cudaFree(x->ring[i]); cudaEventDestroy(x->ring_done[i]); cudaEventDestroy(x->ring_copied[i]); }
         cudaFree(x->metric_vec[0]); cudaFree(x->metric_vec[1]); cudaFree(x->pm_result); cudaFree(x->sort_ids); cudaFree(x->sort_vals); cudaFree(x->bwd_order); cudaFree(x->edge_inv);
     }
     cudaFree(g->d.out_vtx); cudaFree(g->d.col_idx); cudaFree(g->d.out_deg); cudaFree(g->d.row32);
@@ -479,6 +485,7 @@ extern "C" int32_t ppr_graph_create(ppr_ctx* ctx, int64_t n, int64_t m, const in
     x->bcw_ready = false; memset(&x->bcw, 0, sizeof x->bcw);
     x->metric_vec[0] = x->metric_vec[1] = nullptr; x->metric_set[0] = x->metric_set[1] = false; x->pm_result = nullptr; x->last_is_pm = false; x->sort_ids = nullptr; x->sort_vals = nullptr; x->sort_cap = 0; x->bwd_order = nullptr; x->bwd_order_cap = 0; x->edge_inv = nullptr;
     x->batch_ev_ready = false; x->snaps = nullptr; x->snaps_cap = 0; x->bwd_chunks_per_target = 1;
+    x->ring_ready = false; for (int i = 0; i < 8; i++) x->ring[i] = nullptr;
     { std::lock_guard<std::mutex> lk(g_extras_mu); g_extras.push_back(std::make_pair(g, x)); }
     g->d.n = n; g->d.m = m;
     i64* d_ptr = nullptr;
@@ -874,6 +881,17 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
         }
         x->batch_ev_ready = true;
     }
+    constexpr int BATCH_RING = 6;
+    if (!resident && !x->ring_ready) {
+        for (int i = 0; i < 8; i++) { x->ring[i] = nullptr; }
+        for (int i = 0; i < BATCH_RING; i++) {
+            CUDA_TRY(dalloc(&x->ring[i], (size_t)n));
+            CUDA_TRY(cudaEventCreateWithFlags(&x->ring_done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&x->ring_copied[i], cudaEventDisableTiming));
+        }
+        for (int i = BATCH_RING; i < 8; i++) { CUDA_TRY(cudaEventCreateWithFlags(&x->ring_done[i], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&x->ring_copied[i], cudaEventDisableTiming)); }
+        x->ring_ready = true;
+    }
     if (stats_out) {
         try { x->batch_ev.reserve((size_t)nq * 3); } catch (...) { return ctx_fail(ctx, PPR_E_NOMEM, "ppr_fora_batch: host allocation failed"); }
         while (x->batch_ev.size() < (size_t)nq * 3) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); x->batch_ev.push_back(e); }
@@ -889,38 +907,37 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
     cudaError_t ce = cudaSuccess;
     int32_t rc = PPR_OK;
 #define Q_TRY(expr) do { if (ce == cudaSuccess) { ce = (expr); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, #expr, __FILE__, __LINE__); } } while (0)
-    bool used[2] = {false, false};
     // automatic: two queries in flight only while both working sets fit in the L2 together (measured: +17 % at
     // R-MAT scale 20, -1.5 % at scale 22)
     const bool small_graph = 4.0 * (double)g->d.m + 8.0 * (double)g->d.n <= 96.0 * 1024 * 1024;
     // (two cooperative kernels are only resident together when an SM holds two of their CTAs)
     const bool dual = nq > 1 && g->ws[0].coop_blocks >= 2 * ctx->sm_count && (ctx->batch_streams == 2 || (ctx->batch_streams == 0 && small_graph));
-    auto issue_copy = [&](int q) {
-        // download of query q on the copy stream, overlapping the kernels of query q+1
-        Workspace& w = g->ws[q & 1];
-        Q_TRY(cudaStreamWaitEvent(ctx->copy, x->done_ev[q & 1], 0));
-        Q_TRY(cudaMemcpyAsync(ppr_out + (size_t)q * n, w.out_f64, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy));
-        Q_TRY(cudaEventRecord(x->copied_ev[q & 1], ctx->copy));
-    };
+    bool ring_used[8] = {false, false, false, false, false, false, false, false};
     for (int q = 0; q < nq && rc == PPR_OK; q++) {
         Workspace& w = g->ws[q & 1];
+        const int slot = q % BATCH_RING;
         cudaEvent_t* e = stats_out ? &x->batch_ev[(size_t)q * 3] : nullptr;
         // Two compute streams: query q+1 (other workspace, other stream) runs concurrently with query q, so the
         // nearly idle tail iterations of one push overlap the dense phases / walks of the other.  Each cooperative
         // kernel then takes one CTA per SM so that both are resident together.
         cudaStream_t st = dual ? (q & 1 ? ctx->stream2 : ctx->stream) : ctx->stream;
-        if (used[q & 1] && !resident) Q_TRY(cudaStreamWaitEvent(st, x->copied_ev[q & 1], 0));  // out_f64 of this workspace is free again
-        if (rc) break;
         rc = fora_launch(g, w, srcs[q], alpha, eps, seed + (u64)q, flags, conf, 0, 1, e ? e[0] : nullptr, e ? e[1] : nullptr, e ? e[2] : nullptr,
                          &omegas[q], st, dual ? ctx->sm_count : 0);
         if (rc) break;
-        if (!resident) { k_export_f64<<<ctx->sm_count * 8, 256, 0, st>>>(w.reserve, w.out_f64, n, 0.0); Q_TRY(cudaGetLastError()); }
+        if (!resident) {
+            // the doubles leave the workspace for a ring buffer at once; the download of query q (copy stream) overlaps the
+            // kernels of the next BATCH_RING - 1 queries
+            if (ring_used[slot]) Q_TRY(cudaStreamWaitEvent(st, x->ring_copied[slot], 0));   // ring[slot] has been downloaded
+            k_export_f64<<<ctx->sm_count * 8, 256, 0, st>>>(w.reserve, x->ring[slot], n, 0.0);
+            Q_TRY(cudaGetLastError());
+            Q_TRY(cudaEventRecord(x->ring_done[slot], st));
+            Q_TRY(cudaStreamWaitEvent(ctx->copy, x->ring_done[slot], 0));
+            Q_TRY(cudaMemcpyAsync(ppr_out + (size_t)q * n, x->ring[slot], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy));
+            Q_TRY(cudaEventRecord(x->ring_copied[slot], ctx->copy));
+            ring_used[slot] = true;
+        }
         if (stats_out) Q_TRY(cudaMemcpyAsync(&x->snaps[q], w.ctl, sizeof(PushCtl), cudaMemcpyDeviceToHost, st));
-        Q_TRY(cudaEventRecord(x->done_ev[q & 1], st));
-        used[q & 1] = true;
-        if (q > 0 && !resident && rc == PPR_OK) issue_copy(q - 1);
     }
-    if (rc == PPR_OK && nq > 0 && !resident) issue_copy(nq - 1);
 #undef Q_TRY
     cudaError_t s1 = cudaStreamSynchronize(ctx->stream), s2 = cudaStreamSynchronize(ctx->copy);
     { cudaError_t s3 = cudaStreamSynchronize(ctx->stream2); if (s1 == cudaSuccess) s1 = s3; }
@@ -1048,7 +1065,7 @@ static int32_t run_select(ppr_graph* g, Workspace& w, const u64* vals, i64 n, i6
     SelArgs S;
     S.vals = vals; S.n = n; S.k = k; S.hist = w.hist; S.sel_ids = w.sel_ids; S.sel_vals = w.sel_vals; S.sel_cap = w.sel_cap; S.ctl = w.ctl;
     void* args[] = {&S};
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_topk_select, dim3(w.coop_blocks), dim3(SEL_THREADS), args, 0, ctx->stream));
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_topk_select, dim3(w.sel_blocks), dim3(SEL_THREADS), args, 0, ctx->stream));
     return PPR_OK;
 }
 

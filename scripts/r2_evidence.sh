@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 single-GPU evidence: GPU tests, both bench arms, launch list and one full ncu capture (run under gpurun).
 set -x
-O=gpurun_out/r2h
+O=gpurun_out/r2q
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem --format=csv > $O/gpu.txt
 timeout 1500 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "rc=$?" >> $O/pytest_gpu.log
@@ -15,3 +15,7 @@ python scripts/one_query.py 22 4 > $O/oq22.log 2>&1 && timeout 900 ncu --set ful
     -k regex:"k_push_query|k_walk" -s 4 -c 4 -o $O/full_s22 -f python scripts/one_query.py 22 4 > $O/ncu_s22.log 2>&1
 ls -la $O
 tail -3 $O/pytest_gpu.log; cat $O/bench.json | cut -c1-3000
+timeout 600 python scripts/bench_configs.py topk --cpu 0 > $O/config3_topk_1gpu.json 2> $O/config3.err
+PPR_DEBUG_TIMING=1 PPR_BWD_TIMING=1 timeout 600 python scripts/bwd_ab.py > $O/bwd_ab_final.log 2>&1
+python scripts/bwd_ncu.py 5e-5 6000 > $O/bn2.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bwd_cta -s 2 -c 2 -o $O/bwd_5e-5_final -f python scripts/bwd_ncu.py 5e-5 6000 > $O/ncu_bwd.log 2>&1
+ls -la $O
