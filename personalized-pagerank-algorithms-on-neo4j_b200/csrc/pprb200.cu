@@ -2036,7 +2036,9 @@ extern "C" int32_t ppr_pairs_export(const ppr_pairs* p, int64_t* src_ptr, int32_
         if (val_fx) memcpy(val_fx, p->val.data(), p->val.size() * sizeof(u64));
         return PPR_OK;
     }
-    // device-resident index: straight into the caller's arrays (doubles are converted on the device: value * 2^-62 is exact)
+    // device-resident index: straight into the caller's arrays (doubles are converted on the device: value * 2^-62 is exact).
+    // (A hand-rolled double-buffered copy through pinned staging was measured slower than cudaMemcpy into pageable memory here:
+    // 1.3 s against 0.5 s for the 75 M-pair index, the pinned allocations alone cost ~0.1 s per call.)
     if (cudaSetDevice(p->device) != cudaSuccess) return PPR_E_CUDA;
     const size_t c = (size_t)p->count;
     if (tgt && cudaMemcpy(tgt, p->d_tgt, c * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return PPR_E_CUDA;
