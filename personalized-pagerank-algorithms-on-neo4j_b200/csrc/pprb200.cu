@@ -911,7 +911,10 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
     // R-MAT scale 20, -1.5 % at scale 22)
     const bool small_graph = 4.0 * (double)g->d.m + 8.0 * (double)g->d.n <= 96.0 * 1024 * 1024;
     // (two cooperative kernels are only resident together when an SM holds two of their CTAs)
-    const bool dual = nq > 1 && g->ws[0].coop_blocks >= 2 * ctx->sm_count && (ctx->batch_streams == 2 || (ctx->batch_streams == 0 && small_graph));
+    const bool two_per_sm = g->ws[0].coop_blocks >= 2 * ctx->sm_count;
+    const bool dual = nq > 1 && (ctx->batch_streams == 2 || (ctx->batch_streams == 0 && small_graph && two_per_sm));
+    // with one cooperative CTA per SM two queries share the GPU as two halves of the SMs
+    const int dual_blocks = two_per_sm ? ctx->sm_count : std::max(1, ctx->sm_count / 2);
     bool ring_used[8] = {false, false, false, false, false, false, false, false};
     for (int q = 0; q < nq && rc == PPR_OK; q++) {
         Workspace& w = g->ws[q & 1];
@@ -922,7 +925,7 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
         // kernel then takes one CTA per SM so that both are resident together.
         cudaStream_t st = dual ? (q & 1 ? ctx->stream2 : ctx->stream) : ctx->stream;
         rc = fora_launch(g, w, srcs[q], alpha, eps, seed + (u64)q, flags, conf, 0, 1, e ? e[0] : nullptr, e ? e[1] : nullptr, e ? e[2] : nullptr,
-                         &omegas[q], st, dual ? ctx->sm_count : 0);
+                         &omegas[q], st, dual ? dual_blocks : 0);
         if (rc) break;
         if (!resident) {
             // the doubles leave the workspace for a ring buffer at once; the download of query q (copy stream) overlaps the
