@@ -907,12 +907,12 @@ extern "C" int32_t ppr_fora_batch(ppr_graph* g, const int32_t* srcs, int32_t nq,
     cudaError_t ce = cudaSuccess;
     int32_t rc = PPR_OK;
 #define Q_TRY(expr) do { if (ce == cudaSuccess) { ce = (expr); if (ce != cudaSuccess) rc = ctx_fail_cuda(ctx, ce, #expr, __FILE__, __LINE__); } } while (0)
-    // automatic: two queries in flight only while both working sets fit in the L2 together (measured: +17 % at
-    // R-MAT scale 20, -1.5 % at scale 22)
+    // automatic: two queries in flight only while both working sets fit in the L2 together (measured with each query on half of
+    // the SMs: +17.5 % at R-MAT scale 20 (358 -> 421 queries/s), -1 % at scale 22)
     const bool small_graph = 4.0 * (double)g->d.m + 8.0 * (double)g->d.n <= 96.0 * 1024 * 1024;
     // (two cooperative kernels are only resident together when an SM holds two of their CTAs)
     const bool two_per_sm = g->ws[0].coop_blocks >= 2 * ctx->sm_count;
-    const bool dual = nq > 1 && (ctx->batch_streams == 2 || (ctx->batch_streams == 0 && small_graph && two_per_sm));
+    const bool dual = nq > 1 && (ctx->batch_streams == 2 || (ctx->batch_streams == 0 && small_graph));
     // with one cooperative CTA per SM two queries share the GPU as two halves of the SMs
     const int dual_blocks = two_per_sm ? ctx->sm_count : std::max(1, ctx->sm_count / 2);
     bool ring_used[8] = {false, false, false, false, false, false, false, false};
