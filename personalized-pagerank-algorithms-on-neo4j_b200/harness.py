@@ -58,6 +58,7 @@ class Gen_Util:
         self.dir_db = "got.db"
         self.alpha, self.epsilon = 0.15, 0.5
         self.node_property, self.label_type, self.rel_type = "name", "Person", "Relation"
+        self.device_metrics = False   # True: computeError is evaluated in HBM (ppr_metrics_keep / ppr_metrics_compute) instead of on host vectors
         self.node_amount = self.rel_amount = 0
         self.fw = None
         self.rng = np.random.default_rng(1234)
@@ -104,9 +105,17 @@ class Gen_Util:
                 t0 = time.perf_counter_ns()
                 topk_t.computeTopKPPR(q, k, param)
                 duration += time.perf_counter_ns() - t0
+                on_dev = self.device_metrics and algoType != BASE_WHOLE_GRAPH
+                if on_dev:
+                    self.adjM.metrics_keep(1)
                 pm_t.computeTopKPPR(q, k, None)
-                p = compute_error(topk_t, pm_t, PRECISION, k)
-                g = compute_error(topk_t, pm_t, NDCG, k)
+                if on_dev:      # J/Gen_Util.java:264-300 on the device: both vectors are still in HBM
+                    self.adjM.metrics_keep(0)
+                    m = self.adjM.metrics_compute(k)
+                    p, g = m["precision"], m["ndcg"]
+                else:
+                    p = compute_error(topk_t, pm_t, PRECISION, k)
+                    g = compute_error(topk_t, pm_t, NDCG, k)
                 sum_precision += p or 0.0
                 sum_ndcg += g or 0.0
             avg = duration // query_num
@@ -132,8 +141,15 @@ class Gen_Util:
                 else:
                     algo_t.computeWholeGraphPPR(q, param)
                 duration += time.perf_counter_ns() - t0
+                on_dev = self.device_metrics and not prep
+                if on_dev:
+                    self.adjM.metrics_keep(1)
                 pm_t.computeWholeGraphPPR(q, None)
-                sum_max_err += compute_error(algo_t, pm_t, MAX_ERR, -1)
+                if on_dev:      # J/Gen_Util.java:306-321 on the device
+                    self.adjM.metrics_keep(0)
+                    sum_max_err += self.adjM.metrics_compute(0)["max_err"]
+                else:
+                    sum_max_err += compute_error(algo_t, pm_t, MAX_ERR, -1)
             avg = duration // query_num
             row.update(avg_ms=avg / 1e6, max_err=sum_max_err / query_num)
             if not to_be_preprocessed:

@@ -73,6 +73,23 @@ def test_harness_rows(pkg, ctx, got, tmp_path):
     lines = open(tmp_path / "rows.txt").read().splitlines()
     assert lines[0].startswith("0.5,") and lines[1].startswith("0.5,10,") and lines[2].startswith("1.0E-6,")
     assert r1["max_err"] < 0.05 and r2["precision"] > 0.8 and r2["ndcg"] > 0.97 and r3["max_err"] < 1e-4
+    # the same rows with computeError evaluated in HBM (device_metrics): same queries (rng state restored), same seeds (fresh algorithm objects)
+    for dev in (False, True):
+        t.device_metrics = dev
+        rows = []
+        with open(tmp_path / ("rows_%d.txt" % dev), "w") as fw:
+            t.fw = fw
+            for args in (("FORA_WHOLE_GRAPH", 8, -1, 0.5, -1.0, False, "WHOLE_GRAPH"), ("FORA_TOPK", 8, 10, 0.5, -1.0, False, "TOPK"),
+                         ("MC", 8, 10, 1.0, -1.0, False, "TOPK"), ("FWDPUSH", 8, -1, 1e-6, -1.0, False, "WHOLE_GRAPH")):
+                t.rng = np.random.default_rng(99)
+                rows.append(t.algo_perf_test(*args))
+        if dev:
+            for a, b in zip(host_rows, rows):
+                for key in ("max_err", "precision", "ndcg"):
+                    if key in a:
+                        assert abs(a[key] - b[key]) < 1e-12, (a["algo"], key, a[key], b[key])
+        else:
+            host_rows = rows
     t.adjM.close()
 
 
