@@ -132,7 +132,7 @@ __device__ __forceinline__ u32 ld_acquire_u32(const u32* p) { u32 v; asm volatil
 __device__ __forceinline__ void red_release_u32(u32* p, u32 v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 // Barrier among the first K CTAs of the grid (the "small regime" below): one release-add and an acquire spin per
-// CTA on a monotonic counter.  ~1.5 us for K = 32, against ~5 us for a barrier over all 296 CTAs.
+// CTA on a monotonic counter.  ~1.5 us for K = 32, against ~3-5 us for a barrier over the whole grid.
 __device__ __forceinline__ void sub_sync(u32* bar, u32 K, u32& target) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -729,7 +729,7 @@ __device__ __noinline__ void push_mini(const PushArgs& A, int par, u64 rmax_fx, 
 
 // --------------------------------------------------------------------------------- the small regime
 // Frontiers between the single-CTA limit and (midi_v vertices, midi_e edges) are too big for one CTA and far too small
-// for 296: a grid-wide iteration costs ~30 us there, nearly all of it barrier and dependent-round-trip latency.  The
+// for the whole grid: a grid-wide iteration costs ~30 us there, nearly all of it barrier and dependent-round-trip latency.  The
 // first K CTAs (one per SM) iterate them with a barrier among themselves (sub_sync, ~1.5 us) and hand frontiers that
 // shrink further to CTA 0's push_mini without leaving the regime; the other CTAs wait at the next grid barrier.  Same
 // phase functions, same schedule, same bits as the grid-wide iteration.
