@@ -39,6 +39,7 @@ struct BwdCtaArgs {
     i32 t_lo, t_hi;
     u64 alpha_q64, rmax_fx, thr_fx;
     int key_bits;               // B: key = v << B | t
+    u64 scan_edges;             // an iteration whose frontier owns at least this many in-edges adds with plain reductions and finds the next frontier by a sweep of the row
     u64* out_key; u64* out_val; i64 out_cap;
     ull* counters;              // [0] pair cursor, [1] pushes, [2] edges, [3] iterations (summed over targets)
                                 // timing != 0: [4] ticket+seed ns, [5] phase A ns, [6] phase B ns, [7] output+clean ns, [8] targets, [9] longest target ns (thread 0's clock)
@@ -88,6 +89,7 @@ __device__ __forceinline__ void cta_append4(u32* list, u32* sm_cursor, const boo
 struct BwdCursors {
     u32 ticket;
     u32 ncount[2];      // frontier sizes by iteration parity
+    u32 fedges[2];      // in-edges owned by the frontier (staged path), by iteration parity
     u32 npushed, ntouched, overflow;
     u32 outoff, total;  // output compaction
     ull outbase;
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
             __stcg(reinterpret_cast<ull*>(&R[t]), (ull)FX_ONE);
             if (TEAM == 1) mf[0][0] = (u32)t;
             __stcg(&F[0][0], (u32)t); __stcg(&TOUCHED[0], (u32)t);
-            C->ncount[0] = 1; C->ncount[1] = 0; C->ntouched = 1; C->npushed = 0; C->overflow = 0; C->total = 0; C->outoff = 0;
+            C->ncount[0] = 1; C->ncount[1] = 0; C->fedges[0] = 0; C->fedges[1] = 0; C->ntouched = 1; C->npushed = 0; C->overflow = 0; C->total = 0; C->outoff = 0;
         }
         int par = 0;
         u64 acc_pushes = 0, acc_edges = 0, acc_iters = 0;   // rank 0, thread 0
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
         for (;;) {
             const u32 cnt = C->ncount[par];
             if (cnt == 0) break;
-            if (rank == 0 && tid == 0) C->ncount[par ^ 1] = 0;   // last read one iteration ago, behind two team barriers
+            if (rank == 0 && tid == 0) { C->ncount[par ^ 1] = 0; C->fedges[par ^ 1] = 0; }   // last read one iteration ago, behind two team barriers
             u32* next = F[par ^ 1];
             u32* next_m = TEAM == 1 ? mf[par ^ 1] : nullptr;
             // ---- phase A (J/Backward_Search.java:58-68): capture and zero the residue, move the alpha part to the reserve
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                 }
                 cta_append(PUSHED, &C->npushed, fresh, v, nullptr, 0u, cap, &C->overflow);
             } else {
+                u64 my_d = 0;
                 for (u32 base = 0; base < cnt; base += tstride) {
                     const u32 i = base + tfirst;
                     bool fresh = false;
@@ -198,17 +201,23 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                         const u64 old = __ldcg(&RES[v]);
                         __stcg(reinterpret_cast<ull*>(&RES[v]), (ull)(old + a));
                         fresh = old == 0;
-                        __stcg(reinterpret_cast<ull*>(&ST_PK[i]), (ull)__ldg(&A.in_vtx[v]));
+                        const u64 rec = __ldg(&A.in_vtx[v]);
+                        my_d += vtx_deg(rec);
+                        __stcg(reinterpret_cast<ull*>(&ST_PK[i]), (ull)rec);
                         __stcg(reinterpret_cast<ull*>(&ST_Y[i]), (ull)(x - a));
                     }
                     cta_append(PUSHED, &C->npushed, fresh, v, nullptr, 0u, cap, &C->overflow);
                 }
+                const u64 cta_d = block_sum_u64(my_d, scratch);
+                if (tid == 0 && cta_d) atomicAdd(&C->fedges[par], (u32)min(cta_d, (u64)0x7fffffffull));
             }
             team_sync();   // every capture precedes every add of this iteration
             if (clock) { const u64 now = globaltimer_ns(); tmA += now - tm1; tm1 = now; }
             // ---- phase B (J/Backward_Search.java:77-94): tiles of BD frontier vertices; the team's CTAs take equal shares of a
             // tile's concatenated in-edge list, four consecutive edges per thread
             u64 it_edges = 0;
+            u64 fed = single ? 0 : (u64)C->fedges[par];
+            bool scan = false;
             for (u32 base = 0; base < cnt; base += BD) {
                 if (!single) {
                     const u32 i = base + tid;
@@ -224,6 +233,8 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                 m_y[tid] = y;
                 __syncthreads();
                 it_edges += t_d;
+                if (single) fed = t_d;
+                scan = fed >= A.scan_edges;   // uniform over the team: dense iteration, see below
                 const u64 e_lo = TEAM == 1 ? 0 : t_d * rank / TEAM, e_hi = TEAM == 1 ? t_d : t_d * (rank + 1) / TEAM;
                 for (u64 eb = e_lo; eb < e_hi; eb += 4 * BD) {
                     // four consecutive edges per thread: one binary search for the first, the others advance linearly
@@ -250,6 +261,11 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
 #pragma unroll
                         for (int k = 0; k < 4; k++) if (u[k] != 0xffffffffu) inc[k] = mulhi64(inc[k], __ldg(&A.invdeg[u[k]]));
                     }
+                    if (scan) {   // dense iteration: fire-and-forget reductions, nothing waits for a returned value
+#pragma unroll
+                        for (int k = 0; k < 4; k++) if (u[k] != 0xffffffffu && inc[k]) red_add_u64(&R[u[k]], inc[k]);
+                        continue;
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; k++) old[k] = (u[k] != 0xffffffffu && inc[k]) ? atomicAdd((ull*)&R[u[k]], (ull)inc[k]) : 1ull;
                     bool first[4], cross[4];
@@ -263,6 +279,26 @@ __global__ void __launch_bounds__(BD) k_bwd_cta(const __grid_constant__ BwdCtaAr
                     cta_append4(next, &C->ncount[par ^ 1], cross, u, next_m, (u32)BD, cap, &C->overflow);
                 }
                 __syncthreads();
+            }
+            if (scan) {
+                // Dense iteration (J/Backward_Search.java:84-94 with the test r > rmax applied after all adds): the residues above rmax
+                // after the adds are exactly the vertices that crossed during the iteration (everything above rmax before it was in the
+                // frontier and has been zeroed), so a sweep of the row finds the same next frontier as the per-add test.  The touched
+                // list is not maintained: the row is cleaned densely when the search ends.
+                if (tid == 0) C->overflow = 1;
+                __threadfence();
+                team_sync();   // every reduction of the iteration has been performed
+                for (i64 base = 0; base < n; base += 4 * (i64)tstride) {
+                    bool pr[4];
+                    u32 vv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const i64 v = base + (i64)k * tstride + tfirst;
+                        vv[k] = (u32)v;
+                        pr[k] = v < n && __ldcg(&R[v]) > A.rmax_fx;
+                    }
+                    cta_append4(next, &C->ncount[par ^ 1], pr, vv, next_m, (u32)BD, cap, &C->overflow);
+                }
             }
             if (rank == 0 && tid == 0) { acc_pushes += cnt; acc_edges += it_edges; acc_iters += 1; }
             par ^= 1;

@@ -1704,6 +1704,8 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
         A.thr_fx = cl >= 18446744073709551615.0 ? ~0ull : (u64)cl;
     }
     A.key_bits = key_bits;
+    // dense iterations of a search (frontier owning >= n / 8 in-edges): plain reductions + a sweep of the row instead of returning atomics
+    { const char* e = getenv("PPR_BWD_SCAN"); A.scan_edges = e ? (u64)atoll(e) : (u64)std::max<i64>(n / 8, 4096); }
 
     // per-slot state is 48 n bytes; stay within half of the free memory
     size_t free_b = 0, total_b = 0;

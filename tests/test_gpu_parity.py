@@ -546,6 +546,27 @@ def test_all_pairs_cluster_teams(R12, R16, O, ctx, monkeypatch):
     assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"]) and st["launches"] == 3   # probe, teams, rest
 
 
+def test_all_pairs_dense_iterations(R12, G, OG, O, monkeypatch):
+    # iterations whose frontier owns many in-edges add with plain reductions and find the next frontier by sweeping the residue row
+    # (PPR_BWD_SCAN = the switch point in edges): every iteration that way (0), none (huge), a mix (256), as single CTAs and as teams
+    g, og = R12
+    refs = {thr: O.b_base_all_pairs(og, ALPHA, thr, 0, 300) for thr in (1e-3, 1e-6)}
+    gref = O.b_base_all_pairs(OG, ALPHA, 1e-3)
+    for scan in ("0", "256", "1000000000000"):
+        monkeypatch.setenv("PPR_BWD_SCAN", scan)
+        for team in (None, "2"):
+            if team:
+                monkeypatch.setenv("PPR_BWD_FORCE_TEAM", "1"); monkeypatch.setenv("PPR_BWD_TEAM", team)
+            else:
+                monkeypatch.delenv("PPR_BWD_FORCE_TEAM", raising=False); monkeypatch.delenv("PPR_BWD_TEAM", raising=False)
+            for thr, (optr, otgt, oval, ost) in refs.items():
+                ptr, tgt, val, st = g.backward_all_pairs(ALPHA, thr, -1, 0, 300, raw=True)
+                assert np.array_equal(ptr, optr) and np.array_equal(tgt, otgt) and np.array_equal(val, oval), (scan, team, thr)
+                assert (st["pushes"], st["edges"]) == (ost["pushes"], ost["edges"])
+            ptr, tgt, val, st = G.backward_all_pairs(ALPHA, 1e-3, raw=True)       # GOT: dangling targets, tiny rows
+            assert np.array_equal(ptr, gref[0]) and np.array_equal(tgt, gref[1]) and np.array_equal(val, gref[2]), (scan, team)
+
+
 def test_backward_search_dense_graph(pkg, ctx, O):
     # n = 2048 with ~600 in-edges per vertex: one iteration of ONE target stages ceil(indeg / 256) chunk descriptors for
     # every vertex, far more than T * n -- the chunk buffer is sized from the in-degree histogram at export
