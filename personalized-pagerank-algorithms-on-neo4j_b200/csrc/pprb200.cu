@@ -1727,7 +1727,7 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
     //   (C) the rest, heaviest first (longest-processing-time-first); as teams of 2 CTAs when the probe's searches relax >= 64 K edges
     //       on average (fewer searches in flight keep their residue rows in the L2: 836 against 1 090 ms at threshold 5e-5).
     const i64 R = t_hi - t_lo;
-    int team_heavy = 8, team_rest = 2;
+    int team_heavy = 4, team_rest = 2;
     i64 heavy = -1;
     { const char* e;
       if ((e = getenv("PPR_BWD_TEAM"))) { int v = atoi(e); team_heavy = (v == 2 || v == 4 || v == 8) ? v : 1; }
