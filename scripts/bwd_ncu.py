@@ -6,7 +6,6 @@ thr = float(sys.argv[1]) if len(sys.argv) > 1 else 1e-3
 hi = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
 rp, ci = pkg.rmat(100000, 1600000, seed=42, symmetric=True)
 ctx = pkg.Context(0)
-ctx.set_bwd_batch(hi)
 g = pkg.Graph(ctx, rp, ci)
 for rep in range(2):
     ptr, tgt, val, st = g.backward_all_pairs(0.15, thr, -1, 0, hi)
