@@ -1747,7 +1747,7 @@ extern "C" int32_t ppr_backward_all_pairs(ppr_graph* g, double alpha, double thr
             i64 H = 0, probe = 0;
             if (ctx->bwd_batch <= 0 && !force_team) {
                 if (team_heavy > 1) H = std::min<i64>(R, heavy >= 0 ? heavy : (i64)8 * bwd_team_slots(ctx, team_heavy));
-                probe = std::min<i64>(R - H, std::max<i64>(2048, (i64)ctx->sm_count * 16));
+                probe = std::min<i64>(R - H, std::max<i64>(1024, (i64)ctx->sm_count * 8));
             }
             // layout of the order: [probe sample of the non-heavy targets][the H heaviest][the other targets, heaviest first]
             order.reserve((size_t)R);

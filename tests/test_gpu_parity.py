@@ -494,9 +494,9 @@ def test_all_pairs(G, OG, R12, O):
 
 
 def test_all_pairs_launch_split(R16, O, ctx):
-    # n = 65536, 12000 targets: a probe launch (1184 targets, 256-thread CTAs), then the rest in one launch with the CTA shape
-    # chosen from the work per target -- the index must not depend on how targets are split over launches, CTA shapes,
-    # or on the pair buffer being regrown (PPR_BWD_* overrides are exercised by the forced batch below)
+    # n = 65536, 12000 targets: a probe launch over an evenly spaced sample (1184 targets, one CTA per search), the highest in-degree
+    # targets as cluster teams, the rest heaviest first -- the index must not depend on how targets are split over launches or on
+    # the pair buffer being regrown (forced batches below)
     g, og = R16
     hi = 12000
     optr, otgt, oval, ost = O.b_base_all_pairs(og, ALPHA, 1e-3, 0, hi)
