@@ -9,6 +9,8 @@
 // neo4j-graph-algorithms jar is undeclared in pom.xml) and is unseeded (ThreadLocalRandom).  This file
 // restates its algorithms from the source text; the only external anchors are the GOT power-method
 // values recorded in SURVEY.md section 8c and the Random123 Philox4x32-10 known-answer vectors.
+// A second, independently written restatement (tests/java_replay.py, plain Python) is held equal to
+// mode A bit for bit by tests/test_java_replay.py -- a transcription check, not a pin.
 //
 // `J/` = /root/reference/src/main/java/joezie/fora_neo4j/.
 //

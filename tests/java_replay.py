@@ -1,0 +1,222 @@
+"""Second, independent restatement of the reference's deterministic loops -- TEST INFRASTRUCTURE ONLY.
+
+`oracle/ppr_oracle.cpp` (mode A) was written from the Java text once; this file was written from the
+same text a second time, in plain Python with the Java collection semantics spelled out (FIFO
+`ConcurrentLinkedQueue`, membership `HashSet`, `HashMap.get`/`put`/`replace`, `java.util.HashMap`
+bucket iteration order, IEEE doubles == Python floats).  `tests/test_java_replay.py` holds the two
+against each other bit for bit.  It does not pin the oracle to the reference (the reference still cannot
+run here: no JDK, unseeded ThreadLocalRandom) -- it removes single-transcription mistakes from the
+parts of the path that are deterministic.  `J/` = /root/reference/src/main/java/joezie/fora_neo4j/.
+
+Edge order: `adjM.forEachRelationship` is the un-vendored HeavyGraph's adjacency order; both
+restatements take it to be the CSR order of the export (relationship id == CSV row).
+"""
+from collections import deque
+
+
+class JavaHashMap:
+    """java.util.HashMap<Long,Double> as far as iteration order goes: power-of-two table, bucket =
+    spread(Long.hashCode(key)) & (cap-1), insertion order inside a bucket, resize at 0.75 load keeps the
+    relative order of a split bucket (JDK 8 HashMap.resize lo/hi lists).  Buckets stay far below the
+    treeify threshold of 8 for the dense small integer keys used here."""
+
+    def __init__(self, cap=16):
+        self.cap = cap
+        self.size = 0
+        self.tab = [[] for _ in range(cap)]
+
+    @staticmethod
+    def _hash(key):
+        h = (key ^ (key >> 32)) & 0xFFFFFFFF          # Long.hashCode
+        return h ^ (h >> 16)                          # HashMap.hash spread
+
+    @classmethod
+    def copy_of(cls, other):
+        # HashMap(Map m): tableSizeFor(size/0.75 + 1), then put in m's iteration order
+        s = other.size
+        t = int(s / 0.75 + 1.0)
+        cap = 1
+        while cap < t:
+            cap <<= 1
+        m = cls(max(cap, 1))
+        for k, v in other.items():
+            m.put(k, v)
+        return m
+
+    def get(self, key):
+        for k, v in self.tab[self._hash(key) & (self.cap - 1)]:
+            if k == key:
+                return v
+        return None
+
+    def put(self, key, val):
+        b = self.tab[self._hash(key) & (self.cap - 1)]
+        for i, (k, _) in enumerate(b):
+            if k == key:
+                b[i] = (key, val)
+                return
+        b.append((key, val))
+        self.size += 1
+        if self.size > self.cap * 0.75:
+            old = self.tab
+            self.cap *= 2
+            self.tab = [[] for _ in range(self.cap)]
+            for bucket in old:
+                for k, v in bucket:
+                    self.tab[self._hash(k) & (self.cap - 1)].append((k, v))
+
+    def replace(self, key, val):
+        if self.get(key) is not None:
+            self.put(key, val)
+
+    def clear(self):
+        # HashMap.clear keeps the table length
+        self.tab = [[] for _ in range(self.cap)]
+        self.size = 0
+
+    def items(self):
+        for bucket in self.tab:
+            for kv in bucket:
+                yield kv
+
+
+def forward_push(rp, ci, s, alpha, rmax):
+    """J/Forward_Push.java:63-142.  Returns (reserve, residue, rsum_field, pushes, edges)."""
+    n = len(rp) - 1
+    deg = [rp[v + 1] - rp[v] for v in range(n)]
+    reserve, residue = {}, {}
+    rsum_field = None
+    if deg[s] == 0:                                               # :72-76
+        reserve[s] = 1.0
+        return reserve, residue, 0.0, 0, 0
+    rsum_local = 1.0
+    in_q = {s}
+    q = deque([s])
+    residue[s] = 1.0
+    pushes = edges = 0
+    while q:
+        v = q.popleft()
+        in_q.discard(v)
+        x = residue[v]
+        residue[v] = 0.0
+        reserve[v] = reserve.get(v, 0.0) + x * alpha              # :94
+        rsum_local -= x * alpha                                   # :97
+        pushes += 1
+        if deg[v] == 0:                                           # :101-115 (rsum field NOT refreshed on this path)
+            nr = residue[s] + x * (1.0 - alpha)
+            residue[s] = nr
+            if deg[s] > 0 and nr / float(deg[s]) >= rmax and s not in in_q:
+                q.append(s)
+                in_q.add(s)
+            continue
+        avg = ((1.0 - alpha) * x) / float(deg[v])                 # :117
+        for e in range(rp[v], rp[v + 1]):
+            u = ci[e]
+            nr = residue.get(u, 0.0) + avg
+            residue[u] = nr
+            edges += 1
+            du = deg[u]
+            ratio = nr / float(du) if du else float("inf")        # Java double division by 0 -> +Infinity
+            if ratio >= rmax and u not in in_q:                   # :132
+                q.append(u)
+                in_q.add(u)
+        rsum_field = rsum_local                                   # :140
+    return reserve, residue, (1.0 if rsum_field is None else rsum_field), pushes, edges
+
+
+def backward_search(rp_in, ri_in, outdeg, t, alpha, rmax):
+    """J/Backward_Search.java:38-100 on the in-edge lists (rp_in, ri_in).  Returns (reserve, pushes, edges)."""
+    reserve, residue = {}, {}
+    if rp_in[t + 1] - rp_in[t] == 0:                              # :46-49
+        reserve[t] = 1.0
+        return reserve, 0, 0
+    in_q = {t}
+    q = deque([t])
+    residue[t] = 1.0
+    pushes = edges = 0
+    while q:
+        v = q.popleft()
+        in_q.discard(v)
+        x = residue[v]
+        residue[v] = 0.0
+        reserve[v] = reserve.get(v, 0.0) + x * alpha              # :66
+        pushes += 1
+        avg = (1.0 - alpha) * x                                   # :72, divided per in-neighbour below
+        for e in range(rp_in[v], rp_in[v + 1]):
+            u = ri_in[e]
+            nr = residue.get(u, 0.0) + avg / outdeg[u]            # :83
+            residue[u] = nr
+            edges += 1
+            if nr > rmax and u not in in_q:                       # :87 (strict, no degree scaling)
+                q.append(u)
+                in_q.add(u)
+    return reserve, pushes, edges
+
+
+def power_method(rp, ci, s, alpha, iterations=100):
+    """J/Power_Method.java:44-101, including HashMap iteration order of `pairs` (the order in which
+    pushes of one round add into `residue`, which decides the last bits)."""
+    reserve = {}
+    residue = JavaHashMap()
+    residue.put(s, 1.0)
+    for _ in range(iterations):
+        pairs = JavaHashMap.copy_of(residue)                      # :58
+        residue.clear()
+        for v, x in pairs.items():
+            d = rp[v + 1] - rp[v]
+            if x > 0:
+                reserve[v] = reserve.get(v, 0.0) + x * alpha
+                remain = x * (1 - alpha)
+                if d == 0:                                        # :74-80
+                    old = residue.get(s)
+                    residue.put(s, (0.0 if old is None else old) + remain)
+                else:
+                    avg = remain / d
+                    for e in range(rp[v], rp[v + 1]):
+                        u = ci[e]
+                        old = residue.get(u)
+                        residue.put(u, (0.0 if old is None else old) + avg)
+    return reserve
+
+
+def kth_largest(vals, k):
+    """J/Algo_Util.java:32-50: the k-th largest value, null when k is outside 0..len.  The random pivot
+    does not change the answer; sorted() gives the same one.  k == 0 passes the range check, recurses
+    left until the range is empty and then dies in nextInt(0) -- callers never ask for it."""
+    if k < 0 or k > len(vals):
+        return None
+    if k == 0:
+        raise ValueError("J/Algo_Util.java:60 nextInt(0): bound must be positive")
+    return sorted(vals, reverse=True)[k - 1]
+
+
+def base_all_pairs(rp, ci, alpha, threshold, k=-1):
+    """J/Base_Whole_Graph.java:58-164: every vertex as a target in id order, keep pi(v,t) >= threshold
+    under source v in target order; k >= 0 keeps the rows' entries >= the k-th largest (ties included),
+    stable-sorted descending.  Returns ({v: [(t, pi)]}, pushes, edges)."""
+    n = len(rp) - 1
+    outdeg = [rp[v + 1] - rp[v] for v in range(n)]
+    cnt = [0] * (n + 1)
+    for u in ci:
+        cnt[u + 1] += 1
+    for v in range(n):
+        cnt[v + 1] += cnt[v]
+    rp_in, fill, ri_in = cnt, cnt[:-1].copy(), [0] * len(ci)
+    for v in range(n):
+        for e in range(rp[v], rp[v + 1]):
+            ri_in[fill[ci[e]]] = v
+            fill[ci[e]] += 1
+    rows, pushes, edges = {}, 0, 0
+    for t in range(n):
+        res, p, e = backward_search(rp_in, ri_in, outdeg, t, alpha, threshold)
+        pushes += p
+        edges += e
+        for v, pi in res.items():
+            if pi >= threshold:                                   # :83
+                rows.setdefault(v, []).append((t, pi))
+    if k >= 0:
+        for v, row in rows.items():
+            kth = kth_largest([p for _, p in row], k)
+            keep = [(t, p) for t, p in row if kth is None or p >= kth]   # :137-141
+            rows[v] = sorted(keep, key=lambda tp: -tp[1])         # List.sort is stable
+    return rows, pushes, edges
