@@ -220,3 +220,205 @@ def base_all_pairs(rp, ci, alpha, threshold, k=-1):
             keep = [(t, p) for t, p in row if kth is None or p >= kth]   # :137-141
             rows[v] = sorted(keep, key=lambda tp: -tp[1])         # List.sort is stable
     return rows, pushes, edges
+
+
+# ------------------------------------------------------------------------------------------------
+# The randomised algorithms.  The Java draws from an unseeded ThreadLocalRandom; here the terminal of
+# "walk number j from vertex v" comes from an injected function (the oracle's Philox walk in the tests),
+# and residue maps are visited in ascending vertex id (the oracle's choice; java.util.HashMap order
+# would only permute the additions).  What is replayed is everything around the walks.
+import math
+
+
+def conf_whole(n):
+    """J/Algo_Conf.java:44-52."""
+    return {"delta": 1.0 / float(n), "pfail": 1.0 / float(n)}
+
+
+def conf_topk(n, k):
+    """J/Algo_Conf.java:71-81 -- `node_amount / k` is an int division."""
+    return {"min_delta": 1.0 / float(n), "delta": 1.0 / float(k),
+            "pfail": 1.0 / float(n) / float(n) / math.log(n // k)}
+
+
+def monte_carlo(n, s, eps, walk):
+    """J/Monte_Carlo.java:136-158; walk(v, j) -> terminal of the j-th walk from v."""
+    c = conf_whole(n)
+    omega = 3 * math.log(2 / c["pfail"]) / eps / eps / c["delta"]
+    cnt = {}
+    i = 1
+    while i <= omega:
+        t = walk(s, i - 1)
+        cnt[t] = cnt.get(t, 0) + 1
+        i += 1
+    return {v: float(x) / omega for v, x in cnt.items()}, i - 1
+
+
+def fora(rp, ci, s, alpha, eps, walk, walk_cost, max_rounds=64):
+    """J/Fora_Whole_Graph.java:82-146 with the oracle's deterministic stand-in for the wall-clock balance
+    test of :93 (modelled push cost = pops + edges so far, modelled walk cost = walk_cost*rsum*omega)."""
+    n, m = len(rp) - 1, len(ci)
+    c = conf_whole(n)
+    rsum_local = 1.0
+    rmax_local = eps * math.sqrt(c["delta"] / 3.0 / float(m) / math.log(2.0 / c["pfail"])) / (1.0 - alpha)
+    omega_local = (eps + 2.0) * math.log(2.0 / c["pfail"]) / eps / eps / c["delta"]
+    cost, rounds, pushes, edges = 0.0, 0, 0, 0
+    reserve, residue = {}, {}
+    while cost < walk_cost * rsum_local * omega_local and rounds < max_rounds:
+        reserve, residue, rsum_field, p, e = forward_push(rp, ci, s, alpha, rmax_local)
+        pushes += p
+        edges += e
+        cost += float(p + e)
+        rsum_local = rsum_field * (1 - alpha)                    # :101
+        rmax_local /= 2.0
+        rounds += 1
+    num_random_walk = int(omega_local * rsum_local)              # (long) truncation, value is positive
+    walks = 0
+    for v in sorted(residue):
+        rc = residue[v]
+        if not rc > 0:
+            continue                                             # omega_i == 0: the Java loop body never runs
+        reserve[v] = reserve.get(v, 0.0) + rc * alpha            # :120-125
+        rc *= (1.0 - alpha)
+        omega_i = int(math.ceil(rc / rsum_local * float(num_random_walk)))
+        a_i = rc / rsum_local * float(num_random_walk) / float(omega_i)
+        incr = a_i / float(num_random_walk) * rsum_local
+        for j in range(omega_i):
+            t = walk(v, j)                                       # random_walk_no_zero_hop, :132
+            reserve[t] = reserve.get(t, 0.0) + incr
+        walks += omega_i
+    return reserve, {"pushes": pushes, "edges": edges, "rounds": rounds, "walks": walks,
+                     "rmax_final": rmax_local * 2.0, "rsum": rsum_local}
+
+
+def forward_push_topk(rp, ci, s, alpha, st, q, min_rmax, first, rmax):
+    """J/Forward_Push.java:144-250.  st = {"residue": {}, "reserve": {}, "rsum": x, "q_next": deque}."""
+    deg = lambda v: rp[v + 1] - rp[v]
+    residue, reserve = st["residue"], st["reserve"]
+    d_s = deg(s)
+    if d_s == 0:
+        reserve[s] = 1.0
+        st["rsum"] = 0.0
+        return 0, 0
+    if first:
+        residue[s] = 1.0
+    st["q_next"] = q_next = deque()
+    rsum_local = st["rsum"]
+    in_q, in_next = set(q), set()
+    pushes = edges = 0
+
+    def ratio(x, d):                                             # Java double division: x/0 -> +Inf, 0/0 -> NaN
+        return x / float(d) if d else (float("inf") if x > 0 else float("nan"))
+
+    while q:
+        v = q.popleft()
+        in_q.discard(v)
+        x = residue[v]
+        d = deg(v)
+        if ratio(x, d) >= rmax:                                  # :172
+            residue[v] = 0.0
+            reserve[v] = reserve.get(v, 0.0) + x * alpha
+            rsum_local -= x * alpha
+            pushes += 1
+            if d == 0:                                           # :186-207
+                ns = residue[s] + x * (1 - alpha)
+                residue[s] = ns
+                if ns / float(d_s) >= rmax and s not in in_q:
+                    q.append(s)
+                    in_q.add(s)
+                elif ns / float(d_s) >= min_rmax and s not in in_next:
+                    in_next.add(s)
+                    q_next.append(s)
+                continue
+            avg = ((1.0 - alpha) * x) / float(d)
+            for e in range(rp[v], rp[v + 1]):
+                u = ci[e]
+                nr = residue.get(u, 0.0) + avg
+                residue[u] = nr
+                edges += 1
+                r = ratio(nr, deg(u))
+                if r >= rmax and u not in in_q:
+                    q.append(u)
+                    in_q.add(u)
+                elif r >= min_rmax and u not in in_next:
+                    in_next.add(u)
+                    q_next.append(u)
+        elif ratio(x, d) >= min_rmax and v not in in_next:       # :238
+            in_next.add(v)
+            q_next.append(v)
+    st["rsum"] = rsum_local
+    return pushes, edges
+
+
+def fora_topk(rp, ci, s, alpha, eps, k, walk):
+    """J/Fora_Topk.java:102-184 (reading :136 with its missing ';'); walk(v, j, round) -> terminal."""
+    n, m = len(rp) - 1, len(ci)
+    c = conf_topk(n, k)
+    epsilon = eps * 0.5
+    delta_local, min_delta, pfail = c["delta"], c["min_delta"], c["pfail"]
+    min_rmax = epsilon * math.sqrt(min_delta / 3 / m / math.log(2 / pfail))
+    rsum_local = 1.0
+    st = {"residue": {}, "reserve": {}, "rsum": rsum_local, "q_next": deque()}
+    q = deque([s])
+    first, rnd, pushes, edges, walks = True, 0, 0, 0, 0
+    reserve = {}
+    while delta_local >= min_delta:
+        rmax_local = epsilon * math.sqrt(delta_local / 3.0 / float(m) / math.log(2.0 / pfail))
+        omega_local = (epsilon + 2.0) * math.log(2.0 / pfail) / epsilon / epsilon / delta_local
+        if rp[s + 1] - rp[s] == 0:                               # :128-132
+            reserve = {s: 1.0}
+            rsum_local = 0.0
+            break
+        rmax_local *= math.sqrt(float(m) * rmax_local) * 3.0     # :133
+        p, e = forward_push_topk(rp, ci, s, alpha, st, q, min_rmax, first, rmax_local)
+        pushes += p
+        edges += e
+        first = False
+        rsum_local = st["rsum"]
+        reserve = dict(st["reserve"])                            # getReserveCopy
+        q = deque(st["q_next"])
+        rsum_random_walk = rsum_local * (1.0 - alpha)
+        num_random_walk = int(omega_local * rsum_random_walk)
+        for v in sorted(st["residue"]):
+            rc = st["residue"][v]
+            if not rc > 0:
+                continue
+            omega_i = int(math.ceil(rc * float(num_random_walk)))   # :155, no rsum scaling here
+            a_i = rc * float(num_random_walk) / float(omega_i)
+            incr = a_i / float(num_random_walk)
+            for j in range(omega_i):
+                t = walk(v, j, rnd)                              # random_walk (zero hops allowed), :159
+                reserve[t] = reserve.get(t, 0.0) + incr
+            walks += omega_i
+        rnd += 1
+        vals = list(reserve.values())
+        kth = kth_largest(vals, k)
+        kth = 0.0 if kth is None else kth
+        if kth >= (1 + epsilon) * delta_local or delta_local <= min_delta:
+            break
+        delta_local = max(min_delta, delta_local / 4.0)
+    return reserve, {"pushes": pushes, "edges": edges, "rounds": rnd, "walks": walks, "rsum": rsum_local}
+
+
+def random_walk(rp, ci, start, alpha, next_double, next_int, no_zero_hop=False, restart=None):
+    """J/Monte_Carlo.java:60-97 (random_walk) and :99-133 (random_walk_no_zero_hop) with the two
+    ThreadLocalRandom calls injected: next_double() in [0,1), next_int(bound) in [0,bound).
+    Returns (terminal, moves) -- moves counts successful neighbour picks and dangling restarts."""
+    restart = start if restart is None else restart
+    deg = lambda v: rp[v + 1] - rp[v]
+    if deg(start) == 0:                                          # :70-72 / :108-110
+        return start, 0
+    cur, moves = start, 0
+    if no_zero_hop:                                              # :112-114, a mandatory first move
+        cur = ci[rp[start] + next_int(deg(start))]
+        moves = 1
+    while True:
+        if next_double() < alpha:                                # :76
+            break
+        d = deg(cur)
+        if d > 0:
+            cur = ci[rp[cur] + next_int(d)]                      # :84-85
+        else:
+            cur = restart                                        # :87-90
+        moves += 1
+    return cur, moves

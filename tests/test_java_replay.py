@@ -99,3 +99,92 @@ def test_kth_largest_matches(O):
         assert O.kth_ppr(vals, k) == J.kth_largest(vals.tolist(), k)
     assert O.kth_ppr(vals, 51) is None and J.kth_largest(vals.tolist(), 51) is None
     assert O.kth_ppr(vals, -1) is None and J.kth_largest(vals.tolist(), -1) is None
+
+
+SEED, EPS, K = 7, 0.5, 10
+
+
+def test_fora_around_the_walks(O, g, got):
+    """J/Fora_Whole_Graph.java:82-146: balance rounds, walk counts and per-walk increments, with the
+    oracle's Philox walk plugged into the replay -- the whole estimate must come out the same doubles."""
+    rp, ci = got[0].tolist(), got[1].tolist()
+    n = len(rp) - 1
+    deg = np.diff(got[0])
+    for s in (0, 63, int(np.argmax(deg)), int(np.flatnonzero(deg == 0)[0])):
+        walk = lambda v, j: O.walk(g, v, v, j, SEED, 0, ALPHA, True)[0]
+        for cost in (32.0, 6.0):
+            mine, st = J.fora(rp, ci, s, ALPHA, EPS, walk, cost)
+            theirs, ost = O.a_fora(g, s, ALPHA, EPS, SEED, walk_cost=cost)
+            assert np.array_equal(dense(mine, n), theirs), (s, cost)
+            assert all(st[k] == ost[k] for k in ("pushes", "edges", "rounds", "walks", "rsum")), (s, cost, st, ost)
+            assert st["rmax_final"] == ost["rmax_final"]
+
+
+def test_fora_topk_around_the_walks(O, g, got):
+    """J/Fora_Topk.java:102-184 with J/Forward_Push.java:144-250 underneath."""
+    rp, ci = got[0].tolist(), got[1].tolist()
+    n = len(rp) - 1
+    deg = np.diff(got[0])
+    for s in (0, 63, int(np.argmax(deg)), int(np.flatnonzero(deg == 0)[0])):
+        for k in (10, 3):
+            walk = lambda v, j, rnd: O.walk(g, v, v, j, SEED, rnd, ALPHA, False)[0]
+            mine, st = J.fora_topk(rp, ci, s, ALPHA, EPS, k, walk)
+            theirs, ost = O.a_fora_topk(g, s, ALPHA, EPS, k, SEED)
+            assert np.array_equal(dense(mine, n), theirs), (s, k)
+            assert all(st[x] == ost[x] for x in ("pushes", "edges", "rounds", "walks")), (s, k, st, ost)
+
+
+def test_monte_carlo_count_and_scaling(O, g, got):
+    n = len(got[0]) - 1
+    for s in (0, 63):
+        walk = lambda v, j: O.walk(g, v, v, j, SEED, 0, ALPHA, False)[0]
+        mine, walks = J.monte_carlo(n, s, EPS, walk)                # J/Monte_Carlo.java:136-158
+        theirs, st = O.a_monte_carlo(g, s, ALPHA, EPS, SEED)
+        assert walks == st["walks"] and np.array_equal(dense(mine, n), theirs)
+
+
+def test_conf_replay(O):
+    for n, k in ((107, 10), (1 << 20, 500), (4847571, 500)):
+        c, w = O.conf(n, k), J.conf_topk(n, k)
+        assert (c["delta"], c["min_delta"], c["pfail"]) == (w["delta"], w["min_delta"], w["pfail"])
+        c, w = O.conf(n), J.conf_whole(n)
+        assert (c["delta"], c["pfail"]) == (w["delta"], w["pfail"])
+
+
+def test_walk_replay_with_philox_draws(O, g, got):
+    """The Java walk loop (java_replay.random_walk) fed with the draws the SPEC assigns to each step
+    (oracle/ppr_oracle.cpp header): one Philox block per step, counter (start, j lo, j hi, step);
+    nextDouble = the 53-bit fraction of (x0, x1), nextInt(d) = mulhi((x2<<32)|x3, d) of the same block;
+    the mandatory first move of a no-zero-hop walk takes a block of its own."""
+    rp, ci = got[0].tolist(), got[1].tolist()
+    deg = np.diff(got[0])
+
+    def replay(start, j, seed, tag, nzh):
+        k = (seed + tag * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+        st = {"step": 0, "blk": None}
+
+        def block():
+            x = O.philox([start, j & 0xFFFFFFFF, j >> 32, st["step"]], [k & 0xFFFFFFFF, k >> 32])
+            st["step"] += 1
+            return [int(v) for v in x]
+
+        def next_double():
+            st["blk"] = x = block()
+            return ((x[0] << 21) | (x[1] >> 11)) / 2.0 ** 53
+
+        def next_int(bound):
+            x = st["blk"] if st["blk"] is not None else block()
+            st["blk"] = None
+            return (((x[2] << 32) | x[3]) * bound) >> 64
+
+        return J.random_walk(rp, ci, start, ALPHA, next_double, next_int, no_zero_hop=nzh)
+
+    dang = int(np.flatnonzero(deg == 0)[0])
+    for start in (63, 0, int(np.argmax(deg)), dang):
+        for nzh in (False, True):
+            for j in list(range(300)) + [2 ** 32 + 5]:
+                assert replay(start, j, SEED, 0, nzh) == O.walk(g, start, start, j, SEED, 0, ALPHA, nzh), (start, j, nzh)
+    assert replay(63, 9, SEED, 3, True) == O.walk(g, 63, 63, 9, SEED, 3, ALPHA, True)
+    # walks that pass through dangling vertices were among those (36 of GOT's 107 vertices are dangling)
+    draws = iter([0.9, 0.9, 0.9, 0.1])
+    assert J.random_walk(rp, ci, 63, ALPHA, lambda: next(draws), lambda b: 0)[1] == 3
