@@ -12,6 +12,7 @@ that iterates only the non-zero entries, i.e. the entries the Java HashMap would
 import math
 import os
 import shutil
+import time
 from collections.abc import Mapping
 
 import numpy as np
@@ -53,10 +54,38 @@ class PPRVector(Mapping):
 
 
 class Algo_Util:
-    """J/Algo_Util.java: kth_ppr (k-th largest; None when k is out of range)."""
+    """J/Algo_Util.java: getNodeName, kth_ppr (k-th largest; None when k is out of range)."""
 
-    def __init__(self, node_property="name"):
+    def __init__(self, node_property="name", graphDb=None):
         self.node_property = node_property
+        self.graphDb = graphDb
+
+    def getNodeName(self, nodeId, graphDb=None):
+        """J/Algo_Util.java:20-30.  Neo4j is not here: `graphDb` stands for the node-property column, i.e. a
+        sequence or mapping id -> name (what `graphio.load_got` returns); without one the id itself is printed."""
+        db = self.graphDb if graphDb is None else graphDb
+        try:
+            return str(db[int(nodeId)])
+        except (TypeError, KeyError, IndexError):
+            return str(int(nodeId))
+
+    def _print_rows(self, header, ids, vals, limit=None, extra=None):
+        """The print loops of the reference classes (e.g. J/Forward_Push.java:268-281, :366-391): entries sorted
+        by value descending (List.sort is stable; ties keep map order = ascending id here), '@name<TAB>value'."""
+        ids, vals = np.asarray(ids), np.asarray(vals, dtype=np.float64)
+        order = np.argsort(-vals, kind="stable")
+        if limit is not None:
+            order = order[:max(int(limit), 0)]
+        print(header)
+        for i in order:
+            line = "@" + self.getNodeName(ids[i]) + "\t" + _java_double(vals[i])
+            if extra is not None:
+                line += "\t" + _java_double(extra[int(ids[i])])
+            print(line)
+
+    def _print_dense(self, header, dense, limit=None, extra=None):
+        ids = np.flatnonzero(np.asarray(dense) > 0)
+        self._print_rows(header, ids, np.asarray(dense)[ids], limit, extra)
 
     def kth_ppr(self, pprs, k, adjM=None):
         pprs = np.asarray(pprs, dtype=np.float64)
@@ -80,7 +109,7 @@ class Forward_Push(Algo_Util):
     """J/Forward_Push.java -- Whole_Graph_Util_Interface, Topk_Util_Interface, Preprocessing_Interface."""
 
     def __init__(self, alpha, rsum, node_amount, graphDb, adjM, node_property="name", dir_db="db"):
-        super().__init__(node_property)
+        super().__init__(node_property, graphDb)
         self.alpha, self.rsum, self.node_amount, self.adjM, self.dir_db = alpha, rsum, node_amount, adjM, dir_db
         self.reserve = self.residue = None
         self.topk_nodeIds = None
@@ -103,6 +132,10 @@ class Forward_Push(Algo_Util):
     def getWholeGraphPPR(self):
         return PPRVector(self.reserve)
 
+    def printWholeGraphResult(self):
+        """J/Forward_Push.java:268-281: reserve and residue of every node that holds reserve."""
+        self._print_dense("Forward-Push Reserve(pi) & Residue(r):", self.reserve, extra=self.residue)
+
     def computeTopKPPR(self, nodeId_start, k, rmax):
         self.computeWholeGraphPPR(nodeId_start, rmax)
 
@@ -110,6 +143,11 @@ class Forward_Push(Algo_Util):
         if self.topk_nodeIds is None:
             self.topk_nodeIds, _ = _topk_from_dense(self.adjM, self.reserve, k)
         return self.topk_nodeIds
+
+    def printTopKResult(self, k):
+        """J/Forward_Push.java:366-391."""
+        ids = self.getTopKNodeIds(k)
+        self._print_rows("\nForward-Push-Top%d PPR:" % k, ids, self.reserve[ids], limit=k)
 
     # Preprocessing_Interface (J/Forward_Push.java:289-362): one text file per source, "id\tvalue\n"
     def preprocessing(self, dummy, rmax):
@@ -133,7 +171,7 @@ class Monte_Carlo(Algo_Util):
     """J/Monte_Carlo.java."""
 
     def __init__(self, alpha, node_amount, graphDb, pfail, delta, adjM, node_property="name", dir_db="db", seed=1):
-        super().__init__(node_property)
+        super().__init__(node_property, graphDb)
         self.alpha, self.node_amount, self.pfail, self.delta, self.adjM, self.dir_db = alpha, node_amount, pfail, delta, adjM, dir_db
         self.seed = seed
         self.ppr = None
@@ -165,6 +203,10 @@ class Monte_Carlo(Algo_Util):
     def getWholeGraphPPR(self):
         return PPRVector(self.ppr)
 
+    def printWholeGraphResult(self):
+        """J/Monte_Carlo.java:160-173."""
+        self._print_dense("Monte-Carlo PPR:", self.ppr)
+
     def computeTopKPPR(self, nodeId_start, k, epsilon):
         self.computeWholeGraphPPR(nodeId_start, epsilon)
 
@@ -172,6 +214,11 @@ class Monte_Carlo(Algo_Util):
         if self.topk_nodeIds is None:
             self.topk_nodeIds, _ = _topk_from_dense(self.adjM, self.ppr, k)
         return self.topk_nodeIds
+
+    def printTopKResult(self, k):
+        """J/Monte_Carlo.java:276-301."""
+        ids = self.getTopKNodeIds(k)
+        self._print_rows("\nMonte-Carlo-Top%d PPR:" % k, ids, self.ppr[ids], limit=k)
 
     def preprocessing(self, dummy, epsilon):
         self.preprocessing_dirName = os.path.join(self.preprocessing_dirName, repr(float(epsilon)))
@@ -195,7 +242,7 @@ class Fora_Whole_Graph(Algo_Util):
 
     def __init__(self, alpha, rsum, pfail, delta, node_amount, rel_amount, graphDb, adjM, node_property="name",
                  dir_db="db", seed=1, flags=N.RESTART_AT_WALK_START):
-        super().__init__(node_property)
+        super().__init__(node_property, graphDb)
         self.alpha, self.rsum, self.pfail, self.delta = alpha, rsum, pfail, delta
         self.node_amount, self.rel_amount, self.adjM, self.dir_db = node_amount, rel_amount, adjM, dir_db
         self.seed, self.flags = seed, flags
@@ -210,6 +257,10 @@ class Fora_Whole_Graph(Algo_Util):
 
     def getWholeGraphPPR(self):
         return PPRVector(self.reserve)
+
+    def printWholeGraphResult(self):
+        """J/Fora_Whole_Graph.java:55-68."""
+        self._print_dense("Fora-Whole-Graph PPR:", self.reserve)
 
     def preprocessing(self, dummy, epsilon):
         self.preprocessing_dirName = os.path.join(self.preprocessing_dirName, repr(float(epsilon)))
@@ -233,7 +284,7 @@ class Fora_Topk(Algo_Util):
 
     def __init__(self, alpha, rsum, pfail, delta, node_amount, rel_amount, graphDb, min_delta, k, adjM,
                  node_property="name", dir_db="db", seed=1, flags=N.RESTART_AT_WALK_START):
-        super().__init__(node_property)
+        super().__init__(node_property, graphDb)
         self.alpha, self.rsum, self.pfail, self.delta, self.min_delta, self.k = alpha, rsum, pfail, delta, min_delta, k
         self.node_amount, self.rel_amount, self.adjM, self.dir_db = node_amount, rel_amount, adjM, dir_db
         self.seed, self.flags = seed, flags
@@ -250,6 +301,10 @@ class Fora_Topk(Algo_Util):
     def getTopKNodeIds(self, dummy=None):
         return self.topk_nodeIds
 
+    def printTopKResult(self, dummy=None):
+        """J/Fora_Topk.java:60-79: at most k lines although ties at the cut may have kept more ids."""
+        self._print_rows("\nFora-Top%d PPR:" % self.k, self.topk_nodeIds, self.topk_vals, limit=self.k)
+
 
 class Backward_Search:
     """J/Backward_Search.java."""
@@ -258,9 +313,16 @@ class Backward_Search:
         self.alpha, self.rmax, self.node_amount, self.adjM = alpha, rmax, node_amount, adjM
         self.reserve = None
         self.stats = None
+        self.duration = 0
 
     def backward_search_whole_graph(self, nodeId_target):
+        t0 = time.perf_counter_ns()
         self.reserve, self.stats = self.adjM.backward_search(int(nodeId_target), self.alpha, float(self.rmax))
+        self.duration += time.perf_counter_ns() - t0
+
+    def getDuration(self):
+        """J/Backward_Search.java:104-106: nanoseconds spent in backward searches so far."""
+        return self.duration
 
     def getReserve(self):
         return PPRVector(self.reserve)
@@ -270,7 +332,7 @@ class Base_Whole_Graph(Algo_Util):
     """J/Base_Whole_Graph.java -- All-Pair-Backward-Search ("BASE")."""
 
     def __init__(self, alpha, node_amount, graphDb, adjM, node_property="name", dir_db="db", write_files=True):
-        super().__init__(node_property)
+        super().__init__(node_property, graphDb)
         self.alpha, self.node_amount, self.adjM, self.dir_db = alpha, node_amount, adjM, dir_db
         self.write_files = write_files
         self.preprocessing_dirName = os.path.join("BASE_ppr_results", dir_db)
@@ -309,6 +371,12 @@ class Base_Whole_Graph(Algo_Util):
     def getWholeGraphPPR(self):
         return self.ppr_src
 
+    def printWholeGraphResult(self):
+        """J/Base_Whole_Graph.java:188-193: the stored row in stored order, not re-sorted."""
+        print("\nBase-Whole-Graph PPR:")
+        for t, x in self.ppr_src.items():
+            print("@" + self.getNodeName(t) + "\t" + _java_double(x))
+
     def computeTopKPPR(self, nodeId_start, k, dummy=None):
         self.computeWholeGraphPPR(nodeId_start)
 
@@ -316,6 +384,10 @@ class Base_Whole_Graph(Algo_Util):
         if self.topk_nodeIds is None:  # file rows are already sorted when preprocessing ran with k >= 0
             self.topk_nodeIds = np.fromiter(self.ppr_src.keys(), dtype=np.int32, count=len(self.ppr_src))
         return self.topk_nodeIds
+
+    def printTopKResult(self, k):
+        """J/Base_Whole_Graph.java:219-236."""
+        self._print_rows("\nBASE-Top%d PPR:" % k, list(self.ppr_src.keys()), list(self.ppr_src.values()), limit=k)
 
     def getPrepSize(self):
         return _dir_size(self.preprocessing_dirName)
@@ -328,7 +400,7 @@ class Power_Method(Algo_Util):
     """J/Power_Method.java -- the ground truth of the harness (100 synchronous iterations)."""
 
     def __init__(self, graphDb, alpha, adjM, node_property="name", dir_db="db"):
-        super().__init__(node_property)
+        super().__init__(node_property, graphDb)
         self.alpha, self.adjM = alpha, adjM
         self.reserve = None
         self.topk_res = None
@@ -351,6 +423,14 @@ class Power_Method(Algo_Util):
 
     def getTopKNodeIds(self, k):
         return self.topk_nodeIds
+
+    def printWholeGraphResult(self):
+        """J/Power_Method.java:103-116."""
+        self._print_dense("Exact-PPR:", self.reserve)
+
+    def printTopKResult(self, k):
+        """J/Power_Method.java:160-184."""
+        self._print_rows("\nExact-Top%d PPR:" % k, self.topk_nodeIds, self.reserve[self.topk_nodeIds], limit=k)
 
 
 class Algo_Conf:

@@ -252,6 +252,7 @@ class PPR(Gen_Util):
         else:
             raise FileNotFoundError("neither a Neo4j store nor *_Nodes.csv / *_Rels.csv under %s" % self.db_path)
         self.adjM = N.Graph(self.ctx, row_ptr, col_idx)
+        self.graphDb = self.names          # all the algorithm classes ask of graphDb is getNodeName (J/Algo_Util.java:20-30)
         print("\nFinish graph loading in %d(ms)" % ((time.perf_counter_ns() - t0) // 1000000))
 
     def set_configuration(self, alpha, epsilon, node_property, label_type, rel_type):
@@ -291,6 +292,9 @@ def main(argv=None):
     except Exception as e:  # J/PPR.java:196-199
         print("Algo performance batch test failed!")
         raise e
+
+
+PPR.main = staticmethod(main)
 
 
 if __name__ == "__main__":

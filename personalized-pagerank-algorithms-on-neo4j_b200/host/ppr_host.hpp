@@ -112,6 +112,13 @@ struct Algo_Util {
         vals.assign(v.begin(), v.begin() + cnt);
         if (kth) *kth = kk;
     }
+    // J/Algo_Util.java:32-50: the k-th largest value; false (Java: null) when k is outside 1..size
+    static bool kth_ppr(Graph& G, const std::vector<double>& pprs, int k, double* out) {
+        if (k < 1 || (size_t)k > pprs.size()) return false;
+        std::vector<int64_t> ids; std::vector<double> vals;
+        topk(G, pprs, k, ids, vals, out);
+        return true;
+    }
 };
 
 // Preprocessing_Interface (J/Preprocessing_Interface.java) for the single-source algorithms: one text file per source,
@@ -316,7 +323,9 @@ struct Base_Whole_Graph : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Inter
     const std::vector<double>& dense() override { return ppr_dense; }
     void computeTopKPPR(int64_t s, int, double) override { computeWholeGraphPPR(s, 0); }
     const std::vector<int64_t>& getTopKNodeIds(int) override { return topk_nodeIds; }   // rows are sorted when preprocessing ran with k >= 0
+    void readPreprocessedPPR(int64_t s) { computeWholeGraphPPR(s, 0); }   // J/Base_Whole_Graph.java:200-204
     int64_t getPrepSize() const { return prep_bytes; }
+    void deletePrepDir() { src_ptr.clear(); tgt.clear(); val.clear(); prep_bytes = 0; }   // the index lives in memory here (:243-251 clears the directory)
 };
 
 // J/Algo_Conf.java
