@@ -45,6 +45,42 @@ def test_algorithm_classes_like_the_harness_uses_them(pkg, G, O, got):
     assert np.array_equal(bs.reserve, O.b_backward_search(og, 5, ALPHA, 1e-3)[0] * O.FX_INV)
 
 
+def test_print_methods_on_device_results(pkg, G, O, got, capsys):
+    """printWholeGraphResult / printTopKResult of the reference classes (J/Forward_Push.java:268-281, :366-391,
+    J/Fora_Topk.java:60-79, J/Power_Method.java:103-116) over results that came from the device."""
+    names = got[2]
+    og = O.OGraph(got[0], got[1])
+    ac = pkg.Algo_Conf(ALPHA, "name")
+    s = names.index("Tyrion")
+    fp = ac.set_conf_fwdpush(107, 352, names, G, "got.db")
+    fp.computeTopKPPR(s, 5, 1e-6)
+    capsys.readouterr()
+    fp.printTopKResult(5)
+    lines = capsys.readouterr().out.splitlines()
+    res, _, _ = O.b_forward_push(og, s, ALPHA, 1e-6)
+    top = np.argsort(-(res * O.FX_INV), kind="stable")[:5]
+    assert lines[:2] == ["", "Forward-Push-Top5 PPR:"] and len(lines) == 7
+    assert lines[2:] == ["@%s\t%s" % (names[v], pkg.algo._java_double(res[v] * O.FX_INV)) for v in top]
+    assert lines[2].startswith("@Tyrion\t0.39")
+    fp.printWholeGraphResult()
+    lines = capsys.readouterr().out.splitlines()
+    assert lines[0] == "Forward-Push Reserve(pi) & Residue(r):" and len(lines) == 1 + np.count_nonzero(res)
+    assert all(len(ln.split("\t")) == 3 and ln[0] == "@" for ln in lines[1:])
+    tk = ac.set_conf_fora_topk(107, 352, 10, names, G, "got.db")
+    tk.computeTopKPPR(s, 10, 0.5)
+    tk.printTopKResult(10)
+    lines = capsys.readouterr().out.splitlines()
+    assert lines[1] == "Fora-Top10 PPR:" and lines[2].startswith("@Tyrion\t") and 3 <= len(lines) <= 12
+    vals = [float(ln.split("\t")[1]) for ln in lines[2:]]
+    assert vals == sorted(vals, reverse=True)
+    pm = ac.set_conf_power_method(names, G, "got.db")
+    pm.computeTopKPPR(s, 3, None)
+    pm.printTopKResult(3)
+    pm.printWholeGraphResult()
+    lines = capsys.readouterr().out.splitlines()
+    assert lines[1] == "Exact-Top3 PPR:" and lines[2].startswith("@Tyrion\t0.3916") and lines[5] == "Exact-PPR:"
+
+
 def test_base_whole_graph_store(pkg, G, O, got, tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     og = O.OGraph(got[0], got[1])
