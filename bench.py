@@ -116,6 +116,9 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+L2_RED64_GOPS = 180.5   # measured RED.64 ceiling out of the L2 (profiles/r01_microbench_atomics.txt)
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -459,6 +462,7 @@ def main():
     walk_gbs = walk_bytes / (acc["ms_walk"] / 1e3) / 1e9 if acc["ms_walk"] > 0 else 0.0
     traffic, traffic_src = ncu_traffic(args.scale)
     nd = max(acc["nd"], 1)
+    push_edges_s = acc["edges"] / (acc["ms_push"] / 1e3) if acc["ms_push"] > 0 else 0.0
 
     line = {
         "metric": "FORA SSPPR queries/s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K,
@@ -478,7 +482,14 @@ def main():
                                      + "algorithmic bytes per non-dangling launch = %.4g" % (push_bytes / nd),
                      "peak_source": peak_src, "algorithmic_bytes": "48*V_p + 24*E_p", "V_p": acc["pushes"], "E_p": acc["edges"],
                      "launches": nq_rank, "launches_with_work": acc["nd"], "avg_launch_ms": acc["ms_push"] / max(nq_rank, 1),
-                     "avg_launch_ms_with_work": acc["ms_push"] / nd, "share_of_step": acc["ms_push"] / m["ms"]},
+                     "avg_launch_ms_with_work": acc["ms_push"] / nd, "share_of_step": acc["ms_push"] / m["ms"],
+                     # what actually binds the kernel once the residue array sits in the L2: one 64-bit reduction per relaxed edge
+                     "binding_unit": {"bound": "l2_red64", "achieved": push_edges_s / 1e9, "peak": L2_RED64_GOPS, "unit": "Gop/s",
+                                      "frac": push_edges_s / 1e9 / L2_RED64_GOPS,
+                                      "peak_source": "profiles/r01_microbench_atomics.txt (scripts/microbench/atomics.cu: RED.64 to uniformly random "
+                                                     "addresses of an 8-32 MB footprint, 180.4-181.6 Gop/s on this pool's B200)",
+                                      "note": "whole kernel incl. sweeps and small iterations; its dense scatter phase alone runs at 195 G edges/s "
+                                              "(profiles/r02_push_timeline_scale22.txt; hub targets are pre-combined in shared memory)"}},
         "kernels": {"k_push_query": {"ms": acc["ms_push"], "edges_per_s": acc["edges"] / (acc["ms_push"] / 1e3) if acc["ms_push"] else 0,
                                      "iters_per_query": acc["iters"] / nd, "rounds_per_query": acc["rounds"] / nd},
                     "k_walk": {"ms": acc["ms_walk"], "walks_per_s": acc["walks"] / (acc["ms_walk"] / 1e3) if acc["ms_walk"] else 0,
