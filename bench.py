@@ -144,7 +144,8 @@ def workload_config(args):
             "alpha": ALPHA, "eps": args.eps, "delta": "1/n", "p_f": "1/n",
             "sources": "uniform over all n vertices (J/Gen_Util.java:99-107), seed %d; sources without out-edges are answered {s: 1}" % SRC_SEED,
             "walk_cost": args.walk_cost,
-            "l2": "inputs exceed the L2 (edge arrays 2 x %d MB per graph copy vs 126 MB); the GPU arm also writes a 256 MiB buffer before every step" % (4 * n * args.edge_factor >> 20)}
+            "l2": ("inputs exceed the L2" if 8 * n * args.edge_factor > (126 << 20) else "inputs fit the L2") +
+                  " (edge arrays 2 x %.1f MB per graph copy vs 126 MB); the GPU arm also writes a 256 MiB buffer before every step" % (4.0 * n * args.edge_factor / (1 << 20))}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)

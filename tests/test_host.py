@@ -131,3 +131,22 @@ def test_neo4j_store_reader_matches_csv(pkg):
     rp, ci, ids = pkg.graphio.load_neo4j_store(store)
     rp2, ci2, names = pkg.graphio.load_got()
     assert np.array_equal(ids, np.arange(107)) and np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
+
+
+def test_bench_reference_arm_contract(pkg):
+    """`bench.py --impl reference` (the oracle on the host cores) prints the contract line without a GPU; small scale here."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--scale", "12", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "FORA SSPPR queries/s" and line["unit"] == "queries/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 1
+    assert line["value"] > 0 and line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert line["config"]["workload"].startswith("R-MAT scale-12") and line["config"]["l2"].startswith("inputs fit the L2")
+    assert line["oracle_pinned"] is False
