@@ -112,6 +112,8 @@ __device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3,
 // randomly accessed per-vertex tables (vertex records, residues, degrees) out of the 126 MB L2.
 __device__ __forceinline__ u64 l2_policy_evict_first() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ u64 l2_policy_evict_last() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ u64 l2_policy_keep_fraction_25() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.25;" : "=l"(p)); return p; }
+__device__ __forceinline__ u64 l2_policy_keep_fraction_15() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.15;" : "=l"(p)); return p; }
 __device__ __forceinline__ u32 ld_hint_u32(const void* p, u64 pol) {
     u32 v; asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
 }

@@ -87,6 +87,8 @@ __device__ __forceinline__ u64 mul_div_u64(u64 a, u64 b, u64 c) {  // floor(a*b/
 // HINT == 2: as 1, and the vertex record is read as two adjacent 32-bit row pointers from a table half the size of out_vtx
 // (16 MB instead of 32 MB at R-MAT scale 22): the randomly accessed per-vertex data competes with the count / reserve vector and the
 // streamed edge array for the L2, and every record miss costs a 64-byte DRAM fetch.
+// HINT == 3 / 4 / 5 (experiments): as 2, with the neighbour sectors at normal priority / with an address-hashed 25 % / 15 % of them
+// evict-last and the rest evict-first, so that a fixed part of the edge array stays in the L2 next to the row pointers.
 template <int HINT, int NW>
 __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_walk(WalkArgs A) {
     __shared__ u64 win[WALK_THREADS / 32][34];
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_walk(WalkArg
         }
         scur = a;
     }
-    const u64 pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    const u64 pol_keep = l2_policy_evict_last();
+    const u64 pol_stream = HINT == 4 ? l2_policy_keep_fraction_25() : HINT == 5 ? l2_policy_keep_fraction_15() : l2_policy_evict_first();
     u64 wnext = wl;
     // per-slot walk state (arrays are fully unrolled into registers)
     u32 w_start[NW], w_cur[NW], w_step[NW];
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_walk(WalkArg
         for (int k = 0; k < NW; k++) {
             rb[k] = 0; rd[k] = 0;
             if (go[k]) {
-                if (HINT == 2) {
+                if (HINT >= 2) {
                     const u32 b = ld_hint_u32(&A.row32[w_cur[k]], pol_keep), e = ld_hint_u32(&A.row32[w_cur[k] + 1], pol_keep);
                     rb[k] = b; rd[k] = e - b;
                 } else {
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_walk(WalkArg
             nb[k] = A.restart_at_source ? (u32)A.src : w_start[k];
             if (go[k] && d) {
                 const i32* p = &A.col_idx[rb[k] + mulhi64(rnd[k], (u64)d)];
-                nb[k] = HINT ? ld_hint_u32(p, pol_stream) : (u32)__ldg(p);
+                nb[k] = (HINT && HINT != 3) ? ld_hint_u32(p, pol_stream) : (u32)__ldg(p);
             }
         }
         // stage 4: moves and terminals
