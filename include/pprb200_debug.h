@@ -19,9 +19,10 @@ int32_t ppr_timer_elapsed_ms(ppr_ctx* ctx, int32_t slot_a, int32_t slot_b, float
 int32_t ppr_flush_l2(ppr_ctx* ctx);
 
 
-/* Walk kernel variant: -1 automatic (beyond the L2: variant 4), 0 plain loads, 1 L2 eviction-priority hints, 2 hints + the vertex
+/* Walk kernel variant: -1 automatic (beyond the L2: variant 2), 0 plain loads, 1 L2 eviction-priority hints, 2 hints + the vertex
  * record read from the half-size table of 32-bit row pointers (falls back to 1 when m >= 2^32); 3 / 4 / 5 = as 2 with the neighbour
- * sectors at normal priority / an address-hashed 25 % / 15 % of them evict-last and the rest evict-first.
+ * sectors at normal priority / an address-hashed 25 % / 15 % of them evict-last and the rest evict-first (experiments: +2.5 % on
+ * FORA's 1.4 ms walk launches at R-MAT scale 22, -23 % on the 100 ms Monte-Carlo launch, so not the default).
  * Results are identical; the parity tests force each variant on graphs of any size. */
 int32_t ppr_set_walk_variant(ppr_ctx* ctx, int32_t hint);
 

@@ -695,7 +695,7 @@ static cudaError_t launch_walk(ppr_ctx* ctx, ppr_graph* g, Workspace& w, u64* ta
     W.src = src; W.restart_at_source = restart_at_source; W.no_zero_hop = no_zero_hop;
     W.row32 = g->d.row32;
     // graph beyond the L2: eviction hints, and the half-size 32-bit row pointers as the vertex table when they exist
-    int variant = ctx->walk_hint >= 0 ? ctx->walk_hint : (4.0 * (double)g->d.m + 8.0 * (double)g->d.n > 96.0 * 1024 * 1024 ? 4 : 0);
+    int variant = ctx->walk_hint >= 0 ? ctx->walk_hint : (4.0 * (double)g->d.m + 8.0 * (double)g->d.n > 96.0 * 1024 * 1024 ? 2 : 0);
     if (variant >= 2 && !g->d.row32) variant = 1;
     if (variant == 3) k_walk<3, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);
     else if (variant == 4) k_walk<4, WALK_PER_LANE><<<extra_of(g)->walk_blocks, WALK_THREADS, 0, st ? st : ctx->stream>>>(W);

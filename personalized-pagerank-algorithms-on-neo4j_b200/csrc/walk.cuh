@@ -89,6 +89,8 @@ __device__ __forceinline__ u64 mul_div_u64(u64 a, u64 b, u64 c) {  // floor(a*b/
 // streamed edge array for the L2, and every record miss costs a 64-byte DRAM fetch.
 // HINT == 3 / 4 / 5 (experiments): as 2, with the neighbour sectors at normal priority / with an address-hashed 25 % / 15 % of them
 // evict-last and the rest evict-first, so that a fixed part of the edge array stays in the L2 next to the row pointers.
+// Measured at R-MAT scale 22 (profiles/r02_push_variants.txt, run r2x): FORA's short walk launches gain 2.5 % with 4 or 5, but the long
+// Monte-Carlo launch loses 23 % (1.06e10 -> 8.1e9 walks/s): kept sectors + row pointers + the count vector oversubscribe the L2.  Default stays 2.
 template <int HINT, int NW>
 __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_walk(WalkArgs A) {
     __shared__ u64 win[WALK_THREADS / 32][34];

@@ -55,7 +55,7 @@ def test_walk_kernel_with_l2_hints(pkg, ctx, O, rmat16):
     """k_walk<true, 2> (eviction-priority hints) is what every graph beyond the L2 runs.  Forced on R-MAT 2^16 ..."""
     g, og = pkg.Graph(ctx, *rmat16), O.OGraph(*rmat16)
     try:
-        for variant in (4, 2, 1, 0, 3, 5):   # 4 = what graphs beyond the L2 run (32-bit row pointers, a quarter of the edge sectors kept), 2 = hints + row pointers, 1 = hints, 0 = plain
+        for variant in (2, 1, 0, 3, 4, 5):   # 2 = hints + 32-bit row pointers (what graphs beyond the L2 run), 1 = hints, 0 = plain, 3-5 = edge-sector retention experiments
             ctx.set_walk_variant(variant)
             for s in _nondangling(rmat16[0], 2):
                 _check_fora(g, og, O, s, 6.0)
