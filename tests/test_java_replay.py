@@ -63,7 +63,7 @@ def test_backward_search_and_all_pair_index_bitwise(O, g, got):
     for v in range(n):
         row = rows.get(v, [])
         assert [p for _, p in row] == val[ptr[v]:ptr[v + 1]].tolist()
-        assert sorted(t for t, _ in row) == sorted(tgt[ptr[v]:ptr[v + 1]].tolist())
+        assert [t for t, _ in row] == tgt[ptr[v]:ptr[v + 1]].tolist()                # List.sort is stable: ties stay in target order
     # single targets, including one without in-edges (J/Backward_Search.java:46-49)
     indeg = np.bincount(got[1], minlength=n)
     outdeg = np.diff(got[0]).tolist()
@@ -188,3 +188,53 @@ def test_walk_replay_with_philox_draws(O, g, got):
     # walks that pass through dangling vertices were among those (36 of GOT's 107 vertices are dangling)
     draws = iter([0.9, 0.9, 0.9, 0.1])
     assert J.random_walk(rp, ci, 63, ALPHA, lambda: next(draws), lambda b: 0)[1] == 3
+
+
+def _random_digraph(rng, n, m, self_loops=True, multi=True):
+    src = rng.integers(0, n, m)
+    dst = rng.integers(0, n, m)
+    if not self_loops:
+        keep = src != dst
+        src, dst = src[keep], dst[keep]
+    if not multi:
+        pairs = np.unique(np.stack([src, dst], 1), axis=0)
+        src, dst = pairs[:, 0], pairs[:, 1]
+    order = np.argsort(src, kind="stable")
+    src, dst = src[order], dst[order]
+    rp = np.zeros(n + 1, np.int64)
+    np.add.at(rp, src + 1, 1)
+    return np.cumsum(rp), dst.astype(np.int32)
+
+
+def test_replay_on_random_small_digraphs(O):
+    """Self-loops, parallel edges, dangling and isolated vertices, sources without out-edges, targets without in-edges:
+    the two restatements must agree bit for bit on all of them (forward push, backward search, all-pair index, FORA)."""
+    rng = np.random.default_rng(20240607)
+    for trial in range(24):
+        n = int(rng.integers(2, 40))
+        m = int(rng.integers(1, 5 * n))
+        rp, ci = _random_digraph(rng, n, m, self_loops=trial % 2 == 0, multi=trial % 3 != 0)
+        if ci.shape[0] == 0:
+            continue
+        g = O.OGraph(rp, ci)
+        rpl, cil = rp.tolist(), ci.tolist()
+        for s in rng.integers(0, n, 3).tolist():
+            rmax = float(10.0 ** -rng.integers(2, 8))
+            res, r, rsum, pushes, edges = J.forward_push(rpl, cil, s, ALPHA, rmax)
+            ores, orr, orsum, st = O.a_forward_push(g, s, ALPHA, rmax)
+            assert np.array_equal(dense(res, n), ores) and np.array_equal(dense(r, n), orr), (trial, s, rmax)
+            assert (pushes, edges, rsum) == (st["pushes"], st["edges"], orsum), (trial, s, rmax)
+            walk = lambda v, j: O.walk(g, v, v, j, SEED, 0, ALPHA, True)[0]
+            mine, fst = J.fora(rpl, cil, s, ALPHA, EPS, walk, 32.0)
+            theirs, ost = O.a_fora(g, s, ALPHA, EPS, SEED)
+            assert np.array_equal(dense(mine, n), theirs), (trial, s)
+            assert (fst["rounds"], fst["walks"]) == (ost["rounds"], ost["walks"])
+        thr = float(10.0 ** -rng.integers(2, 6))
+        for k in (-1, 2):
+            rows, pushes, edges = J.base_all_pairs(rpl, cil, ALPHA, thr, k)
+            ptr, tgt, val, st = O.a_base_all_pairs(g, ALPHA, thr, k=k)
+            assert (pushes, edges) == (st["pushes"], st["edges"]), (trial, thr, k)
+            for v in range(n):
+                row = rows.get(v, [])
+                assert [p for _, p in row] == val[ptr[v]:ptr[v + 1]].tolist(), (trial, thr, k, v)
+                assert [t for t, _ in row] == tgt[ptr[v]:ptr[v + 1]].tolist(), (trial, thr, k, v)   # ties keep target order (stable sort)
