@@ -34,11 +34,14 @@ def compute_error(algo, pm, err_type, k):
             return None
         gnd_set = set(int(x) for x in gnd_ids)
         if err_type == PRECISION:
-            hit = sum(1.0 for x in algo_ids if int(x) in gnd_set)
+            hit = float(sum(1 for x in algo_ids if int(x) in gnd_set))
             return hit / float(len(gnd_ids))
         gnd = pm.getTopK(k)
-        zk = sum((math.pow(2.0, gnd[int(v)]) - 1.0) / math.log(i + 1.0) / math.log(2.0) for i, v in enumerate(gnd_ids, 1))
-        dcg = sum((math.pow(2.0, gnd.get(int(v), 0.0)) - 1.0) / math.log(i + 1.0) / math.log(2.0) for i, v in enumerate(algo_ids, 1))
+        zk = dcg = 0.0   # plain left-to-right accumulation as in the Java (Python's sum() compensates and differs in the last bit)
+        for i, v in enumerate(gnd_ids, 1):
+            zk += (math.pow(2.0, gnd[int(v)]) - 1.0) / math.log(i + 1.0) / math.log(2.0)
+        for i, v in enumerate(algo_ids, 1):
+            dcg += (math.pow(2.0, gnd.get(int(v), 0.0)) - 1.0) / math.log(i + 1.0) / math.log(2.0)
         return dcg / zk
     gnd = pm.getWholeGraphPPR()
     est = algo.getWholeGraphPPR()

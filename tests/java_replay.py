@@ -422,3 +422,29 @@ def random_walk(rp, ci, start, alpha, next_double, next_int, no_zero_hop=False, 
             cur = restart                                        # :87-90
         moves += 1
     return cur, moves
+
+
+def compute_error(err_type, gnd_reserve, gnd_topk_ids, gnd_topk, algo_reserve, algo_topk_ids):
+    """J/Gen_Util.java:259-326 on plain dicts / lists: gnd_reserve, algo_reserve = {id: ppr}; gnd_topk = {id: ppr} of the power
+    method's top-k; *_topk_ids = id lists sorted by value (possibly longer than k, ties)."""
+    if err_type == "PRECISION":                                  # :273-281, divided by the ground-truth list length
+        hit = 0.0
+        for v in algo_topk_ids:
+            if v in gnd_topk_ids:
+                hit += 1
+        return hit / float(len(gnd_topk_ids))
+    if err_type == "NDCG":                                       # :283-301
+        zk = dcg = 0.0
+        for i in range(1, len(gnd_topk) + 1):
+            zk += (math.pow(2.0, gnd_topk[gnd_topk_ids[i - 1]]) - 1.0) / math.log(i + 1.0) / math.log(2.0)
+        for i in range(1, len(algo_topk_ids) + 1):
+            p = gnd_topk.get(algo_topk_ids[i - 1])
+            p = 0.0 if p is None else p
+            dcg += (math.pow(2.0, p) - 1.0) / math.log(i + 1.0) / math.log(2.0)
+        return dcg / zk
+    mx = 0.0                                                     # MAX_ERR :308-321: only ground-truth entries are visited
+    for v, real in gnd_reserve.items():
+        est = algo_reserve.get(v)
+        est = 0.0 if est is None else est
+        mx = max(mx, abs(est - real))
+    return mx

@@ -238,3 +238,37 @@ def test_replay_on_random_small_digraphs(O):
                 row = rows.get(v, [])
                 assert [p for _, p in row] == val[ptr[v]:ptr[v + 1]].tolist(), (trial, thr, k, v)
                 assert [t for t, _ in row] == tgt[ptr[v]:ptr[v + 1]].tolist(), (trial, thr, k, v)   # ties keep target order (stable sort)
+
+
+def test_compute_error_replay(O, pkg, g, got):
+    """J/Gen_Util.java:259-326 three ways: the replay, the oracle (orc_topk_metrics / orc_max_err) and the harness' host path."""
+    n = len(got[0]) - 1
+    exact = O.power_method(g, 63, ALPHA)
+    est, _ = O.a_fora(g, 63, ALPHA, EPS, SEED)
+    est[5] += 0.25 if exact[5] == 0 else 0.0                     # an estimate on a vertex the ground truth does not hold is NOT counted
+    for k in (3, 10, 50):
+        gids = O.topk_select(exact, k).tolist()
+        aids = O.topk_select(est, k).tolist()
+        gtop = {v: float(exact[v]) for v in gids}
+        prec = J.compute_error("PRECISION", None, gids, gtop, None, aids)
+        ndcg = J.compute_error("NDCG", None, gids, gtop, None, aids)
+        m = O.topk_metrics(exact, k, aids)
+        assert prec == m["precision"] and ndcg == m["ndcg"]
+
+        class Stub:
+            def __init__(self, dense, ids, top=None):
+                self.dense, self.ids, self.top = dense, ids, top
+            def getTopKNodeIds(self, k):
+                return np.asarray(self.ids, np.int32)
+            def getTopK(self, k):
+                return self.top
+            def getWholeGraphPPR(self):
+                return pkg.algo.PPRVector(self.dense)
+        pm, al = Stub(exact, gids, gtop), Stub(est, aids)
+        assert pkg.compute_error(al, pm, "PRECISION", k) == prec
+        assert pkg.compute_error(al, pm, "NDCG", k) == ndcg
+    gmap = {v: float(exact[v]) for v in range(n) if exact[v] > 0}
+    amap = {v: float(est[v]) for v in range(n) if est[v] > 0}
+    mx = J.compute_error("MAX_ERR", gmap, None, None, amap, None)
+    assert mx == O.max_err(exact, est) == pkg.compute_error(Stub(est, []), Stub(exact, []), "MAX_ERR", -1)
+    assert mx < 0.25
