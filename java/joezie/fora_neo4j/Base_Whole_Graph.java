@@ -31,7 +31,7 @@ public class Base_Whole_Graph extends Gpu_Algo_Base implements Whole_Graph_Util_
     @Override protected void query(Long nodeId_start, Object dummy) { readPreprocessedPPR(nodeId_start); }
 
     @Override public void preprocessing(Double threshold, Object k) {
-        preprocessing_dirName += "/" + threshold;
+        preprocessing_dirName += ("/" + threshold + "_" + k);   // J/Base_Whole_Graph.java:65
         Path dir = Paths.get(preprocessing_dirName);
         try {
             if (Files.isDirectory(dir)) deletePrepDir();
@@ -55,5 +55,11 @@ public class Base_Whole_Graph extends Gpu_Algo_Base implements Whole_Graph_Util_
 
     @Override public void computeTopKPPR(Long nodeId_start, int dummy1, Object dummy2) { readPreprocessedPPR(nodeId_start); }   // rows were cut to top-k at preprocessing time
     @Override public Vector<Long> getTopKNodeIds(int k) { return new Vector<>(ppr_src.keySet()); }
-    @Override public void printTopKResult(int k) { printSorted(ppr_src); }
+    @Override protected String wholeGraphHeader() { return "\nBase-Whole-Graph PPR:"; }
+    @Override protected String topkHeaderPrefix() { return "BASE-Top"; }
+    @Override public void printWholeGraphResult() {   // J/Base_Whole_Graph.java:188-193: stored order, not re-sorted
+        System.out.println(wholeGraphHeader());
+        for (Map.Entry<Long, Double> e : ppr_src.entrySet()) System.out.println("@" + getNodeName(e.getKey(), graphDb) + '\t' + e.getValue());
+    }
+    @Override public void printTopKResult(int k) { printSorted("\n" + topkHeaderPrefix() + k + " PPR:", ppr_src, k); }
 }

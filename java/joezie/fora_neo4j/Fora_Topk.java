@@ -36,5 +36,7 @@ public class Fora_Topk extends Gpu_Algo_Base implements Topk_Util_Interface {
         try { query(nodeId_start, eps); } catch (Throwable t) { t.printStackTrace(); }
     }
     @Override public Vector<Long> getTopKNodeIds(int dummy) { return topk_nodeIds; }
-    @Override public void printTopKResult(int dummy) { printSorted(topk_res); }
+    @Override protected String wholeGraphHeader() { return "Fora-Top" + k + " PPR:"; }
+    @Override protected String topkHeaderPrefix() { return "Fora-Top"; }
+    @Override public void printTopKResult(int dummy) { printSorted("\nFora-Top" + k + " PPR:", topk_res, k); }   // J/Fora_Topk.java:60-79
 }

@@ -18,6 +18,9 @@ public class Fora_Whole_Graph extends Gpu_Algo_Base implements Whole_Graph_Util_
         this.rsum = rsum; this.pfail = pfail; this.delta = delta; this.rel_amount = rel_amount;
     }
 
+    @Override protected String wholeGraphHeader() { return "Fora-Whole-Graph PPR:"; }
+    @Override protected String topkHeaderPrefix() { return "Fora-Whole-Graph-Top"; }   // the reference class has no top-k print
+
     @Override protected void query(Long nodeId_start, Object epsilon) throws Throwable {
         reserve = gpu.fora(nodeId_start, alpha, (Double) epsilon, delta, pfail, seed++);
     }

@@ -1,6 +1,10 @@
 package joezie.fora_neo4j;
 
+import java.util.ArrayList;
+import java.util.Comparator;
 import java.util.HashMap;
+import java.util.List;
+import java.util.Map;
 import java.util.Queue;
 import java.util.concurrent.ConcurrentLinkedQueue;
 
@@ -28,6 +32,17 @@ public class Forward_Push extends Gpu_Algo_Base implements Whole_Graph_Util_Inte
         reserve = out[0];
         residue = out[1];
         rsum = rs[0];
+    }
+
+    @Override protected String wholeGraphHeader() { return "Forward-Push Reserve(pi) & Residue(r):"; }
+    @Override protected String topkHeaderPrefix() { return "Forward-Push-Top"; }
+
+    @Override public void printWholeGraphResult() {   // J/Forward_Push.java:268-281: a third column with the residue
+        List<Map.Entry<Long, Double>> rows = new ArrayList<>(reserve.entrySet());
+        rows.sort(Map.Entry.<Long, Double>comparingByValue(Comparator.reverseOrder()));
+        System.out.println(wholeGraphHeader());
+        for (Map.Entry<Long, Double> e : rows)
+            System.out.println("@" + getNodeName(e.getKey(), graphDb) + '\t' + e.getValue() + '\t' + residue.get(e.getKey()));
     }
 
     public Double getUpdatedRsum() { return rsum; }

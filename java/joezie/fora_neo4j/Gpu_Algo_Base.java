@@ -58,7 +58,12 @@ abstract class Gpu_Algo_Base extends Algo_Util {
 
     public HashMap<Long, Double> getWholeGraphPPR() { return reserve; }
 
-    public void printWholeGraphResult() { printSorted(reserve); }
+    /** first line of printWholeGraphResult, e.g. "Fora-Whole-Graph PPR:" (J/Fora_Whole_Graph.java:65) */
+    protected abstract String wholeGraphHeader();
+    /** "Forward-Push-Top" in "\nForward-Push-Top10 PPR:" (J/Forward_Push.java:384) */
+    protected abstract String topkHeaderPrefix();
+
+    public void printWholeGraphResult() { printSorted(wholeGraphHeader(), reserve, Integer.MAX_VALUE); }
 
     // ---- top-k over the whole-graph result (Forward_Push / Monte_Carlo / Power_Method / Base_Whole_Graph)
     public void computeTopKPPR(Long nodeId_start, int k, Object param) {
@@ -76,12 +81,22 @@ abstract class Gpu_Algo_Base extends Algo_Util {
 
     public Vector<Long> getTopKNodeIds(int k) { return topk_nodeIds; }
 
-    public void printTopKResult(int k) { printSorted(topk_res); }
+    public void printTopKResult(int k) {
+        if (topk_res.isEmpty()) retrieveTopK(k);
+        printSorted("\n" + topkHeaderPrefix() + k + " PPR:", topk_res, k);
+    }
 
-    protected void printSorted(HashMap<Long, Double> res) {
+    /** the print loops of the reference (e.g. J/Forward_Push.java:366-391): value-descending (stable), "@name \t value", at most limit rows */
+    protected void printSorted(String header, Map<Long, Double> res, int limit) {
         List<Map.Entry<Long, Double>> rows = new ArrayList<>(res.entrySet());
         rows.sort(Map.Entry.<Long, Double>comparingByValue(Comparator.reverseOrder()));
-        for (Map.Entry<Long, Double> e : rows) System.out.println(getNodeName(e.getKey(), graphDb) + "\t" + e.getValue());
+        System.out.println(header);
+        int count = 0;
+        for (Map.Entry<Long, Double> e : rows) {
+            if (count >= limit) break;     // ties at the cut may have kept more than k entries
+            count++;
+            System.out.println("@" + getNodeName(e.getKey(), graphDb) + '\t' + e.getValue());
+        }
     }
 
     // ---- result store (Preprocessing_Interface)

@@ -23,6 +23,9 @@ public class Monte_Carlo extends Gpu_Algo_Base implements Whole_Graph_Util_Inter
         reserve = gpu.monteCarlo(nodeId_start, alpha, (Double) epsilon, delta, pfail, seed++);
     }
 
+    @Override protected String wholeGraphHeader() { return "Monte-Carlo PPR:"; }
+    @Override protected String topkHeaderPrefix() { return "Monte-Carlo-Top"; }
+
     public Long random_walk(Long nodeId_start) { return walk(nodeId_start, false); }
     public Long random_walk_no_zero_hop(Long nodeId_start) { return walk(nodeId_start, true); }
 

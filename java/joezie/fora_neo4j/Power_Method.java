@@ -21,5 +21,8 @@ public class Power_Method extends Gpu_Algo_Base implements Whole_Graph_Util_Inte
         reserve = gpu.powerMethod(nodeId_start, alpha, ITERATIONS);
     }
 
+    @Override protected String wholeGraphHeader() { return "Exact-PPR:"; }
+    @Override protected String topkHeaderPrefix() { return "Exact-Top"; }
+
     public HashMap<Long, Double> getTopK(int k) { return topk_res; }
 }

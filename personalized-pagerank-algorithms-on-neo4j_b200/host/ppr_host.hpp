@@ -112,6 +112,35 @@ struct Algo_Util {
         vals.assign(v.begin(), v.begin() + cnt);
         if (kth) *kth = kk;
     }
+    // J/Algo_Util.java:20-30: the node-property column of the export stands for graphDb; an id without a name prints as itself
+    static std::string getNodeName(int64_t nodeId, const Graph& G) {
+        return (nodeId >= 0 && (size_t)nodeId < G.names.size()) ? G.names[(size_t)nodeId] : std::to_string(nodeId);
+    }
+    // The print loops of the reference classes (e.g. J/Forward_Push.java:268-281, :366-391): value-descending (stable, ties keep
+    // ascending id), "@name \t Double.toString(value)", at most `limit` rows; `extra` adds the residue column of Forward_Push.
+    typedef std::vector<std::pair<int64_t, double>> Rows;
+    static Rows rows_of(const std::vector<double>& dense) {
+        Rows r;
+        for (size_t v = 0; v < dense.size(); v++) if (dense[v] > 0) r.emplace_back((int64_t)v, dense[v]);
+        return r;
+    }
+    static Rows rows_of(const std::vector<int64_t>& ids, const std::vector<double>& dense) {
+        Rows r;
+        for (int64_t v : ids) r.emplace_back(v, dense[(size_t)v]);
+        return r;
+    }
+    static void print_rows(const Graph& G, const std::string& header, Rows rows, size_t limit, bool sorted = true, const std::vector<double>* extra = nullptr) {
+        if (sorted) std::stable_sort(rows.begin(), rows.end(), [](const std::pair<int64_t, double>& a, const std::pair<int64_t, double>& b) { return a.second > b.second; });
+        std::printf("%s\n", header.c_str());
+        size_t count = 0;
+        for (const auto& r : rows) {
+            if (count >= limit) break;
+            count++;
+            std::printf("@%s\t%s", getNodeName(r.first, G).c_str(), java_double(r.second).c_str());
+            if (extra) std::printf("\t%s", java_double((*extra)[(size_t)r.first]).c_str());
+            std::printf("\n");
+        }
+    }
     // J/Algo_Util.java:32-50: the k-th largest value; false (Java: null) when k is outside 1..size
     static bool kth_ppr(Graph& G, const std::vector<double>& pprs, int k, double* out) {
         if (k < 1 || (size_t)k > pprs.size()) return false;
@@ -186,6 +215,8 @@ struct Power_Method : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Interface
     }
     const PprMap& getTopK(int) { return topk_res; }
     const std::vector<int64_t>& getTopKNodeIds(int) override { return topk_nodeIds; }
+    void printWholeGraphResult() { print_rows(adjM, "Exact-PPR:", rows_of(reserve), SIZE_MAX); }                                                   // J/Power_Method.java:103-116
+    void printTopKResult(int k) { print_rows(adjM, "\nExact-Top" + std::to_string(k) + " PPR:", rows_of(topk_nodeIds, reserve), (size_t)std::max(k, 0)); }   // :167-184
 };
 
 // J/Forward_Push.java
@@ -212,6 +243,8 @@ struct Forward_Push : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Interface
         if (topk_nodeIds.empty()) { std::vector<double> v; topk(adjM, reserve, k, topk_nodeIds, v, nullptr); }
         return topk_nodeIds;
     }
+    void printWholeGraphResult() { print_rows(adjM, "Forward-Push Reserve(pi) & Residue(r):", rows_of(reserve), SIZE_MAX, true, &residue); }      // J/Forward_Push.java:268-281
+    void printTopKResult(int k) { print_rows(adjM, "\nForward-Push-Top" + std::to_string(k) + " PPR:", rows_of(getTopKNodeIds(k), reserve), (size_t)std::max(k, 0)); }   // :366-391
 };
 
 // J/Monte_Carlo.java
@@ -238,6 +271,8 @@ struct Monte_Carlo : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Interface,
         if (topk_nodeIds.empty()) { std::vector<double> v; topk(adjM, ppr, k, topk_nodeIds, v, nullptr); }
         return topk_nodeIds;
     }
+    void printWholeGraphResult() { print_rows(adjM, "Monte-Carlo PPR:", rows_of(ppr), SIZE_MAX); }                                                 // J/Monte_Carlo.java:160-173
+    void printTopKResult(int k) { print_rows(adjM, "\nMonte-Carlo-Top" + std::to_string(k) + " PPR:", rows_of(getTopKNodeIds(k), ppr), (size_t)std::max(k, 0)); }   // :276-301
 private:
     int64_t one_walk(int64_t start, int nzh) {
         int32_t t = 0;
@@ -263,6 +298,7 @@ struct Fora_Whole_Graph : Algo_Util, Whole_Graph_Util_Interface, Prep_Store {
     }
     const PprMap& getWholeGraphPPR() override { return reserve_map; }
     const std::vector<double>& dense() override { return reserve; }
+    void printWholeGraphResult() { print_rows(adjM, "Fora-Whole-Graph PPR:", rows_of(reserve), SIZE_MAX); }                                        // J/Fora_Whole_Graph.java:55-68
 };
 
 // J/Fora_Topk.java
@@ -281,17 +317,25 @@ struct Fora_Topk : Algo_Util, Topk_Util_Interface {
         topk_vals.resize((size_t)cnt);
     }
     const std::vector<int64_t>& getTopKNodeIds(int) override { return topk_nodeIds; }
+    void printTopKResult(int) {                                                                                                                 // J/Fora_Topk.java:60-79
+        Rows r;
+        for (size_t i = 0; i < topk_nodeIds.size(); i++) r.emplace_back(topk_nodeIds[i], topk_vals[i]);
+        print_rows(adjM, "\nFora-Top" + std::to_string(k) + " PPR:", r, (size_t)std::max(k, 0));
+    }
 };
 
 // J/Backward_Search.java
 struct Backward_Search {
-    Graph& adjM; double alpha, rmax; std::vector<double> reserve;
+    Graph& adjM; double alpha, rmax; std::vector<double> reserve; int64_t duration = 0;
     Backward_Search(double alpha_, double rmax_, Graph& g) : adjM(g), alpha(alpha_), rmax(rmax_) {}
     void backward_search_whole_graph(int64_t t) {
+        const auto t0 = std::chrono::steady_clock::now();
         reserve.assign((size_t)adjM.n, 0.0);
         check(ppr_backward_search(adjM.g, (int32_t)t, alpha, rmax, reserve.data(), nullptr), adjM.ctx);
+        duration += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     }
     PprMap getReserve() const { return to_map(reserve); }
+    int64_t getDuration() const { return duration; }   // J/Backward_Search.java:104-106, nanoseconds
 };
 
 // J/Base_Whole_Graph.java (All-Pair-Backward-Search).  The inverted index stays in memory; the per-source
@@ -324,6 +368,9 @@ struct Base_Whole_Graph : Algo_Util, Whole_Graph_Util_Interface, Topk_Util_Inter
     void computeTopKPPR(int64_t s, int, double) override { computeWholeGraphPPR(s, 0); }
     const std::vector<int64_t>& getTopKNodeIds(int) override { return topk_nodeIds; }   // rows are sorted when preprocessing ran with k >= 0
     void readPreprocessedPPR(int64_t s) { computeWholeGraphPPR(s, 0); }   // J/Base_Whole_Graph.java:200-204
+    Rows stored_row() const { Rows r; for (int64_t t : topk_nodeIds) r.emplace_back(t, ppr_src.at(t)); return r; }
+    void printWholeGraphResult() { print_rows(adjM, "\nBase-Whole-Graph PPR:", stored_row(), SIZE_MAX, false); }                                 // :188-193, stored order
+    void printTopKResult(int k) { print_rows(adjM, "\nBASE-Top" + std::to_string(k) + " PPR:", stored_row(), (size_t)std::max(k, 0)); }          // :219-236
     int64_t getPrepSize() const { return prep_bytes; }
     void deletePrepDir() { src_ptr.clear(); tgt.clear(); val.clear(); prep_bytes = 0; }   // the index lives in memory here (:243-251 clears the directory)
 };

@@ -98,3 +98,37 @@ def test_cpp_host_driver_builds_and_fails_loudly(pkg, tmp_path):
     if not os.path.exists("/dev/nvidia0"):
         r = subprocess.run([exe, "-query", "1", "-db", os.path.join(ROOT, "tests", "golden", "got"), "-out", str(tmp_path)], capture_output=True, text=True)
         assert r.returncode == 1 and "no CPU fallback" in r.stdout
+
+
+def test_cpp_host_print_rows(pkg, tmp_path):
+    """The print loop of the C++ host classes (host/ppr_host.hpp print_rows, J/Forward_Push.java:268-281, :366-391) on hand-made
+    results: same lines as the Python mirror prints (tests/test_api_surface.py).  Host-only code: no device call is made."""
+    import subprocess
+    pdir = os.path.dirname(pkg.__file__)
+    src = tmp_path / "rows.cpp"
+    src.write_text('''
+#include "%s/host/ppr_host.hpp"
+using namespace fora_neo4j;
+int main() {
+    Graph G;
+    G.names = {"Aemon", "Grenn", "Samwell", "Craster"};
+    std::vector<double> reserve = {0.5, 0.0, 0.25, 1e-4}, residue = {0.0, 0.125, 0.0, 2e-5};
+    Algo_Util::print_rows(G, "Forward-Push Reserve(pi) & Residue(r):", Algo_Util::rows_of(reserve), SIZE_MAX, true, &residue);
+    Algo_Util::print_rows(G, "\\nForward-Push-Top2 PPR:", Algo_Util::rows_of(std::vector<int64_t>{0, 2, 3}, reserve), 2);
+    Algo_Util::Rows stored = {{1, 0.125}, {0, 0.5}, {9, 0.5}};
+    Algo_Util::print_rows(G, "\\nBase-Whole-Graph PPR:", stored, SIZE_MAX, false);
+    Algo_Util::print_rows(G, "\\nBASE-Top2 PPR:", stored, 2);
+    return 0;
+}
+''' % pdir)
+    exe = tmp_path / "rows"
+    cc = subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-o", str(exe), str(src), "-L" + pdir, "-lpprb200", "-Wl,-rpath," + pdir],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.splitlines() == [
+        "Forward-Push Reserve(pi) & Residue(r):", "@Aemon\t0.5\t0.0", "@Samwell\t0.25\t0.0", "@Craster\t1.0E-4\t2.0E-5",
+        "", "Forward-Push-Top2 PPR:", "@Aemon\t0.5", "@Samwell\t0.25",
+        "", "Base-Whole-Graph PPR:", "@Grenn\t0.125", "@Aemon\t0.5", "@9\t0.5",
+        "", "BASE-Top2 PPR:", "@Aemon\t0.5", "@9\t0.5"]

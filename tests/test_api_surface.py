@@ -24,11 +24,10 @@ WAIVED = {
     ("PPR", "run"): "body of the anonymous JVM shutdown-hook thread, not a method of PPR",
 }
 CPP_WAIVED = {
-    ("Algo_Util", "getNodeName"), ("PPR", "create_index"), ("PPR", "main"),           # main() lives in host/ppr_main.cpp
+    ("PPR", "create_index"), ("PPR", "main"),                                         # no schema index; main() lives in host/ppr_main.cpp
     ("Gen_Util", "newAlgoObj"), ("Gen_Util", "algo_perf_test"),                       # split into whole_graph_test/topk_test/prep_test
-    ("Backward_Search", "getDuration"),
 }
-CPP_PRINTS = {"printWholeGraphResult", "printTopKResult"}                              # C++ host returns maps; printing is the caller's
+CPP_PRINTS = set()
 JAVA_CLASSES = ["Forward_Push", "Monte_Carlo", "Fora_Whole_Graph", "Fora_Topk", "Backward_Search", "Base_Whole_Graph", "Power_Method"]
 
 
