@@ -2,6 +2,7 @@
 tests/golden/make_api_surface.py) against the three host mirrors of this repo -- the Python classes
 (algo.py / harness.py), the C++ header (host/ppr_host.hpp) and the rewired Java sources (java/).  A user of
 the reference must find every method of the in-scope classes, or an explicit waiver saying where it went."""
+import inspect
 import io
 import json
 import os
@@ -28,6 +29,7 @@ CPP_WAIVED = {
     ("Gen_Util", "newAlgoObj"), ("Gen_Util", "algo_perf_test"),                       # split into whole_graph_test/topk_test/prep_test
 }
 CPP_PRINTS = set()
+PY_ARITY_WAIVED = set()             # none needed: every mirrored method takes the reference's positional arguments
 JAVA_CLASSES = ["Forward_Push", "Monte_Carlo", "Fora_Whole_Graph", "Fora_Topk", "Backward_Search", "Base_Whole_Graph", "Power_Method"]
 
 
@@ -55,6 +57,16 @@ def test_python_mirror_has_every_method(pkg):
         owner = getattr(pkg.harness, cls, None) or getattr(pkg.algo, cls, None)
         if owner is None or not callable(getattr(owner, name, None)):
             missing.append((cls, name, where))
+            continue
+        # the method must take the reference's argument count positionally (extra optional arguments are fine)
+        params = [p for p in inspect.signature(getattr(owner, name)).parameters.values() if p.name != "self"]
+        required = sum(1 for p in params if p.default is p.empty and p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD))
+        varargs = any(p.kind == p.VAR_POSITIONAL for p in params)
+        positional = sum(1 for p in params if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD))
+        if (cls, name) in PY_ARITY_WAIVED:
+            continue
+        if required > nargs or (positional < nargs and not varargs):
+            missing.append((cls, name, where, "arity %d, reference %d" % (positional, nargs)))
     assert not missing, missing
 
 
