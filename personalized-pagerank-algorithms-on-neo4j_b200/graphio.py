@@ -59,6 +59,52 @@ def load_neo4j_csv(nodes_csv, rels_csv):
     return row_ptr, col_idx, names
 
 
+def load_edge_list(path, undirected=False, delimiter=None, comments="#%"):
+    """Plain edge-list text (SNAP `ca-GrQc.txt` / `com-amazon.ungraph.txt` style: `# comment` lines, one `src dst` pair per
+    line, whitespace- or `delimiter`-separated; BlogCatalog / Flickr `edges.csv` with delimiter=",") -- the form in which the
+    dissertation's datasets are distributed before `neo4j-admin import` (Dissertation p.36-37).
+
+    Node ids are relabelled to 0..n-1 in ascending order of the original id (the order `neo4j-admin import` assigns node ids
+    for a nodes file sorted by id); `undirected=True` stores both directions of every pair, which is how the dissertation
+    loads its (undirected) datasets.  Returns (row_ptr, col_idx, original_ids)."""
+    src, dst = [], []
+    with open(path, encoding="utf-8-sig") as f:
+        for line in f:
+            line = line.strip()
+            if not line or line[0] in comments:
+                continue
+            parts = line.split(delimiter)
+            if len(parts) < 2:
+                raise ValueError("not an edge: %r in %s" % (line, path))
+            src.append(int(parts[0]))
+            dst.append(int(parts[1]))
+    src, dst = np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)
+    original_ids, inv = np.unique(np.concatenate([src, dst]), return_inverse=True)
+    s, d = inv[:src.size], inv[src.size:]
+    if undirected:
+        loops = s == d                                              # a self-loop is one relationship, not two
+        s, d = np.concatenate([s, d[~loops]]), np.concatenate([d, s[~loops]])
+    row_ptr, col_idx = csr_from_edges(original_ids.size, s, d)
+    return row_ptr, col_idx, original_ids
+
+
+def write_neo4j_csv(row_ptr, col_idx, nodes_csv, rels_csv, names=None, rel_type="Relation"):
+    """The inverse of load_neo4j_csv: `:ID,name` / `:START_ID,:END_ID,:TYPE` files for `neo4j-admin import`
+    (the step the reference's README describes for building `target/got.db`)."""
+    n = len(row_ptr) - 1
+    with open(nodes_csv, "w", newline="", encoding="utf-8") as f:
+        w = csv.writer(f)
+        w.writerow([":ID", "name"])
+        for v in range(n):
+            w.writerow([v, names[v] if names is not None else v])
+    with open(rels_csv, "w", newline="", encoding="utf-8") as f:
+        w = csv.writer(f)
+        w.writerow([":START_ID", ":END_ID", ":TYPE"])
+        for v in range(n):
+            for e in range(int(row_ptr[v]), int(row_ptr[v + 1])):
+                w.writerow([v, int(col_idx[e]), rel_type])
+
+
 NODE_RECORD, REL_RECORD = 15, 34   # Neo4j 3.x "standard" record format
 
 

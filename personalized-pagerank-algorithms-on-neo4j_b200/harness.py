@@ -252,6 +252,10 @@ class PPR(Gen_Util):
             self.names = [str(i) for i in self.original_ids]
         elif nodes and rels:
             row_ptr, col_idx, self.names = graphio.load_neo4j_csv(nodes[0], rels[0])
+        elif os.path.isfile(self.db_path):                                        # a plain edge list (SNAP text / edges.csv)
+            row_ptr, col_idx, self.original_ids = graphio.load_edge_list(
+                self.db_path, undirected=getattr(self, "undirected", False), delimiter="," if self.db_path.endswith(".csv") else None)
+            self.names = [str(i) for i in self.original_ids]
         else:
             raise FileNotFoundError("neither a Neo4j store nor *_Nodes.csv / *_Rels.csv under %s" % self.db_path)
         self.adjM = N.Graph(self.ctx, row_ptr, col_idx)
@@ -282,8 +286,10 @@ def main(argv=None):
     ap.add_argument("-help", "--help", action="help")
     ap.add_argument("--tests", default="1,2,3", help="subset of the three harness tests to run")
     ap.add_argument("--out", default=".")
+    ap.add_argument("--undirected", action="store_true", help="-db names a plain edge-list file: store both directions of every pair")
     a = ap.parse_args(argv)
     t = PPR()
+    t.undirected = a.undirected
     try:
         t.createDb(a.db_dir)
         t.setupAdjMatrix()

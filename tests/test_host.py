@@ -150,3 +150,23 @@ def test_bench_reference_arm_contract(pkg):
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert line["config"]["workload"].startswith("R-MAT scale-12") and line["config"]["l2"].startswith("inputs fit the L2")
     assert line["oracle_pinned"] is False
+
+
+def test_edge_list_loader_and_csv_writer(pkg, tmp_path):
+    """SNAP-style edge list -> CSR (ids relabelled in ascending order), undirected doubling, and the neo4j-admin CSV round trip."""
+    (tmp_path / "g.txt").write_text("# Directed graph\n# FromNodeId\tToNodeId\n30\t10\n10\t20\n30\t20\n30\t10\n20\t20\n")
+    rp, ci, ids = pkg.graphio.load_edge_list(str(tmp_path / "g.txt"))
+    assert list(ids) == [10, 20, 30]
+    assert list(rp) == [0, 1, 2, 5] and list(ci) == [1, 1, 0, 0, 1]           # parallel edge and self-loop kept
+    rp, ci, ids = pkg.graphio.load_edge_list(str(tmp_path / "g.txt"), undirected=True)
+    assert list(rp) == [0, 3, 6, 9] and list(ci) == [1, 2, 2, 0, 1, 2, 0, 0, 1]  # both directions; the self-loop stored once
+    (tmp_path / "e.csv").write_text("1,2\n2,3\n")
+    rp, ci, ids = pkg.graphio.load_edge_list(str(tmp_path / "e.csv"), delimiter=",")
+    assert list(rp) == [0, 1, 2, 2] and list(ci) == [1, 2] and list(ids) == [1, 2, 3]
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.txt").write_text("7\n")
+        pkg.graphio.load_edge_list(str(tmp_path / "bad.txt"))
+    grp, gci, names = pkg.graphio.load_got()
+    pkg.graphio.write_neo4j_csv(grp, gci, str(tmp_path / "N.csv"), str(tmp_path / "R.csv"), names)
+    rp2, ci2, names2 = pkg.graphio.load_neo4j_csv(str(tmp_path / "N.csv"), str(tmp_path / "R.csv"))
+    assert np.array_equal(rp2, grp) and np.array_equal(ci2, gci) and names2 == list(names)
