@@ -559,9 +559,9 @@ struct PPR : Gen_Util {
         if (adjM.ctx) { ppr_shutdown(adjM.ctx); adjM.ctx = nullptr; }
     }
     // J/PPR.java:136-152: one-time export (here from the Neo4j import CSVs: `:ID,name` / `:START_ID,:END_ID,:TYPE`)
-    void setupAdjMatrix(const std::string& nodes_csv, const std::string& rels_csv) {
-        printf("\nLoading graph from database...\n");
-        int64_t t0 = now_ns();
+    typedef std::vector<std::pair<int64_t, int64_t>> EdgeList;
+    // `neo4j-admin import` CSV pair (":ID,name" / ":START_ID,:END_ID,:TYPE"): mapped id = row of the nodes file
+    static void read_import_csv(const std::string& nodes_csv, const std::string& rels_csv, std::vector<std::string>& names, EdgeList& edges) {
         std::ifstream fn(nodes_csv), fr(rels_csv);
         if (!fn || !fr) throw std::runtime_error("cannot open " + nodes_csv + " / " + rels_csv);
         std::string line;
@@ -571,10 +571,9 @@ struct PPR : Gen_Util {
             if (!line.empty() && line.back() == '\r') line.pop_back();
             if (line.empty()) continue;
             std::string id = line.substr(0, line.find(','));
-            index.emplace(id, (int64_t)adjM.names.size());
-            adjM.names.push_back(line.substr(line.find(',') + 1));
+            index.emplace(id, (int64_t)names.size());
+            names.push_back(line.substr(line.find(',') + 1));
         }
-        std::vector<std::pair<int64_t, int64_t>> edges;
         std::getline(fr, line);
         while (std::getline(fr, line)) {
             if (!line.empty() && line.back() == '\r') line.pop_back();
@@ -583,6 +582,34 @@ struct PPR : Gen_Util {
             std::getline(ss, a, ','); std::getline(ss, b, ',');
             edges.emplace_back(index.at(a), index.at(b));
         }
+    }
+    // A Neo4j 3.x store directory (the reference's own -db argument, e.g. target/got.db), read without a JVM:
+    // neostore.nodestore.db = 15-byte records, bit 0 of byte 0 = in use, node id = record index;
+    // neostore.relationshipstore.db = 34-byte records, byte 0 = in-use bit + bits 32-34 of the first node, bytes 1-4 / 5-8 = low 32 bits
+    // of the first / second node (big endian), bytes 9-12 = type int whose bits 28-30 carry bits 32-34 of the second node.
+    // Mapped id = rank of the Neo4j id among the ids in use (the IdMap of Graph.toMappedNodeId); names = the Neo4j ids.
+    static void read_neo4j_store(const std::string& db_dir, std::vector<std::string>& names, EdgeList& edges) {
+        auto slurp = [](const std::string& path) {
+            std::ifstream f(path, std::ios::binary);
+            if (!f) throw std::runtime_error("cannot open " + path);
+            return std::vector<unsigned char>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        };
+        const std::vector<unsigned char> nodes = slurp(db_dir + "/neostore.nodestore.db"), rels = slurp(db_dir + "/neostore.relationshipstore.db");
+        std::vector<int64_t> mapped(nodes.size() / 15, -1);
+        for (size_t i = 0; i < mapped.size(); i++)
+            if (nodes[i * 15] & 1) { mapped[i] = (int64_t)names.size(); names.push_back(std::to_string(i)); }
+        auto be32 = [](const unsigned char* b) { return ((int64_t)b[0] << 24) | ((int64_t)b[1] << 16) | ((int64_t)b[2] << 8) | (int64_t)b[3]; };
+        for (size_t r = 0; r + 34 <= rels.size(); r += 34) {
+            const unsigned char* b = &rels[r];
+            if (!(b[0] & 1)) continue;
+            const int64_t first = be32(b + 1) | ((int64_t)((b[0] & 0x0E) >> 1) << 32);
+            const int64_t second = be32(b + 5) | ((be32(b + 9) & 0x70000000LL) << 4);
+            if (first < 0 || second < 0 || (size_t)first >= mapped.size() || (size_t)second >= mapped.size() || mapped[(size_t)first] < 0 || mapped[(size_t)second] < 0)
+                throw std::runtime_error("relationship store references a node that is not in use");
+            edges.emplace_back(mapped[(size_t)first], mapped[(size_t)second]);
+        }
+    }
+    void build_graph(EdgeList& edges, int64_t t0) {
         std::sort(edges.begin(), edges.end());   // canonical order: ascending target inside a row, duplicates kept
         adjM.n = (int64_t)adjM.names.size(); adjM.m = (int64_t)edges.size();
         adjM.row_ptr.assign((size_t)adjM.n + 1, 0);
@@ -592,6 +619,21 @@ struct PPR : Gen_Util {
         for (size_t i = 0; i < edges.size(); i++) col[i] = (int32_t)edges[i].second;
         check(ppr_graph_create(adjM.ctx, adjM.n, adjM.m, adjM.row_ptr.data(), col.data(), &adjM.g), adjM.ctx);
         printf("\nFinish graph loading in %lld(ms)\n", (long long)((now_ns() - t0) / 1000000));
+    }
+    // J/PPR.java:136-152: one-time export of the topology to the device
+    void setupAdjMatrix(const std::string& nodes_csv, const std::string& rels_csv) {
+        printf("\nLoading graph from database...\n");
+        int64_t t0 = now_ns();
+        EdgeList edges;
+        read_import_csv(nodes_csv, rels_csv, adjM.names, edges);
+        build_graph(edges, t0);
+    }
+    void setupAdjMatrix(const std::string& neo4j_store_dir) {
+        printf("\nLoading graph from database...\n");
+        int64_t t0 = now_ns();
+        EdgeList edges;
+        read_neo4j_store(neo4j_store_dir, adjM.names, edges);
+        build_graph(edges, t0);
     }
     void set_configuration(double a, double e, const std::string& np, const std::string& lt, const std::string& rt) {
         alpha = a; epsilon = e; node_property = np; label_type = lt; rel_type = rt;

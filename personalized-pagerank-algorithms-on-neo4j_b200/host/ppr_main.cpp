@@ -1,6 +1,7 @@
 // ppr_main.cpp -- `PPR`, the reference's command-line driver (J/PPR.java:154-200), over libpprb200.so.
 // Same options and defaults: -alpha 0.15 -eps 0.5 -query 50 -k 10 -node name -label Person -rel Relation -db <dir> -help.
-// -db names a directory with the Neo4j import CSVs (*_Nodes.csv, *_Rels.csv); -out is where
+// -db names a Neo4j 3.x store directory (target/got.db: nodestore / relationshipstore records are read natively, no JVM) or a
+// directory with the Neo4j import CSVs (*_Nodes.csv, *_Rels.csv); -out is where
 // <db>_AlgoPerfResults.txt is appended (default: current directory).
 #include <dirent.h>
 
@@ -18,7 +19,7 @@ static std::string find_csv(const std::string& dir, const char* suffix) {
         if (f.size() >= strlen(suffix) && f.compare(f.size() - strlen(suffix), strlen(suffix), suffix) == 0 && (best.empty() || f < best)) best = f;
     }
     closedir(d);
-    if (best.empty()) throw std::runtime_error(std::string("no *") + suffix + " under " + dir + " (a Neo4j store needs a JVM to open)");
+    if (best.empty()) throw std::runtime_error(std::string("no *") + suffix + " and no neostore.nodestore.db under " + dir);
     return dir + "/" + best;
 }
 
@@ -32,7 +33,7 @@ int main(int argc, char** argv) {
         if (a == "-help" || a == "--help") {
             printf("usage: PPR\n -alpha <arg>  The possibility that a random walk stops at current node (Default: 0.15)\n -eps <arg>    The relative error bound (Default: 0.5)\n"
                    " -query <arg>  The number of queries for the test (Default: 50)\n -k <arg>      For Top-k Algorithm tests (Default: 10)\n -node <arg>   The node property (Default: \"name\")\n"
-                   " -label <arg>  The nodes' label type (Default: \"Person\")\n -rel <arg>    The relationships' type (Default: \"Relation\")\n -db <arg>     The directory of the input database CSVs\n -help\n");
+                   " -label <arg>  The nodes' label type (Default: \"Person\")\n -rel <arg>    The relationships' type (Default: \"Relation\")\n -db <arg>     The directory of the input database (Neo4j store or import CSVs)\n -help\n");
             return 0;
         } else if (a == "-alpha" || a == "--alpha") alpha = std::stod(val());
         else if (a == "-eps" || a == "--epsilon") eps = std::stod(val());
@@ -48,7 +49,8 @@ int main(int argc, char** argv) {
     fora_neo4j::PPR t;
     try {
         t.createDb(db);
-        t.setupAdjMatrix(find_csv(db, "Nodes.csv"), find_csv(db, "Rels.csv"));
+        if (std::ifstream(db + "/neostore.nodestore.db").good()) t.setupAdjMatrix(db);   // a Neo4j 3.x store directory (the reference's -db), read natively
+        else t.setupAdjMatrix(find_csv(db, "Nodes.csv"), find_csv(db, "Rels.csv"));
         t.set_configuration(alpha, eps, node, label, rel);
         printf("\nCreating index ...\nIndex created\n");
         t.algo_perf_batch_test(query, k, out);

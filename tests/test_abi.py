@@ -132,3 +132,36 @@ int main() {
         "", "Forward-Push-Top2 PPR:", "@Aemon\t0.5", "@Samwell\t0.25",
         "", "Base-Whole-Graph PPR:", "@Grenn\t0.125", "@Aemon\t0.5", "@9\t0.5",
         "", "BASE-Top2 PPR:", "@Aemon\t0.5", "@9\t0.5"]
+
+
+def test_cpp_host_reads_the_neo4j_store(pkg, tmp_path):
+    """host/ppr_host.hpp read_neo4j_store (15-/34-byte records) against read_import_csv on the GOT fixtures: the reference's own
+    `-db target/got.db` argument works in the compiled driver without a JVM.  Host-only: no device call is made."""
+    import subprocess
+    pdir = os.path.dirname(pkg.__file__)
+    src = tmp_path / "store.cpp"
+    src.write_text('''
+#include "%s/host/ppr_host.hpp"
+using namespace fora_neo4j;
+int main(int argc, char** argv) {
+    std::vector<std::string> n1, n2;
+    PPR::EdgeList e1, e2;
+    PPR::read_neo4j_store(argv[1], n1, e1);
+    PPR::read_import_csv(argv[2], argv[3], n2, e2);
+    std::printf("%%zu %%zu %%zu %%zu %%d\\n", n1.size(), e1.size(), n2.size(), e2.size(), (int)(e1 == e2));
+    std::printf("%%s %%s %%lld %%lld\\n", n1.front().c_str(), n2.front().c_str(), (long long)e1.front().first, (long long)e1.front().second);
+    return 0;
+}
+''' % pdir)
+    exe = tmp_path / "store"
+    cc = subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-o", str(exe), str(src), "-L" + pdir, "-lpprb200", "-Wl,-rpath," + pdir],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    g = os.path.join(ROOT, "tests", "golden")
+    out = subprocess.run([str(exe), os.path.join(g, "got.db"), os.path.join(g, "got", "GOT_Nodes.csv"), os.path.join(g, "got", "GOT_Rels.csv")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    assert lines[0] == "107 352 107 352 1"                  # same relationships in the same (relationship id = CSV row) order: SURVEY F10
+    rp, ci, ids = pkg.graphio.load_neo4j_store(os.path.join(g, "got.db"))
+    assert lines[1].split()[0] == str(int(ids[0]))
